@@ -1,0 +1,72 @@
+"""ctypes binding of libsduss_b200.so (the C ABI declared in include/sduss_b200.h).
+
+There is no fallback: if the library is missing the import of any product module raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsduss_b200.so")
+
+OK = 0
+ERR_INVALID = 10001
+ERR_DRIVER = 10002
+ERR_UNSUPPORTED = 10003
+
+c_int = ctypes.c_int
+c_float = ctypes.c_float
+c_void_p = ctypes.c_void_p
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+
+
+class EpilogueDesc(ctypes.Structure):
+    """Mirror of B200EpilogueDesc (include/sduss_b200.h)."""
+    _fields_ = [
+        ("C", c_void_p), ("ldc", ctypes.c_int32), ("out_fp32", ctypes.c_int32),
+        ("bias", c_void_p),
+        ("resid", c_void_p), ("ldr", ctypes.c_int32),
+        ("gate", c_void_p), ("ldg", ctypes.c_int32),
+        ("row_group", c_void_p),
+        ("rowvec", c_void_p), ("ldv", ctypes.c_int32),
+        ("rms_wq", c_void_p), ("rms_wk", c_void_p),
+        ("rms_q_cols", ctypes.c_int32), ("rms_k_cols", ctypes.c_int32),
+        ("rms_eps", c_float), ("q_scale", c_float),
+    ]
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m sduss_b200.build` "
+            "(nvcc, sm_100a). sduss_b200 has no CPU or PyTorch fallback.")
+    return ctypes.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+# name -> argtypes; every function returns int status.
+SIGNATURES = {
+    "b200_version": [],
+    "b200_sm_count": [],
+    "b200_gemm_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                       ctypes.POINTER(EpilogueDesc), c_void_p],
+}
+
+
+def _bind():
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
+
+
+_bind()
+
+
+def check(status, what):
+    if status != OK:
+        raise B200Error(f"{what} failed with status {status}")

@@ -1,0 +1,181 @@
+// Fused epilogues shared by the tcgen05 GEMM and implicit-GEMM convolution kernels.
+// One epilogue thread owns one accumulator row (TMEM lane) and walks it in chunks of 64
+// fp32 columns, so per-row reductions (q/k RMSNorm over a 64-wide head) are thread-local.
+#pragma once
+#include "ptx.cuh"
+
+namespace b200 {
+
+enum EpiMode : int {
+  EPI_BIAS = 0,        // C = acc + bias
+  EPI_GELU_TANH = 1,   // C = gelu_tanh(acc + bias)                       (SD3 FeedForward)
+  EPI_GATE_RESID = 2,  // C = resid + gate[group[row]] * (acc + bias)     (gate null -> 1)
+  EPI_QK_RMSNORM = 3,  // per 64-col head: q,k column ranges RMS-normalised, v passthrough
+  EPI_GEGLU = 4,       // weights interleaved [32 h | 32 g]: C[:, n/2] = h * gelu_erf(g)
+  EPI_ROWVEC = 5,      // C = acc + bias + rowvec[group[row]]            (resnet conv1 + temb)
+};
+
+struct EpiArgs {
+  void* C;              // bf16 (or fp32 when out_fp32) [M, ldc]
+  int ldc;
+  int out_fp32;
+  const __nv_bfloat16* bias;   // [N] or null
+  const __nv_bfloat16* resid;  // [M, ldr] or null (may alias C)
+  int ldr;
+  const __nv_bfloat16* gate;   // [G, ldg] or null
+  int ldg;
+  const int* row_group;        // [M] group (request/latent) id of each row, or null
+  const __nv_bfloat16* rowvec; // [G, ldv]
+  int ldv;
+  const __nv_bfloat16* rms_wq; // [64]
+  const __nv_bfloat16* rms_wk; // [64]
+  int rms_q_cols;              // columns [0, q_cols) are q heads
+  int rms_k_cols;              // columns [q_cols, q_cols + k_cols) are k heads
+  float rms_eps;
+  float q_scale;               // multiplied into normalised q (softmax scale * log2 e)
+};
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float u = k0 * (x + k1 * x * x * x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return 0.5f * x * (1.f + t);
+}
+__device__ __forceinline__ float gelu_erf_f(float x) {
+  return 0.5f * x * (1.f + erff(x * 0.7071067811865476f));
+}
+
+__device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float* out) {
+  uint4 v = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    out[2 * i] = f.x;
+    out[2 * i + 1] = f.y;
+  }
+}
+
+// acc: 64 fp32 accumulator columns of one row; n0 = first global column of this chunk.
+// Writes the finished chunk to global memory. N is the logical GEMM N (pre-GEGLU halving).
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk64(const EpiArgs& e, float* acc, int row, int n0,
+                                                 int M, int N) {
+  if (row >= M || n0 >= N) return;
+  const int ncols = min(64, N - n0);  // multiple of 8 by contract
+  if (e.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 64; j += 8) {
+      if (j < ncols) {
+        float b[8];
+        load8_bf16(e.bias + n0 + j, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j + i] += b[i];
+      }
+    }
+  }
+  if constexpr (EPI == EPI_GELU_TANH) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[j] = gelu_tanh_f(acc[j]);
+  }
+  if constexpr (EPI == EPI_ROWVEC) {
+    const int g = e.row_group[row];
+    const __nv_bfloat16* v = e.rowvec + size_t(g) * e.ldv + n0;
+#pragma unroll
+    for (int j = 0; j < 64; j += 8) {
+      if (j < ncols) {
+        float b[8];
+        load8_bf16(v + j, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j + i] += b[i];
+      }
+    }
+  }
+  if constexpr (EPI == EPI_GATE_RESID) {
+    if (e.gate != nullptr) {
+      const int g = e.row_group[row];
+      const __nv_bfloat16* gp = e.gate + size_t(g) * e.ldg + n0;
+#pragma unroll
+      for (int j = 0; j < 64; j += 8) {
+        if (j < ncols) {
+          float b[8];
+          load8_bf16(gp + j, b);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[j + i] *= b[i];
+        }
+      }
+    }
+    if (e.resid != nullptr) {
+      const __nv_bfloat16* rp = e.resid + size_t(row) * e.ldr + n0;
+#pragma unroll
+      for (int j = 0; j < 64; j += 8) {
+        if (j < ncols) {
+          float b[8];
+          load8_bf16(rp + j, b);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[j + i] += b[i];
+        }
+      }
+    }
+  }
+  if constexpr (EPI == EPI_QK_RMSNORM) {
+    // n0 is 64-aligned, so a chunk is exactly one head.
+    const bool is_q = n0 < e.rms_q_cols;
+    const bool is_k = !is_q && n0 < e.rms_q_cols + e.rms_k_cols;
+    if (is_q || is_k) {
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) ss += acc[j] * acc[j];
+      float r = rsqrtf(ss * (1.f / 64.f) + e.rms_eps);
+      if (is_q) r *= e.q_scale;
+      const __nv_bfloat16* w = is_q ? e.rms_wq : e.rms_wk;
+#pragma unroll
+      for (int j = 0; j < 64; j += 8) {
+        float b[8];
+        load8_bf16(w + j, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j + i] = acc[j + i] * r * b[i];
+      }
+    }
+  }
+  if constexpr (EPI == EPI_GEGLU) {
+    // chunk = [32 hidden | 32 gate] -> 32 output columns at n0/2
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = acc[j] * gelu_erf_f(acc[32 + j]);
+    __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(e.C) + size_t(row) * e.ldc + (n0 >> 1);
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      uint4 v;
+      v.x = pack_bf16x2(acc[j], acc[j + 1]);
+      v.y = pack_bf16x2(acc[j + 2], acc[j + 3]);
+      v.z = pack_bf16x2(acc[j + 4], acc[j + 5]);
+      v.w = pack_bf16x2(acc[j + 6], acc[j + 7]);
+      *reinterpret_cast<uint4*>(cp + j) = v;
+    }
+    return;
+  }
+  if (e.out_fp32) {
+    float* cp = reinterpret_cast<float*>(e.C) + size_t(row) * e.ldc + n0;
+#pragma unroll
+    for (int j = 0; j < 64; j += 4) {
+      if (j < ncols)
+        *reinterpret_cast<float4*>(cp + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+    }
+  } else {
+    __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(e.C) + size_t(row) * e.ldc + n0;
+#pragma unroll
+    for (int j = 0; j < 64; j += 8) {
+      if (j < ncols) {
+        uint4 v;
+        v.x = pack_bf16x2(acc[j], acc[j + 1]);
+        v.y = pack_bf16x2(acc[j + 2], acc[j + 3]);
+        v.z = pack_bf16x2(acc[j + 4], acc[j + 5]);
+        v.w = pack_bf16x2(acc[j + 6], acc[j + 7]);
+        *reinterpret_cast<uint4*>(cp + j) = v;
+      }
+    }
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,265 @@
+// C[M,N] = epilogue(A[M,K] * W[N,K]^T) in bf16 with fp32 accumulation on the sm_100a tensor
+// cores. Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer,
+// warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers -> fused epilogue -> HBM).
+// Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the main loop
+// of tile i+1. Replaces the F.linear call sites of the reference's denoising step
+// (sduss/model_executor/modules/resnet.py:163, attention.py:73-96,259-274,411 and the
+// diffusers FeedForward / AdaLayerNorm linears they wrap).
+#include "../../include/sduss_b200.h"
+#include "epilogue.cuh"
+#include "host_util.h"
+
+namespace b200 {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 256;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (256 or 512)
+};
+
+struct GemmShape {
+  int M, N, K;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 GemmShape s, EpiArgs e) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* smemA = smem;
+  uint8_t* smemB = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;                       // [kStages]
+  uint64_t* empty = bars + Cfg::kStages;       // [kStages]
+  uint64_t* tfull = bars + 2 * Cfg::kStages;   // [2]
+  uint64_t* tempty = tfull + 2;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_m = (s.M + BM - 1) / BM;
+  const int tiles_n = (s.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (s.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m0 = (t / tiles_n) * BM;
+      const int n0 = (t % tiles_n) * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (lane == 0) {
+          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+          tma_load_2d(smemA + stage * Cfg::kABytes, &tmA, &full[stage], kb * BK, m0);
+          tma_load_2d(smemB + stage * Cfg::kBBytes, &tmB, &full[stage], kb * BK, n0);
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t da = make_sdesc_sw128(smem_u32(smemA + stage * Cfg::kABytes));
+          const uint64_t db = make_sdesc_sw128(smem_u32(smemB + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 bytes (encoded >>4) per 16-element K step inside the 128B swizzle span
+            umma_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc,
+                    (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (kb == num_kb - 1) umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int m0 = (t / tiles_n) * BM;
+      const int n0 = (t % tiles_n) * BN;
+      mbar_wait(&tfull[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        float v[64];
+        tmem_ld32(t_row + c * 64, reinterpret_cast<uint32_t*>(v));
+        tmem_ld32(t_row + c * 64 + 32, reinterpret_cast<uint32_t*>(v) + 32);
+        tmem_wait_ld();
+        epilogue_chunk64<EPI>(e, v, row, n0 + c * 64, s.M, s.N);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN, int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmShape s,
+                       const EpiArgs& e, int num_sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_kernel<BN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t err =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (err != cudaSuccess) return static_cast<int>(err);
+    configured = true;
+  }
+  const int tiles = ((s.M + BM - 1) / BM) * ((s.N + BN - 1) / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(tmA, tmB, s, e);
+  return launch_status();
+}
+
+template <int BN>
+static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmShape s,
+                        const EpiArgs& e, int num_sms, cudaStream_t stream) {
+  switch (epi) {
+    case EPI_BIAS: return launch_gemm<BN, EPI_BIAS>(tmA, tmB, s, e, num_sms, stream);
+    case EPI_GELU_TANH: return launch_gemm<BN, EPI_GELU_TANH>(tmA, tmB, s, e, num_sms, stream);
+    case EPI_GATE_RESID: return launch_gemm<BN, EPI_GATE_RESID>(tmA, tmB, s, e, num_sms, stream);
+    case EPI_QK_RMSNORM: return launch_gemm<BN, EPI_QK_RMSNORM>(tmA, tmB, s, e, num_sms, stream);
+    case EPI_GEGLU: return launch_gemm<BN, EPI_GEGLU>(tmA, tmB, s, e, num_sms, stream);
+    case EPI_ROWVEC: return launch_gemm<BN, EPI_ROWVEC>(tmA, tmB, s, e, num_sms, stream);
+    default: return B200_ERR_INVALID;
+  }
+}
+
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 0;
+  }
+  return sms;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// See include/sduss_b200.h for the contract.
+extern "C" int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+                              int epi_mode, const B200EpilogueDesc* ep, void* stream_) {
+  if (!A || !W || !ep || !ep->C || M <= 0 || N <= 0 || K <= 0) return B200_ERR_INVALID;
+  if ((N & 7) || (K & 7) || (lda & 7) || (ldw & 7) || (ep->ldc & 7)) return B200_ERR_INVALID;
+  if (epi_mode == EPI_QK_RMSNORM && ((N & 63) || !ep->rms_wq || !ep->rms_wk)) return B200_ERR_INVALID;
+  if (epi_mode == EPI_GEGLU && (N & 63)) return B200_ERR_INVALID;
+  if ((epi_mode == EPI_ROWVEC && (!ep->rowvec || !ep->row_group)) ||
+      (epi_mode == EPI_GATE_RESID && ep->gate && !ep->row_group))
+    return B200_ERR_INVALID;
+  const int sms = device_sm_count();
+  if (sms <= 0) return B200_ERR_DRIVER;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+
+  // Small-N problems (and ones whose 256-wide tiling leaves most SMs idle) use 128-wide tiles.
+  const long tiles256 = long((M + BM - 1) / BM) * ((N + 255) / 256);
+  const bool bn256 = (N >= 256) && (tiles256 >= sms);
+  const int BN = bn256 ? 256 : 128;
+
+  CUtensorMap tmA, tmB;
+  uint64_t dA[2] = {uint64_t(K), uint64_t(M)}, sA[1] = {uint64_t(lda) * 2};
+  uint32_t bA[2] = {BK, BM};
+  int rc = get_tmap_bf16_sw128(&tmA, A, 2, dA, sA, bA);
+  if (rc) return rc;
+  uint64_t dB[2] = {uint64_t(K), uint64_t(N)}, sB[1] = {uint64_t(ldw) * 2};
+  uint32_t bB[2] = {BK, uint32_t(BN)};
+  rc = get_tmap_bf16_sw128(&tmB, W, 2, dB, sB, bB);
+  if (rc) return rc;
+
+  EpiArgs e;
+  e.C = ep->C;
+  e.ldc = ep->ldc;
+  e.out_fp32 = ep->out_fp32;
+  e.bias = static_cast<const __nv_bfloat16*>(ep->bias);
+  e.resid = static_cast<const __nv_bfloat16*>(ep->resid);
+  e.ldr = ep->ldr;
+  e.gate = static_cast<const __nv_bfloat16*>(ep->gate);
+  e.ldg = ep->ldg;
+  e.row_group = ep->row_group;
+  e.rowvec = static_cast<const __nv_bfloat16*>(ep->rowvec);
+  e.ldv = ep->ldv;
+  e.rms_wq = static_cast<const __nv_bfloat16*>(ep->rms_wq);
+  e.rms_wk = static_cast<const __nv_bfloat16*>(ep->rms_wk);
+  e.rms_q_cols = ep->rms_q_cols;
+  e.rms_k_cols = ep->rms_k_cols;
+  e.rms_eps = ep->rms_eps;
+  e.q_scale = ep->q_scale;
+  GemmShape s{M, N, K};
+  return bn256 ? dispatch_epi<256>(epi_mode, tmA, tmB, s, e, sms, stream)
+               : dispatch_epi<128>(epi_mode, tmA, tmB, s, e, sms, stream);
+}

@@ -1,0 +1,24 @@
+"""Micro-benchmark of the tcgen05 GEMM vs torch.matmul (cuBLAS) on the hot-path shapes."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from sduss_b200 import ops
+
+def timeit(fn, n=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(n): fn()
+    e.record(); torch.cuda.synchronize()
+    return s.elapsed_time(e) / n
+
+dev = torch.device("cuda")
+for (M, N, K) in [(14848, 4608, 1536), (14848, 1536, 1536), (14848, 6144, 1536), (14848, 1536, 6144),
+                  (1998, 4608, 1536), (40960, 320, 2880), (8192, 8192, 8192)]:
+    a = torch.randn(M, K, device=dev).bfloat16(); w = (torch.randn(N, K, device=dev) * .05).bfloat16()
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    t1 = timeit(lambda: ops.gemm(a, w, out=out))
+    t2 = timeit(lambda: torch.matmul(a, w.t(), out=out))
+    fl = 2 * M * N * K / 1e9
+    print(f"M={M} N={N} K={K}: b200 {t1:.3f} ms {fl/t1:.0f} TF/s | cublas {t2:.3f} ms {fl/t2:.0f} TF/s", flush=True)
