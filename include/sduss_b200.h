@@ -74,6 +74,35 @@ typedef struct B200EpilogueDesc {
 int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
                    int epi_mode, const B200EpilogueDesc* ep, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Packed variable-length attention, head_dim 64, non-causal, bf16 (tcgen05 + TMEM + TMA).
+ * One launch for all requests of the batch. Each sequence's queries and keys/values are the
+ * concatenation of up to two row segments ("A" then "B") that live in two source buffers:
+ *   SD3 joint attention : A = image tokens, B = context tokens (Q, K and V from both)
+ *   SD3 attn2, SDXL self: A only
+ *   SDXL cross          : Q from A (image tokens), K/V from B (text tokens)
+ * Replaces xformers.ops.memory_efficient_attention / F.scaled_dot_product_attention and the
+ * per-resolution Python loops at sduss/model_executor/modules/attention.py:86,155-203,297-368.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct B200AttnSource {
+  const void* q;  int32_t ldq;  int32_t q_col;   /* [q_rows, ldq] bf16; head h at q_col + 64 h  */
+  int32_t q_rows;
+  const void* k;  int32_t ldk;  int32_t k_col;   /* [kv_rows, ldk]                              */
+  const void* v;  int32_t ldv;  int32_t v_col;   /* [kv_rows, ldv]                              */
+  int32_t kv_rows;
+  void* out;      int32_t ldo;  int32_t o_col;   /* [q_rows, ldo] attention output of this side */
+} B200AttnSource;
+
+/* seq_table: int32 [n_seq][8] = {qa_row, qa_len, qb_row, qb_len, ka_row, ka_len, kb_row, kb_len}
+ *            (row offsets into the A / B source buffers; a length of 0 disables the segment).
+ * work_items: int32 [n_items][4] = {seq, q_segment (0 = A, 1 = B), row offset of the 128-row
+ *            query tile inside that segment, 0}; one CTA per (item, head).
+ * Every row of the K / V source buffers must hold finite values. src_b may be NULL.
+ * NULL q / k / v pointers inside a source mean that side contributes no such segment. */
+int b200_attn_varlen_bf16(const B200AttnSource* src_a, const B200AttnSource* src_b,
+                          const int32_t* seq_table, const int32_t* work_items, int n_items,
+                          int n_heads, float softmax_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

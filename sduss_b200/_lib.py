@@ -34,6 +34,17 @@ class EpilogueDesc(ctypes.Structure):
     ]
 
 
+class AttnSource(ctypes.Structure):
+    """Mirror of B200AttnSource (include/sduss_b200.h)."""
+    _fields_ = [
+        ("q", c_void_p), ("ldq", ctypes.c_int32), ("q_col", ctypes.c_int32), ("q_rows", ctypes.c_int32),
+        ("k", c_void_p), ("ldk", ctypes.c_int32), ("k_col", ctypes.c_int32),
+        ("v", c_void_p), ("ldv", ctypes.c_int32), ("v_col", ctypes.c_int32),
+        ("kv_rows", ctypes.c_int32),
+        ("out", c_void_p), ("ldo", ctypes.c_int32), ("o_col", ctypes.c_int32),
+    ]
+
+
 class B200Error(RuntimeError):
     pass
 
@@ -54,6 +65,8 @@ SIGNATURES = {
     "b200_sm_count": [],
     "b200_gemm_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                        ctypes.POINTER(EpilogueDesc), c_void_p],
+    "b200_attn_varlen_bf16": [ctypes.POINTER(AttnSource), ctypes.POINTER(AttnSource), c_void_p,
+                              c_void_p, c_int, c_int, c_float, c_void_p],
 }
 
 

@@ -1,0 +1,344 @@
+// Packed variable-length attention (head_dim 64, non-causal) on tcgen05 / TMEM / TMA.
+//
+// One launch covers every request of a mixed-resolution batch. A "sequence" is one latent;
+// its queries and keys/values are each the concatenation of up to two row segments that live
+// in (possibly different) packed buffers:
+//   SD3 joint attention : Q = K = V = [image tokens of latent i ; 333 context tokens of i]
+//   SD3 attn2 / SDXL self: segment A only (image tokens)
+//   SDXL cross attention : Q = segment A (image tokens), K/V = segment B (77 text tokens)
+// This replaces the per-resolution Python loops around xformers / SDPA in the reference
+// (sduss/model_executor/modules/attention.py:155-203 self, :59-110 cross, :297-368 joint).
+//
+// CTA = one 128-row query tile of one (sequence, head). Warp 0: TMA producer (Q once, K and V
+// rings). Warp 1: tcgen05.mma issuer: S = Q K^T into a double-buffered TMEM tile, then
+// O_j = P_j V_j with P read back from TMEM (A-from-TMEM MMA). Warps 2-5: online softmax, one
+// thread per query row (TMEM lane), P written to TMEM as packed bf16 over the S tile; the
+// per-tile PV result is folded into a register accumulator with the usual rescale.
+#include "../../include/sduss_b200.h"
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int ATT_BM = 128;   // query rows per CTA
+constexpr int ATT_BN = 128;   // kv rows per tile
+constexpr int ATT_D = 64;     // head dim
+constexpr int ATT_KS = 3;     // K ring depth
+constexpr int ATT_VS = 3;     // V ring depth
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_TILE_BYTES = 128 * ATT_D * 2;  // 16 KB
+constexpr int ATT_SMEM = (1 + ATT_KS + ATT_VS) * ATT_TILE_BYTES + 1024 + 256;
+
+struct AttnArgs {
+  const int* seq_table;   // [n_seq][8]: qa_row, qa_len, qb_row, qb_len, ka_row, ka_len, kb_row, kb_len
+  const int* work_items;  // [n_items][4]: seq, q_seg (0 = A, 1 = B), row offset in segment, unused
+  int q_col[2], k_col[2], v_col[2];  // column of head 0 inside each source buffer
+  __nv_bfloat16* out[2];             // output buffers for Q segment A / B
+  int ldo[2];
+  int o_col[2];
+  float scale_log2;                  // softmax scale * log2(e)
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant__ CUtensorMap tmQB,
+                const __grid_constant__ CUtensorMap tmKA, const __grid_constant__ CUtensorMap tmKB,
+                const __grid_constant__ CUtensorMap tmVA, const __grid_constant__ CUtensorMap tmVB,
+                AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + ATT_TILE_BYTES;
+  uint8_t* sV = sK + ATT_KS * ATT_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_VS * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;             // 1
+  uint64_t* k_full = bars + 1;         // KS
+  uint64_t* k_empty = k_full + ATT_KS; // KS
+  uint64_t* v_full = k_empty + ATT_KS; // VS
+  uint64_t* v_empty = v_full + ATT_VS; // VS
+  uint64_t* s_full = v_empty + ATT_VS; // 2
+  uint64_t* p_full = s_full + 2;       // 2
+  uint64_t* o_full = p_full + 2;       // 2
+  uint64_t* o_empty = o_full + 2;      // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+
+  const int4 item = reinterpret_cast<const int4*>(a.work_items)[blockIdx.x];
+  const int* st = a.seq_table + item.x * 8;
+  const int q_seg = item.y;
+  const int q_row0 = st[q_seg * 2] + item.z;
+  const int q_valid = min(ATT_BM, st[q_seg * 2 + 1] - item.z);
+  const int ka_row = st[4], ka_len = st[5], kb_row = st[6], kb_len = st[7];
+  const int nA = (ka_len + ATT_BN - 1) / ATT_BN;
+  const int nB = (kb_len + ATT_BN - 1) / ATT_BN;
+  const int n_tiles = nA + nB;
+
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < ATT_KS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+    }
+    for (int i = 0; i < ATT_VS; ++i) {
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;         // S0 / S1: 128 columns each (P overlays the front 64)
+  const uint32_t tO = tmem_base + 256;   // O0 / O1: 64 columns each
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_2d(sQ, q_seg == 0 ? &tmQA : &tmQB, q_full, a.q_col[q_seg] + head * ATT_D, q_row0);
+    }
+    int ks = 0, vs = 0;
+    uint32_t kph = 0, vph = 0;
+    for (int j = 0; j < n_tiles; ++j) {
+      const bool inA = j < nA;
+      const int row = inA ? ka_row + j * ATT_BN : kb_row + (j - nA) * ATT_BN;
+      mbar_wait(&k_empty[ks], kph ^ 1);
+      if (lane == 0) {
+        mbar_expect_tx(&k_full[ks], ATT_TILE_BYTES);
+        tma_load_2d(sK + ks * ATT_TILE_BYTES, inA ? &tmKA : &tmKB, &k_full[ks],
+                    a.k_col[inA ? 0 : 1] + head * ATT_D, row);
+      }
+      mbar_wait(&v_empty[vs], vph ^ 1);
+      if (lane == 0) {
+        mbar_expect_tx(&v_full[vs], ATT_TILE_BYTES);
+        tma_load_2d(sV + vs * ATT_TILE_BYTES, inA ? &tmVA : &tmVB, &v_full[vs],
+                    a.v_col[inA ? 0 : 1] + head * ATT_D, row);
+      }
+      __syncwarp();
+      if (++ks == ATT_KS) { ks = 0; kph ^= 1; }
+      if (++vs == ATT_VS) { vs = 0; vph ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, ATT_D, 0, 1);  // V is MN-major
+    int ks = 0, vs = 0;
+    uint32_t kph = 0, vph = 0;
+    mbar_wait(q_full, 0);
+    const uint64_t dq = make_sdesc_sw128(smem_u32(sQ));
+    auto issue_qk = [&](int j) {
+      mbar_wait(&k_full[ks], kph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t dk = make_sdesc_sw128(smem_u32(sK + ks * ATT_TILE_BYTES));
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_ss(tS + (j & 1) * ATT_BN, dq + uint64_t(2 * k), dk + uint64_t(2 * k), idesc_qk,
+                  k != 0 ? 1u : 0u);
+        umma_commit(&k_empty[ks]);
+        umma_commit(&s_full[j & 1]);
+      }
+      __syncwarp();
+      if (++ks == ATT_KS) { ks = 0; kph ^= 1; }
+    };
+    issue_qk(0);
+    for (int j = 0; j < n_tiles; ++j) {
+      if (j + 1 < n_tiles) issue_qk(j + 1);
+      const int b = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&p_full[b], ph);
+      mbar_wait(&v_full[vs], vph);
+      mbar_wait(&o_empty[b], ph ^ 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t dv = make_sdesc_sw128(smem_u32(sV + vs * ATT_TILE_BYTES));
+#pragma unroll
+        for (int k = 0; k < ATT_BN / 16; ++k)
+          // A: 16 bf16 of K = 8 TMEM columns; B: 16 kv rows = 2048 bytes (>>4 = 128)
+          umma_ts(tO + b * ATT_D, tS + b * ATT_BN + 8 * k, dv + uint64_t(128 * k), idesc_pv,
+                  k != 0 ? 1u : 0u);
+        umma_commit(&v_empty[vs]);
+        umma_commit(&o_full[b]);
+      }
+      __syncwarp();
+      if (++vs == ATT_VS) { vs = 0; vph ^= 1; }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax + output
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;  // query row inside the tile == TMEM lane
+    const uint32_t lane_off = uint32_t(qd * 32) << 16;
+    float o_acc[ATT_D];
+#pragma unroll
+    for (int i = 0; i < ATT_D; ++i) o_acc[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+    const float sc = a.scale_log2;
+
+    auto fold_o = [&](int j, float alpha) {
+      const int b = j & 1;
+      mbar_wait(&o_full[b], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t v[ATT_D];
+      tmem_ld32(tO + lane_off + b * ATT_D, v);
+      tmem_ld32(tO + lane_off + b * ATT_D + 32, v + 32);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[b]);
+#pragma unroll
+      for (int i = 0; i < ATT_D; ++i) o_acc[i] = fmaf(o_acc[i], alpha, __uint_as_float(v[i]));
+    };
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int b = j & 1;
+      const bool inA = j < nA;
+      const int n_valid = inA ? min(ATT_BN, ka_len - j * ATT_BN) : min(ATT_BN, kb_len - (j - nA) * ATT_BN);
+      mbar_wait(&s_full[b], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_s = tS + lane_off + b * ATT_BN;
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_s + c * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float s = (c * 32 + i < n_valid) ? __uint_as_float(v[i]) : -INFINITY;
+          mx = fmaxf(mx, s);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = fast_exp2((m_run - m_new) * sc);
+      const float m_sc = m_new * sc;
+      // pass 2: p = exp2(s * scale - m * scale), row sum, bf16 P into TMEM (over S)
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_s + c * 32, v);
+        tmem_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = (c * 32 + i < n_valid) ? fast_exp2(fmaf(__uint_as_float(v[i]), sc, -m_sc)) : 0.f;
+          float p1 = (c * 32 + i + 1 < n_valid) ? fast_exp2(fmaf(__uint_as_float(v[i + 1]), sc, -m_sc)) : 0.f;
+          sum += p0 + p1;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        tmem_st16(t_s + c * 16, pk);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[b]);
+      l_run = l_run * alpha + sum;
+      m_run = m_new;
+      if (j > 0) fold_o(j - 1, alpha_prev);
+      alpha_prev = alpha;
+    }
+    fold_o(n_tiles - 1, alpha_prev);
+
+    if (r < q_valid) {
+      const float inv = 1.f / l_run;
+      __nv_bfloat16* op = a.out[q_seg] + size_t(q_row0 + r) * a.ldo[q_seg] + a.o_col[q_seg] + head * ATT_D;
+#pragma unroll
+      for (int i = 0; i < ATT_D; i += 8) {
+        uint4 v;
+        v.x = pack_bf16x2(o_acc[i] * inv, o_acc[i + 1] * inv);
+        v.y = pack_bf16x2(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
+        v.z = pack_bf16x2(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
+        v.w = pack_bf16x2(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
+        *reinterpret_cast<uint4*>(op + i) = v;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int make_rows_map(CUtensorMap* m, const void* base, int rows, int cols, int ld) {
+  if (base == nullptr) return B200_ERR_INVALID;
+  uint64_t d[2] = {uint64_t(cols), uint64_t(rows)}, s[1] = {uint64_t(ld) * 2};
+  uint32_t b[2] = {ATT_D, 128};
+  return get_tmap_bf16_sw128(m, base, 2, d, s, b);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_attn_varlen_bf16(const B200AttnSource* src_a, const B200AttnSource* src_b,
+                                     const int32_t* seq_table, const int32_t* work_items,
+                                     int n_items, int n_heads, float softmax_scale, void* stream_) {
+  if (!src_a || !seq_table || !work_items || n_items <= 0 || n_heads <= 0) return B200_ERR_INVALID;
+  const B200AttnSource* srcs[2] = {src_a, src_b ? src_b : src_a};
+  CUtensorMap tm[2][3];
+  bool have[2][3] = {{false, false, false}, {false, false, false}};
+  const CUtensorMap* any = nullptr;
+  AttnArgs a;
+  for (int s = 0; s < 2; ++s) {
+    const B200AttnSource* p = srcs[s];
+    const void* bases[3] = {p->q, p->k, p->v};
+    const int rows[3] = {p->q_rows, p->kv_rows, p->kv_rows};
+    const int lds[3] = {p->ldq, p->ldk, p->ldv};
+    for (int t = 0; t < 3; ++t) {
+      if (bases[t] == nullptr) continue;  // this side has no such segment
+      if ((lds[t] & 7) || rows[t] <= 0) return B200_ERR_INVALID;
+      int rc = make_rows_map(&tm[s][t], bases[t], rows[t], lds[t], lds[t]);
+      if (rc) return rc;
+      have[s][t] = true;
+      if (!any) any = &tm[s][t];
+    }
+    a.q_col[s] = p->q_col;
+    a.k_col[s] = p->k_col;
+    a.v_col[s] = p->v_col;
+    a.out[s] = static_cast<__nv_bfloat16*>(p->out);
+    a.ldo[s] = p->ldo;
+    a.o_col[s] = p->o_col;
+  }
+  if (!any) return B200_ERR_INVALID;
+  // Absent segments get a valid (never dereferenced) map so the kernel signature stays fixed.
+  for (int s = 0; s < 2; ++s)
+    for (int t = 0; t < 3; ++t)
+      if (!have[s][t]) tm[s][t] = *any;
+  a.seq_table = seq_table;
+  a.work_items = work_items;
+  a.scale_log2 = softmax_scale * 1.4426950408889634f;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t err = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (err != cudaSuccess) return static_cast<int>(err);
+    configured = true;
+  }
+  dim3 grid(n_items, n_heads);
+  attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      tm[0][0], tm[1][0], tm[0][1], tm[1][1], tm[0][2], tm[1][2], a);
+  return launch_status();
+}

@@ -6,7 +6,9 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import EpilogueDesc, check, lib
+import numpy as np
+
+from ._lib import AttnSource, EpilogueDesc, check, lib
 
 EPI_BIAS, EPI_GELU_TANH, EPI_GATE_RESID, EPI_QK_RMSNORM, EPI_GEGLU, EPI_ROWVEC = range(6)
 
@@ -51,3 +53,46 @@ def gemm(a, w, out=None, *, epi=EPI_BIAS, bias=None, resid=None, gate=None, row_
     check(lib.b200_gemm_bf16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), M, N, K, epi,
                              ctypes.byref(d), _stream()), "b200_gemm_bf16")
     return out
+
+
+# ------------------------------------------------------------------ attention
+def attn_source(q=None, q_col=0, k=None, k_col=0, v=None, v_col=0, out=None, o_col=0):
+    """Describes one side (A or B) of the packed attention inputs. q/k/v/out are 2-D bf16
+    buffers [rows, ld]; head h of q sits at columns [q_col + 64 h, q_col + 64 h + 64)."""
+    s = AttnSource()
+    for name, t in (("q", q), ("k", k), ("v", v), ("out", out)):
+        if t is not None:
+            _req(t)
+            assert t.dim() == 2 and t.stride(1) == 1
+    s.q, s.ldq, s.q_col = _ptr(q), (q.stride(0) if q is not None else 0), q_col
+    s.q_rows = q.shape[0] if q is not None else 0
+    s.k, s.ldk, s.k_col = _ptr(k), (k.stride(0) if k is not None else 0), k_col
+    s.v, s.ldv, s.v_col = _ptr(v), (v.stride(0) if v is not None else 0), v_col
+    s.kv_rows = k.shape[0] if k is not None else 0
+    s.out, s.ldo, s.o_col = _ptr(out), (out.stride(0) if out is not None else 0), o_col
+    s._keep = (q, k, v, out)
+    return s
+
+
+def build_attn_plan(seqs, device):
+    """seqs: list of 8-tuples (qa_row, qa_len, qb_row, qb_len, ka_row, ka_len, kb_row, kb_len).
+    Returns (seq_table, work_items, n_items) as int32 device tensors; query tiles of the
+    longest sequences come first so the tail of the grid is made of short ones."""
+    table = np.asarray(seqs, dtype=np.int32).reshape(-1, 8)
+    items = []
+    for i, s in enumerate(table):
+        kv = int(s[5]) + int(s[7])
+        for seg in (0, 1):
+            qlen = int(s[2 * seg + 1])
+            for off in range(0, qlen, 128):
+                items.append((kv, i, seg, off))
+    items.sort(key=lambda t: -t[0])
+    work = np.asarray([(i, seg, off, 0) for _, i, seg, off in items], dtype=np.int32).reshape(-1, 4)
+    return (torch.from_numpy(table).to(device), torch.from_numpy(work).to(device), len(items))
+
+
+def attn_varlen(src_a, src_b, seq_table, work_items, n_items, n_heads, scale):
+    check(lib.b200_attn_varlen_bf16(ctypes.byref(src_a),
+                                    ctypes.byref(src_b) if src_b is not None else None,
+                                    _ptr(seq_table), _ptr(work_items), n_items, n_heads,
+                                    ctypes.c_float(scale), _stream()), "b200_attn_varlen_bf16")

@@ -1,0 +1,87 @@
+"""Packed varlen tcgen05 attention vs PyTorch fp32 softmax attention, per sequence."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+H = 3
+
+
+def _rand(shape, dev, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randn(shape, generator=g).to(dev).to(torch.bfloat16)
+
+
+def _ref(q, k, v, scale):
+    # q: [Sq, H, 64] etc. fp32 reference
+    q, k, v = (t.float().transpose(0, 1) for t in (q, k, v))
+    p = torch.softmax(q @ k.transpose(1, 2) * scale, dim=-1)
+    return (p @ v).transpose(0, 1)
+
+
+def _check(out, ref):
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2, err
+    cos = torch.nn.functional.cosine_similarity(out.float().flatten(), ref.flatten(), dim=0).item()
+    assert cos > 0.9995, cos
+
+
+@pytest.mark.parametrize("img_lens,ctx_len", [((128,), 0), ((256, 1024), 0), ((1024, 256, 2304), 333),
+                                              ((256,), 45), ((200, 77), 50)])
+def test_joint_and_self(cuda, img_lens, ctx_len):
+    from sduss_b200 import ops
+    L = len(img_lens)
+    Ta, Tb = sum(img_lens), L * ctx_len
+    C = H * 64
+    qkv_a = _rand((Ta, 3 * C), cuda, 1)
+    out_a = torch.zeros(Ta, C, device=cuda, dtype=torch.bfloat16)
+    if ctx_len:
+        qkv_b = _rand((Tb, 3 * C), cuda, 2)
+        out_b = torch.zeros(Tb, C, device=cuda, dtype=torch.bfloat16)
+    seqs, ra = [], 0
+    for i, s in enumerate(img_lens):
+        seqs.append((ra, s, i * ctx_len, ctx_len, ra, s, i * ctx_len, ctx_len))
+        ra += s
+    table, work, n = ops.build_attn_plan(seqs, cuda)
+    sa = ops.attn_source(q=qkv_a, q_col=0, k=qkv_a, k_col=C, v=qkv_a, v_col=2 * C, out=out_a)
+    sb = ops.attn_source(q=qkv_b, q_col=0, k=qkv_b, k_col=C, v=qkv_b, v_col=2 * C, out=out_b) if ctx_len else None
+    scale = 1 / math.sqrt(64)
+    ops.attn_varlen(sa, sb, table, work, n, H, scale)
+    torch.cuda.synchronize()
+    ra = 0
+    for i, s in enumerate(img_lens):
+        x = qkv_a[ra:ra + s].view(s, 3, H, 64)
+        if ctx_len:
+            y = qkv_b[i * ctx_len:(i + 1) * ctx_len].view(ctx_len, 3, H, 64)
+            x = torch.cat([x, y], 0)
+        ref = _ref(x[:, 0], x[:, 1], x[:, 2], scale).reshape(-1, C)
+        _check(out_a[ra:ra + s], ref[:s])
+        if ctx_len:
+            _check(out_b[i * ctx_len:(i + 1) * ctx_len], ref[s:])
+        ra += s
+
+
+def test_cross(cuda):
+    """SDXL cross attention: Q = image tokens (A), K/V = 77 text tokens (B)."""
+    from sduss_b200 import ops
+    img_lens, T = (1024, 4096, 256), 77
+    C = H * 64
+    q = _rand((sum(img_lens), C), cuda, 3)
+    kv = _rand((len(img_lens) * T, 2 * C), cuda, 4)
+    out = torch.zeros_like(q)
+    seqs, ra = [], 0
+    for i, s in enumerate(img_lens):
+        seqs.append((ra, s, 0, 0, 0, 0, i * T, T))
+        ra += s
+    table, work, n = ops.build_attn_plan(seqs, cuda)
+    sa = ops.attn_source(q=q, out=out)
+    sb = ops.attn_source(k=kv, k_col=0, v=kv, v_col=C)
+    ops.attn_varlen(sa, sb, table, work, n, H, 0.125)
+    torch.cuda.synchronize()
+    ra = 0
+    for i, s in enumerate(img_lens):
+        kk = kv[i * T:(i + 1) * T].view(T, 2, H, 64)
+        ref = _ref(q[ra:ra + s].view(s, H, 64), kk[:, 0], kk[:, 1], 0.125).reshape(s, C)
+        _check(out[ra:ra + s], ref)
+        ra += s
