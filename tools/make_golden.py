@@ -1,0 +1,196 @@
+"""Generates tests/golden/*.npz by EXECUTING THE REFERENCE'S OWN CODE from /root/reference
+(read-only; nothing is copied). Run in the build container only -- /root/reference does not
+exist on the GPU box, which is why the outputs are committed as small fixtures.
+
+  pack_sdxl.npz  : PatchUNet.split_sample / concat_sample (modules/unet.py:104-202), extracted
+                   from the class source with `ast` (the module itself imports diffusers) and
+                   run on CPU with `.cuda()` neutralised.
+  pack_sd3.npz   : split_sample_sd3 / concat_sample (modules/utils.py:86-136), imported as is.
+  sched_*.npz    : EulerDiscreteScheduler.batch_scale_model_input / batch_step and
+                   FlowMatchEulerDiscreteScheduler.batch_step
+                   (diffusers/schedulers/*.py), imported with a stub `diffusers` base class
+                   (the methods under test only read self.config.prediction_type).
+"""
+import ast
+import importlib.util
+import math
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference/sduss/model_executor"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+class _CpuTorch:
+    """Context: make `.cuda()` and device='cuda' no-ops so the reference's pack code runs here."""
+    def __enter__(self):
+        self._cuda = torch.Tensor.cuda
+        self._tensor = torch.tensor
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        real = self._tensor
+
+        def tensor(*a, **k):
+            if k.get("device") == "cuda":
+                k.pop("device")
+            return real(*a, **k)
+        torch.tensor = tensor
+        return self
+
+    def __exit__(self, *exc):
+        torch.Tensor.cuda = self._cuda
+        torch.tensor = self._tensor
+
+
+def load_utils():
+    spec = importlib.util.spec_from_file_location("ref_utils", f"{REF}/modules/utils.py")
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def load_unet_methods():
+    """Extract split_sample / concat_sample of class PatchUNet without importing diffusers."""
+    src = open(f"{REF}/modules/unet.py").read()
+    tree = ast.parse(src)
+    fns = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.ClassDef) and node.name == "PatchUNet":
+            for item in node.body:
+                if isinstance(item, ast.FunctionDef) and item.name in ("split_sample", "concat_sample"):
+                    mod = ast.Module(body=[item], type_ignores=[])
+                    ns = {"torch": torch, "math": math}
+                    exec(compile(mod, f"{REF}/modules/unet.py", "exec"), ns)
+                    fns[item.name] = ns[item.name]
+    return fns
+
+
+def gen_pack():
+    g = torch.Generator().manual_seed(0)
+    u = load_unet_methods()
+    cases = {}
+    # case a: BASELINE config-1 shape (512 + 1024, CFG -> 2 latents each); case b: 256/768 mix.
+    for tag, spec in (("a", {"512": 2, "1024": 2}), ("b", {"256": 1, "512": 3, "768": 2})):
+        samples = {r: torch.randint(-2 ** 15, 2 ** 15, (n, 4, int(r) // 8, int(r) // 8), generator=g).float()
+                   for r, n in spec.items()}
+        ids = {r: [f"req{r}_{i}" for i in range(n)] for r, n in spec.items()}
+        with _CpuTorch():
+            _, padding_idx, latent_offset, resolution_offset, patches, patch_map = u["split_sample"](
+                None, {k: v.clone() for k, v in samples.items()}, 256, ids)
+        inner = patches[:, :, 1:-1, 1:-1].contiguous()
+        back = u["concat_sample"](None, 256, inner, latent_offset["cpu"])
+        for r in spec:
+            cases[f"{tag}_in_{r}"] = samples[r].numpy().astype(np.int16)
+            cases[f"{tag}_back_{r}"] = back[r].numpy().astype(np.int16)
+        cases[f"{tag}_patches"] = patches.numpy().astype(np.int16)
+        cases[f"{tag}_padding_idx"] = torch.stack(padding_idx["cpu"]).numpy().astype(np.int16)
+        cases[f"{tag}_latent_offset"] = np.asarray(latent_offset["cpu"], np.int32)
+        cases[f"{tag}_resolution_offset"] = np.asarray(resolution_offset["cpu"], np.int32)
+        cases[f"{tag}_patch_map"] = np.asarray(patch_map["cpu"], np.int32)
+    np.savez_compressed(os.path.join(OUT, "pack_sdxl.npz"), **cases)
+
+    m = load_utils()
+    cases = {}
+    D = 8
+    for tag, spec in (("a", {"512": 2, "768": 2, "1024": 2}), ("b", {"256": 2, "1024": 1})):
+        samples = {r: torch.randint(-2 ** 15, 2 ** 15, (n, (int(r) // 16) ** 2, D), generator=g).float()
+                   for r, n in spec.items()}
+        ids = {r: [f"req{r}_{i}" for i in range(n)] for r, n in spec.items()}
+        indices, enc_idx, latent_offset, resolution_offset, chunks = m.split_sample_sd3(samples, 256, ids)
+        back = m.concat_sample(256, chunks, latent_offset["cpu"])
+        for r in spec:
+            cases[f"{tag}_in_{r}"] = samples[r].numpy().astype(np.int16)
+            cases[f"{tag}_back_{r}"] = back[r].numpy().astype(np.int16)
+        cases[f"{tag}_chunks"] = chunks.numpy().astype(np.int16)
+        cases[f"{tag}_latent_offset"] = np.asarray(latent_offset["cpu"], np.int32)
+        cases[f"{tag}_resolution_offset"] = np.asarray(resolution_offset["cpu"], np.int32)
+    np.savez_compressed(os.path.join(OUT, "pack_sd3.npz"), **cases)
+
+
+def _stub_diffusers():
+    d = types.ModuleType("diffusers")
+
+    class _Base:
+        def __init__(self, prediction_type="epsilon"):
+            self.config = types.SimpleNamespace(prediction_type=prediction_type)
+    d.EulerDiscreteScheduler = type("EulerDiscreteScheduler", (_Base,), {})
+    d.FlowMatchEulerDiscreteScheduler = type("FlowMatchEulerDiscreteScheduler", (_Base,), {})
+    d.PNDMScheduler = type("PNDMScheduler", (_Base,), {})
+    du = types.ModuleType("diffusers.utils")
+    dt = types.ModuleType("diffusers.utils.torch_utils")
+    dt.randn_tensor = lambda shape, dtype=None, device=None, generator=None: torch.randn(shape, dtype=dtype)
+    sys.modules.update({"diffusers": d, "diffusers.utils": du, "diffusers.utils.torch_utils": dt})
+
+
+def load_ref_schedulers():
+    _stub_diffusers()
+    pkg = types.ModuleType("refsched")
+    pkg.__path__ = [f"{REF}/diffusers/schedulers"]
+    sys.modules["refsched"] = pkg
+    mods = {}
+    for name in ("utils", "scheduling_euler_discrete", "scheduling_flow_match_euler_discrete"):
+        spec = importlib.util.spec_from_file_location(f"refsched.{name}", f"{REF}/diffusers/schedulers/{name}.py")
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[f"refsched.{name}"] = m
+        spec.loader.exec_module(m)
+        mods[name] = m
+    return mods
+
+
+class _Req:
+    def __init__(self, sigmas, step):
+        self.scheduler_states = types.SimpleNamespace(sigmas=sigmas, _step_index=step)
+
+
+def gen_sched():
+    sys.path.insert(0, os.path.dirname(OUT.rstrip("/")).rsplit("/tests", 1)[0])
+    from oracle import schedulers as osch
+    mods = load_ref_schedulers()
+    g = torch.Generator().manual_seed(0)
+    # ---- Euler (SDXL)
+    E = mods["scheduling_euler_discrete"].EulerDiscreteScheduler
+    cases = {}
+    for pt in ("epsilon", "v_prediction"):
+        sch = E(prediction_type=pt)
+        for dt_name, dt in (("f32", torch.float32), ("bf16", torch.bfloat16)):
+            steps = [50, 30, 50]
+            idx = [0, 7, 48]
+            reqs = [_Req(osch.euler_sigmas(n)[0], i) for n, i in zip(steps, idx)]
+            x = (torch.randn(3, 4, 16, 16, generator=g) * 5).to(dt)
+            eps = torch.randn(3, 4, 16, 16, generator=g).to(dt)
+            xin = torch.cat([x, x])
+            scaled = sch.batch_scale_model_input(reqs, xin, None)
+            torch.manual_seed(0)
+            prev = sch.batch_step(reqs, eps, None, x, return_dict=False)
+            assert [r.scheduler_states._step_index for r in reqs] == [i + 1 for i in idx]
+            tag = f"{pt}_{dt_name}"
+            cases[tag + "_steps"] = np.asarray(steps); cases[tag + "_idx"] = np.asarray(idx)
+            cases[tag + "_x"] = x.float().numpy(); cases[tag + "_eps"] = eps.float().numpy()
+            cases[tag + "_scaled"] = scaled.float().numpy(); cases[tag + "_prev"] = prev.float().numpy()
+    np.savez_compressed(os.path.join(OUT, "sched_euler.npz"), **cases)
+    # ---- flow match (SD3)
+    Fm = mods["scheduling_flow_match_euler_discrete"].FlowMatchEulerDiscreteScheduler
+    sch = Fm()
+    cases = {}
+    for dt_name, dt in (("f32", torch.float32), ("bf16", torch.bfloat16)):
+        steps = [28, 50, 28]
+        idx = [0, 20, 27]
+        reqs = [_Req(osch.flow_match_sigmas(n)[0], i) for n, i in zip(steps, idx)]
+        x = torch.randn(3, 16, 8, 8, generator=g).to(dt)
+        v = torch.randn(3, 16, 8, 8, generator=g).to(dt)
+        prev = sch.batch_step(reqs, v, x, None, return_dict=False)
+        cases[dt_name + "_steps"] = np.asarray(steps); cases[dt_name + "_idx"] = np.asarray(idx)
+        cases[dt_name + "_x"] = x.float().numpy(); cases[dt_name + "_v"] = v.float().numpy()
+        cases[dt_name + "_prev"] = prev.float().numpy()
+    np.savez_compressed(os.path.join(OUT, "sched_flow_match.npz"), **cases)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    gen_pack()
+    gen_sched()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
