@@ -103,6 +103,60 @@ int b200_attn_varlen_bf16(const B200AttnSource* src_a, const B200AttnSource* src
                           const int32_t* seq_table, const int32_t* work_items, int n_items,
                           int n_heads, float softmax_scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * HBM-bound kernels (coalesced 16-byte vectors, warp-shuffle reductions).
+ * ---------------------------------------------------------------------------------------- */
+
+/* y = LN(x) [*gamma + beta] [*(1 + mod[g, scale_col:]) + mod[g, shift_col:]], g = row_group[row]
+ * (g = 0 when row_group is NULL); optional second output y2 with (scale2_col, shift2_col).
+ * Covers diffusers LayerNorm, AdaLayerNormZero, SD35AdaLayerNormZeroX and
+ * AdaLayerNormContinuous as called from sduss modules/transformer.py:185-279,317-386 and
+ * modules/SD3Transformer.py:238. x, y: [T, ld] bf16; D <= 2048, D % 8 == 0; mod: [G, ldm] bf16. */
+int b200_layernorm_mod_bf16(const void* x, int ldx, int T, int D, float eps, const void* gamma,
+                            const void* beta, const void* mod, int ldm, const int32_t* row_group,
+                            int shift_col, int scale_col, void* y, int ldy, int shift2_col,
+                            int scale2_col, void* y2, int ldy2, void* stream);
+
+/* y = x * sigmoid(x), n % 8 == 0 elements of bf16. */
+int b200_silu_bf16(const void* x, void* y, long long n, void* stream);
+
+/* Sinusoidal embedding, flip_sin_to_cos=True, freq_shift=0 (diffusers Timesteps; call sites
+ * sduss modules/unet.py:314-334, SD3Transformer.py:81): out[i] = [cos(t_i f) | sin(t_i f)],
+ * t: [n] fp32, out: [n, ldo] bf16. */
+int b200_timestep_embedding(const float* t, int n, int dim, void* out, int ldo, void* stream);
+
+/* SD3 pack: latents [C, h, w] bf16 (one device pointer per latent) -> packed token buffer
+ * tokens[tok_off_i + ty*wt + tx, c*p*p + py*p + px] (im2col of the k=p,s=p PatchEmbed conv,
+ * SD3Transformer.py:82-83). The packed buffer is, row for row, the reference's
+ * split_sample_sd3 chunk stack viewed as [T*256, D] (modules/utils.py:86-122).
+ * desc: int32 [n][4] = {token offset, tokens per row (w/p), token rows (h/p), 0}. */
+int b200_sd3_patchify(const uint64_t* lat_ptr, const int32_t* desc, int n_latents, int max_tokens,
+                      int C, int p, void* tokens, int ldt, void* stream);
+
+/* SD3 scatter: tokens [T, p*p*C] -> latents [C, h, w] (concat_sample + einsum nhwpqc->nchpwq,
+ * modules/utils.py:124-136, SD3Transformer.py:244-259). */
+int b200_sd3_unpatchify(const void* tokens, int ldt, const int32_t* desc, int n_latents,
+                        int max_tokens, int C, int p, const uint64_t* out_ptr, void* stream);
+
+/* Fused CFG combine + scheduler update, one pass over the latents of all requests.
+ *   mode 0: flow-match Euler (scheduling_flow_match_euler_discrete.py:159-203)
+ *   mode 1: Euler, epsilon prediction; mode 2: Euler, v_prediction
+ *           (scheduling_euler_discrete.py:187-274)
+ * cfg != 0: eps = u + guidance * (c - u) (pipeline_stable_diffusion_xl_esymred.py:382-385).
+ * desc: int64 [R][4] = {element offset of request r in x/out, elements, offset of the uncond
+ * prediction in eps, offset of the cond prediction in eps}; sigmas: fp32 [R][2] = {sigma,
+ * sigma_next}. eps, x, out bf16. Arithmetic order and rounding follow the reference
+ * (fp32 update, bf16 result). */
+int b200_cfg_scheduler_step(const void* eps, const void* x, void* out, const int64_t* desc,
+                            const float* sigmas, int n_requests, long long max_elems,
+                            float guidance, int cfg, int mode, void* stream);
+
+/* y = x / sqrt(sigma_l^2 + 1) per latent (batch_scale_model_input,
+ * scheduling_euler_discrete.py:161-184). desc: int64 [L][2] = {element offset, elements};
+ * sigmas fp32 [L]. */
+int b200_euler_scale_input(const void* x, void* y, const int64_t* desc, const float* sigmas,
+                           int n_latents, long long max_elems, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,19 @@ SIGNATURES = {
                        ctypes.POINTER(EpilogueDesc), c_void_p],
     "b200_attn_varlen_bf16": [ctypes.POINTER(AttnSource), ctypes.POINTER(AttnSource), c_void_p,
                               c_void_p, c_int, c_int, c_float, c_void_p],
+    "b200_layernorm_mod_bf16": [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+                                c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
+                                c_int, c_void_p, c_int, c_void_p],
+    "b200_silu_bf16": [c_void_p, c_void_p, ctypes.c_longlong, c_void_p],
+    "b200_timestep_embedding": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
+    "b200_sd3_patchify": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                          c_void_p],
+    "b200_sd3_unpatchify": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                            c_void_p],
+    "b200_cfg_scheduler_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                ctypes.c_longlong, c_float, c_int, c_int, c_void_p],
+    "b200_euler_scale_input": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, ctypes.c_longlong,
+                               c_void_p],
 }
 
 

@@ -96,3 +96,57 @@ def attn_varlen(src_a, src_b, seq_table, work_items, n_items, n_heads, scale):
                                     ctypes.byref(src_b) if src_b is not None else None,
                                     _ptr(seq_table), _ptr(work_items), n_items, n_heads,
                                     ctypes.c_float(scale), _stream()), "b200_attn_varlen_bf16")
+
+
+# ------------------------------------------------------------------ HBM-bound kernels
+def layernorm_mod(x, y, *, eps, gamma=None, beta=None, mod=None, row_group=None, shift_col=0,
+                  scale_col=0, y2=None, shift2_col=0, scale2_col=0):
+    """y = LN(x)[*gamma+beta][*(1+mod[g,scale_col:])+mod[g,shift_col:]]; optional y2."""
+    _req(x), _req(y)
+    T, D = x.shape
+    check(lib.b200_layernorm_mod_bf16(
+        _ptr(x), x.stride(0), T, D, ctypes.c_float(eps), _ptr(gamma), _ptr(beta), _ptr(mod),
+        (mod.stride(0) if mod is not None else 0), _ptr(row_group), shift_col, scale_col,
+        _ptr(y), y.stride(0), shift2_col, scale2_col, _ptr(y2),
+        (y2.stride(0) if y2 is not None else 0), _stream()), "b200_layernorm_mod_bf16")
+    return y
+
+
+def silu(x, y=None):
+    _req(x)
+    assert x.is_contiguous()
+    y = torch.empty_like(x) if y is None else y
+    check(lib.b200_silu_bf16(_ptr(x), _ptr(y), x.numel(), _stream()), "b200_silu_bf16")
+    return y
+
+
+def timestep_embedding(t, dim, out=None):
+    """t: [n] fp32 -> [n, dim] bf16 = [cos | sin]."""
+    _req(t, torch.float32)
+    n = t.numel()
+    out = torch.empty((n, dim), device=t.device, dtype=torch.bfloat16) if out is None else out
+    check(lib.b200_timestep_embedding(_ptr(t), n, dim, _ptr(out), out.stride(0), _stream()),
+          "b200_timestep_embedding")
+    return out
+
+
+def sd3_patchify(lat_ptr, desc, n_latents, max_tokens, C, p, tokens):
+    check(lib.b200_sd3_patchify(_ptr(lat_ptr), _ptr(desc), n_latents, max_tokens, C, p,
+                                _ptr(tokens), tokens.stride(0), _stream()), "b200_sd3_patchify")
+
+
+def sd3_unpatchify(tokens, desc, n_latents, max_tokens, C, p, out_ptr):
+    check(lib.b200_sd3_unpatchify(_ptr(tokens), tokens.stride(0), _ptr(desc), n_latents,
+                                  max_tokens, C, p, _ptr(out_ptr), _stream()),
+          "b200_sd3_unpatchify")
+
+
+def cfg_scheduler_step(eps, x, out, desc, sigmas, n_requests, max_elems, guidance, cfg, mode):
+    check(lib.b200_cfg_scheduler_step(_ptr(eps), _ptr(x), _ptr(out), _ptr(desc), _ptr(sigmas),
+                                      n_requests, max_elems, ctypes.c_float(guidance), int(cfg),
+                                      mode, _stream()), "b200_cfg_scheduler_step")
+
+
+def euler_scale_input(x, y, desc, sigmas, n_latents, max_elems):
+    check(lib.b200_euler_scale_input(_ptr(x), _ptr(y), _ptr(desc), _ptr(sigmas), n_latents,
+                                     max_elems, _stream()), "b200_euler_scale_input")

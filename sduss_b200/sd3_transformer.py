@@ -1,0 +1,305 @@
+"""B200-native drop-in for sduss' PatchSD3Transformer2DModel
+(reference: sduss/model_executor/modules/SD3Transformer.py:25-262).
+
+Same forward signature and return type (dict resolution -> [n_r, 16, h, w] in, tuple(dict) out,
+conditioning rows ordered resolution by resolution), but no 256-px chunk machinery: all image
+tokens of all latents live in ONE packed buffer [sum S_i, 1536] bf16 (row for row identical to
+the reference's split_sample_sd3 chunk stack), context tokens in [L*333, 1536], and every op
+is a single launch of a hand-written sm_100a kernel through the C ABI (sduss_b200.ops):
+tcgen05 GEMMs with fused bias / q-k RMSNorm / GELU / gate+residual epilogues, one packed
+varlen joint-attention launch, warp-per-row LayerNorm+AdaLN modulation. AdaLN modulation
+vectors for all 24 blocks come from one up-front GEMM per step (they depend only on temb and
+are computed per latent, not per chunk as the reference does).
+"""
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+@dataclass
+class SD3Config:
+    num_layers: int = 24
+    num_attention_heads: int = 24
+    attention_head_dim: int = 64
+    in_channels: int = 16
+    out_channels: int = 16
+    patch_size: int = 2
+    pos_embed_max_size: int = 384
+    sample_size: int = 128
+    joint_attention_dim: int = 4096
+    caption_projection_dim: int = 1536
+    pooled_projection_dim: int = 2048
+    dual_attention_layers: List[int] = field(default_factory=lambda: list(range(13)))
+
+    @property
+    def inner_dim(self):
+        return self.num_attention_heads * self.attention_head_dim
+
+    @classmethod
+    def from_any(cls, cfg):
+        """Accepts this class, a diffusers FrozenDict/config object or a plain dict."""
+        if isinstance(cfg, cls):
+            return cls(**{k: getattr(cfg, k) for k in cls.__dataclass_fields__})
+        get = cfg.get if hasattr(cfg, "get") else lambda k, d=None: getattr(cfg, k, d)
+        kw = {}
+        for k in cls.__dataclass_fields__:
+            v = get(k, None)
+            if v is not None:
+                kw[k] = list(v) if k == "dual_attention_layers" else v
+        return cls(**kw)
+
+
+class _Plan:
+    """Everything that depends only on the batch composition ((resolution, count) tuple):
+    descriptor tables, attention work lists, gathered positional rows and workspaces."""
+
+    def __init__(self, model: "B200SD3Transformer2DModel", comp, ctx_len: int):
+        cfg, dev = model.cfg, model.device
+        D, p = cfg.inner_dim, cfg.patch_size
+        self.comp = comp
+        self.ctx_len = ctx_len
+        lat = []  # (res_key, index in res, h_tok, w_tok)
+        for res, n, h, w in comp:
+            for i in range(n):
+                lat.append((res, i, h // p, w // p))
+        self.L = L = len(lat)
+        S = [ht * wt for _, _, ht, wt in lat]
+        off = np.concatenate([[0], np.cumsum(S)]).astype(np.int64)
+        self.T, self.Tc = int(off[-1]), L * ctx_len
+        self.max_tokens = max(S)
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        # static input / output staging per resolution (stable pointers -> graph-capturable)
+        self.stage_in = {res: torch.empty((n, cfg.in_channels, h, w), **bf) for res, n, h, w in comp}
+        self.stage_out = {res: torch.empty((n, cfg.out_channels, h, w), **bf) for res, n, h, w in comp}
+        in_ptr, out_ptr, desc = [], [], []
+        for l, (res, i, ht, wt) in enumerate(lat):
+            in_ptr.append(self.stage_in[res][i].data_ptr())
+            out_ptr.append(self.stage_out[res][i].data_ptr())
+            desc.append((int(off[l]), wt, ht, 0))
+        self.in_ptr = torch.tensor(in_ptr, dtype=torch.int64).to(dev)
+        self.out_ptr = torch.tensor(out_ptr, dtype=torch.int64).to(dev)
+        self.desc = torch.tensor(desc, dtype=torch.int32).to(dev)
+        self.row_group = torch.from_numpy(np.repeat(np.arange(L, dtype=np.int32), S)).to(dev)
+        self.row_group_ctx = torch.from_numpy(
+            np.repeat(np.arange(L, dtype=np.int32), ctx_len)).to(dev)
+        # positional rows: cropped sincos table per latent, gathered once per composition
+        pos = []
+        M = cfg.pos_embed_max_size
+        for _, _, ht, wt in lat:
+            top, left = (M - ht) // 2, (M - wt) // 2
+            rows = (torch.arange(top, top + ht)[:, None] * M + torch.arange(left, left + wt)[None]).reshape(-1)
+            pos.append(rows)
+        self.pos_rows = model.pos_table[torch.cat(pos).to(dev)].contiguous()
+        # attention work lists
+        joint = [(int(off[l]), S[l], l * ctx_len, ctx_len, int(off[l]), S[l], l * ctx_len, ctx_len)
+                 for l in range(L)]
+        self.joint_plan = ops.build_attn_plan(joint, dev)
+        selfp = [(int(off[l]), S[l], 0, 0, int(off[l]), S[l], 0, 0) for l in range(L)]
+        self.self_plan = ops.build_attn_plan(selfp, dev)
+        # workspaces
+        T, Tc = self.T, self.Tc
+        self.tokens = torch.empty((T, cfg.in_channels * p * p), **bf)
+        self.x = torch.empty((T, D), **bf)
+        self.xn = torch.empty((T, D), **bf)
+        self.xn2 = torch.empty((T, D), **bf)
+        self.c = torch.empty((Tc, D), **bf)
+        self.cn = torch.empty((Tc, D), **bf)
+        self.qkv = torch.empty((T, 3 * D), **bf)
+        self.qkv_c = torch.empty((Tc, 3 * D), **bf)
+        self.att = torch.empty((T, D), **bf)
+        self.att_c = torch.empty((Tc, D), **bf)
+        self.ff = torch.empty((T, 4 * D), **bf)
+        self.ff_c = torch.empty((Tc, 4 * D), **bf)
+        self.out_tok = torch.empty((T, p * p * cfg.out_channels), **bf)
+        self.mod = torch.empty((L, model.mod_cols), **bf)
+        self.t32 = torch.empty((L,), device=dev, dtype=torch.float32)
+        self.tsin = torch.empty((L, 256), **bf)
+        self.e1 = torch.empty((L, D), **bf)
+        self.e2 = torch.empty((L, D), **bf)
+        self.e3 = torch.empty((L, D), **bf)
+        self.temb = torch.empty((L, D), **bf)
+        self.pooled = torch.empty((L, cfg.pooled_projection_dim), **bf)
+        self.ehs = torch.empty((Tc, cfg.joint_attention_dim), **bf)
+        # attention sources (pointers are static)
+        self.src_img = ops.attn_source(q=self.qkv, q_col=0, k=self.qkv, k_col=D, v=self.qkv,
+                                       v_col=2 * D, out=self.att)
+        self.src_ctx = ops.attn_source(q=self.qkv_c, q_col=0, k=self.qkv_c, k_col=D, v=self.qkv_c,
+                                       v_col=2 * D, out=self.att_c)
+
+
+class B200SD3Transformer2DModel(torch.nn.Module):
+    """Built from a diffusers-style SD3Transformer2DModel state dict; weights are re-laid out
+    once (fused q|k|v matrices, all AdaLN linears concatenated) and kept in bf16 on the GPU."""
+
+    SUPPORT_RESOLUTIONS = [256, 512, 768, 1024]
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], config, device="cuda"):
+        super().__init__()
+        self.cfg = cfg = SD3Config.from_any(config)
+        self.config = config
+        self.device = torch.device(device)
+        self.dtype = torch.bfloat16
+        assert cfg.attention_head_dim == 64, "attention kernel is specialised for head_dim 64"
+        D = cfg.inner_dim
+        sd = state_dict
+
+        def w(name):
+            return sd[name].to(device=self.device, dtype=torch.bfloat16).contiguous()
+
+        def cat(names):
+            return torch.cat([sd[n] for n in names], 0).to(device=self.device, dtype=torch.bfloat16).contiguous()
+
+        self.pe_w = w("pos_embed.proj.weight").reshape(D, -1).contiguous()
+        self.pe_b = w("pos_embed.proj.bias")
+        self.pos_table = sd["pos_embed.pos_embed"].reshape(-1, D).to(self.device, torch.bfloat16)
+        self.te = {k: w(f"time_text_embed.{k}") for k in (
+            "timestep_embedder.linear_1.weight", "timestep_embedder.linear_1.bias",
+            "timestep_embedder.linear_2.weight", "timestep_embedder.linear_2.bias",
+            "text_embedder.linear_1.weight", "text_embedder.linear_1.bias",
+            "text_embedder.linear_2.weight", "text_embedder.linear_2.bias")}
+        self.ctx_w, self.ctx_b = w("context_embedder.weight"), w("context_embedder.bias")
+        self.blocks = []
+        mod_w, mod_b, col = [], [], 0
+        for i in range(cfg.num_layers):
+            b = f"transformer_blocks.{i}"
+            dual = i in cfg.dual_attention_layers
+            last = i == cfg.num_layers - 1
+            blk = {"dual": dual, "last": last}
+            blk["mod"] = col
+            mod_w.append(sd[b + ".norm1.linear.weight"]); mod_b.append(sd[b + ".norm1.linear.bias"])
+            col += (9 if dual else 6) * D
+            blk["cmod"] = col
+            mod_w.append(sd[b + ".norm1_context.linear.weight"]); mod_b.append(sd[b + ".norm1_context.linear.bias"])
+            col += (2 if last else 6) * D
+            blk["qkv_w"] = cat([f"{b}.attn.to_{n}.weight" for n in "qkv"])
+            blk["qkv_b"] = cat([f"{b}.attn.to_{n}.bias" for n in "qkv"])
+            blk["aqkv_w"] = cat([f"{b}.attn.add_{n}_proj.weight" for n in "qkv"])
+            blk["aqkv_b"] = cat([f"{b}.attn.add_{n}_proj.bias" for n in "qkv"])
+            for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"):
+                blk[n] = w(f"{b}.attn.{n}.weight")
+            blk["out_w"], blk["out_b"] = w(b + ".attn.to_out.0.weight"), w(b + ".attn.to_out.0.bias")
+            if not last:
+                blk["aout_w"], blk["aout_b"] = w(b + ".attn.to_add_out.weight"), w(b + ".attn.to_add_out.bias")
+                blk["ffc1_w"], blk["ffc1_b"] = w(b + ".ff_context.net.0.proj.weight"), w(b + ".ff_context.net.0.proj.bias")
+                blk["ffc2_w"], blk["ffc2_b"] = w(b + ".ff_context.net.2.weight"), w(b + ".ff_context.net.2.bias")
+            if dual:
+                blk["qkv2_w"] = cat([f"{b}.attn2.to_{n}.weight" for n in "qkv"])
+                blk["qkv2_b"] = cat([f"{b}.attn2.to_{n}.bias" for n in "qkv"])
+                blk["norm_q2"], blk["norm_k2"] = w(b + ".attn2.norm_q.weight"), w(b + ".attn2.norm_k.weight")
+                blk["out2_w"], blk["out2_b"] = w(b + ".attn2.to_out.0.weight"), w(b + ".attn2.to_out.0.bias")
+            blk["ff1_w"], blk["ff1_b"] = w(b + ".ff.net.0.proj.weight"), w(b + ".ff.net.0.proj.bias")
+            blk["ff2_w"], blk["ff2_b"] = w(b + ".ff.net.2.weight"), w(b + ".ff.net.2.bias")
+            self.blocks.append(blk)
+        self.out_mod = col
+        mod_w.append(sd["norm_out.linear.weight"]); mod_b.append(sd["norm_out.linear.bias"])
+        col += 2 * D
+        self.mod_cols = col
+        self.mod_w = torch.cat(mod_w, 0).to(self.device, torch.bfloat16).contiguous()
+        self.mod_b = torch.cat(mod_b, 0).to(self.device, torch.bfloat16).contiguous()
+        self.proj_w, self.proj_b = w("proj_out.weight"), w("proj_out.bias")
+        self._plans: Dict[tuple, _Plan] = {}
+
+    @classmethod
+    def from_diffusers(cls, model, device="cuda"):
+        """`model` is the diffusers SD3Transformer2DModel that sduss' loader hands to
+        instantiate_pipeline (pipeline_stable_diffusion_3_esymred.py:24-36)."""
+        return cls(model.state_dict(), model.config, device=device)
+
+    # ------------------------------------------------------------------
+    def _plan(self, hidden_states, ctx_len) -> _Plan:
+        comp = tuple((res, t.shape[0], t.shape[-2], t.shape[-1])
+                     for res, t in hidden_states.items() if t is not None and t.shape[0] > 0)
+        key = (comp, ctx_len)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._plans[key] = _Plan(self, comp, ctx_len)
+        return plan
+
+    @torch.no_grad()
+    def forward(self, hidden_states: Dict[str, torch.Tensor], encoder_hidden_states=None,
+                pooled_projections=None, timestep=None, block_controlnet_hidden_states=None,
+                joint_attention_kwargs=None, return_dict: bool = False, skip_layers=None,
+                patch_size: Optional[int] = None, is_sliced: bool = True, save_index: int = 0,
+                input_indices: Optional[dict] = None, _borrow: bool = False):
+        assert block_controlnet_hidden_states is None and skip_layers is None
+        assert not joint_attention_kwargs, "joint_attention_kwargs (LoRA scale / IP-adapter) unsupported"
+        plan = self._plan(hidden_states, encoder_hidden_states.shape[1])
+        for res, _, _, _ in plan.comp:
+            plan.stage_in[res].copy_(hidden_states[res])
+        plan.ehs.copy_(encoder_hidden_states.reshape(plan.Tc, -1))
+        plan.pooled.copy_(pooled_projections)
+        plan.t32.copy_(timestep.reshape(-1))
+        self._run(plan)
+        out = plan.stage_out if _borrow else {k: v.clone() for k, v in plan.stage_out.items()}
+        return (out,)
+
+    def _run(self, pl: _Plan):
+        cfg = self.cfg
+        D, H, p = cfg.inner_dim, cfg.num_attention_heads, cfg.patch_size
+        G = ops.gemm
+        te = self.te
+        scale = 1.0 / math.sqrt(cfg.attention_head_dim)
+        # conditioning: temb = MLP(sinusoid(t)) + MLP(pooled); all AdaLN vectors in one GEMM
+        ops.timestep_embedding(pl.t32, 256, out=pl.tsin)
+        G(pl.tsin, te["timestep_embedder.linear_1.weight"], pl.e1, bias=te["timestep_embedder.linear_1.bias"])
+        ops.silu(pl.e1, pl.e1)
+        G(pl.e1, te["timestep_embedder.linear_2.weight"], pl.e2, bias=te["timestep_embedder.linear_2.bias"])
+        G(pl.pooled, te["text_embedder.linear_1.weight"], pl.e3, bias=te["text_embedder.linear_1.bias"])
+        ops.silu(pl.e3, pl.e3)
+        G(pl.e3, te["text_embedder.linear_2.weight"], pl.temb, bias=te["text_embedder.linear_2.bias"],
+          epi=ops.EPI_GATE_RESID, resid=pl.e2)
+        ops.silu(pl.temb, pl.e1)
+        G(pl.e1, self.mod_w, pl.mod, bias=self.mod_b)
+        # streams
+        G(pl.ehs, self.ctx_w, pl.c, bias=self.ctx_b)
+        ops.sd3_patchify(pl.in_ptr, pl.desc, pl.L, pl.max_tokens, cfg.in_channels, p, pl.tokens)
+        G(pl.tokens, self.pe_w, pl.x, bias=self.pe_b, epi=ops.EPI_GATE_RESID, resid=pl.pos_rows)
+        mod = pl.mod
+        for blk in self.blocks:
+            m, cm = blk["mod"], blk["cmod"]
+            dual, last = blk["dual"], blk["last"]
+            ops.layernorm_mod(pl.x, pl.xn, eps=1e-6, mod=mod, row_group=pl.row_group,
+                              shift_col=m, scale_col=m + D,
+                              y2=pl.xn2 if dual else None, shift2_col=m + 6 * D, scale2_col=m + 7 * D)
+            if last:  # AdaLayerNormContinuous: (scale, shift)
+                ops.layernorm_mod(pl.c, pl.cn, eps=1e-6, mod=mod, row_group=pl.row_group_ctx,
+                                  shift_col=cm + D, scale_col=cm)
+            else:
+                ops.layernorm_mod(pl.c, pl.cn, eps=1e-6, mod=mod, row_group=pl.row_group_ctx,
+                                  shift_col=cm, scale_col=cm + D)
+            G(pl.xn, blk["qkv_w"], pl.qkv, bias=blk["qkv_b"], epi=ops.EPI_QK_RMSNORM,
+              rms_wq=blk["norm_q"], rms_wk=blk["norm_k"], rms_q_cols=D, rms_k_cols=D)
+            G(pl.cn, blk["aqkv_w"], pl.qkv_c, bias=blk["aqkv_b"], epi=ops.EPI_QK_RMSNORM,
+              rms_wq=blk["norm_added_q"], rms_wk=blk["norm_added_k"], rms_q_cols=D, rms_k_cols=D)
+            ops.attn_varlen(pl.src_img, pl.src_ctx, *pl.joint_plan, H, scale)
+            G(pl.att, blk["out_w"], pl.x, bias=blk["out_b"], epi=ops.EPI_GATE_RESID, resid=pl.x,
+              gate=mod[:, m + 2 * D:m + 3 * D], row_group=pl.row_group)
+            if dual:
+                G(pl.xn2, blk["qkv2_w"], pl.qkv, bias=blk["qkv2_b"], epi=ops.EPI_QK_RMSNORM,
+                  rms_wq=blk["norm_q2"], rms_wk=blk["norm_k2"], rms_q_cols=D, rms_k_cols=D)
+                ops.attn_varlen(pl.src_img, None, *pl.self_plan, H, scale)
+                G(pl.att, blk["out2_w"], pl.x, bias=blk["out2_b"], epi=ops.EPI_GATE_RESID,
+                  resid=pl.x, gate=mod[:, m + 8 * D:m + 9 * D], row_group=pl.row_group)
+            ops.layernorm_mod(pl.x, pl.xn, eps=1e-6, mod=mod, row_group=pl.row_group,
+                              shift_col=m + 3 * D, scale_col=m + 4 * D)
+            G(pl.xn, blk["ff1_w"], pl.ff, bias=blk["ff1_b"], epi=ops.EPI_GELU_TANH)
+            G(pl.ff, blk["ff2_w"], pl.x, bias=blk["ff2_b"], epi=ops.EPI_GATE_RESID, resid=pl.x,
+              gate=mod[:, m + 5 * D:m + 6 * D], row_group=pl.row_group)
+            if not last:
+                G(pl.att_c, blk["aout_w"], pl.c, bias=blk["aout_b"], epi=ops.EPI_GATE_RESID,
+                  resid=pl.c, gate=mod[:, cm + 2 * D:cm + 3 * D], row_group=pl.row_group_ctx)
+                ops.layernorm_mod(pl.c, pl.cn, eps=1e-6, mod=mod, row_group=pl.row_group_ctx,
+                                  shift_col=cm + 3 * D, scale_col=cm + 4 * D)
+                G(pl.cn, blk["ffc1_w"], pl.ff_c, bias=blk["ffc1_b"], epi=ops.EPI_GELU_TANH)
+                G(pl.ff_c, blk["ffc2_w"], pl.c, bias=blk["ffc2_b"], epi=ops.EPI_GATE_RESID,
+                  resid=pl.c, gate=mod[:, cm + 5 * D:cm + 6 * D], row_group=pl.row_group_ctx)
+        om = self.out_mod
+        ops.layernorm_mod(pl.x, pl.xn, eps=1e-6, mod=mod, row_group=pl.row_group,
+                          shift_col=om + D, scale_col=om)
+        G(pl.xn, self.proj_w, pl.out_tok, bias=self.proj_b)
+        ops.sd3_unpatchify(pl.out_tok, pl.desc, pl.L, pl.max_tokens, cfg.out_channels, p, pl.out_ptr)

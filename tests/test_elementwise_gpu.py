@@ -1,0 +1,154 @@
+"""HBM-bound kernels vs oracle / golden fixtures. Index and scheduler work is bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_layernorm_mod(cuda):
+    from sduss_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for T, D in ((100, 1536), (37, 640), (64, 1280), (9, 128)):
+        x = (torch.randn(T, D, generator=g) * 3 + 1).cuda().bfloat16()
+        mod = torch.randn(4, 6 * D, generator=g).cuda().bfloat16()
+        grp = (torch.arange(T) % 4).int().cuda()
+        y, y2 = torch.empty_like(x), torch.empty_like(x)
+        ops.layernorm_mod(x, y, eps=1e-6, mod=mod, row_group=grp, shift_col=0, scale_col=D,
+                          y2=y2, shift2_col=2 * D, scale2_col=3 * D)
+        n = torch.nn.functional.layer_norm(x.float(), (D,), eps=1e-6)
+        m = mod.float()[grp.long()]
+        assert (y.float() - (n * (1 + m[:, D:2 * D]) + m[:, :D])).abs().max() < 0.06
+        assert (y2.float() - (n * (1 + m[:, 3 * D:4 * D]) + m[:, 2 * D:3 * D])).abs().max() < 0.06
+        gam, bet = torch.randn(D, generator=g).cuda().bfloat16(), torch.randn(D, generator=g).cuda().bfloat16()
+        ops.layernorm_mod(x, y, eps=1e-5, gamma=gam, beta=bet)
+        ref = torch.nn.functional.layer_norm(x.float(), (D,), gam.float(), bet.float(), 1e-5)
+        assert (y.float() - ref).abs().max() < 0.06
+
+
+def test_timestep_embedding_and_silu(cuda):
+    from oracle.sd3_mmdit import timestep_embedding
+    from sduss_b200 import ops
+    t = torch.tensor([999.0, 981.0, 1.0, 0.0, 512.5, 1024.0], device=cuda)
+    for dim in (256, 320):
+        out = ops.timestep_embedding(t, dim)
+        ref = timestep_embedding(t.cpu(), dim)
+        assert (out.float().cpu() - ref).abs().max() < 1e-2  # bf16 output rounding + fp32 sincos
+    x = torch.randn(16, 1536, device=cuda).bfloat16()
+    assert (ops.silu(x).float() - torch.nn.functional.silu(x.float())).abs().max() < 2e-2
+
+
+def test_sd3_pack_scatter_bit_exact(cuda):
+    """patchify rows == the reference's split_sample_sd3 row order (golden) and
+    unpatchify(patchify(x)) == x; values are small integers, exact in bf16."""
+    from sduss_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    C, p = 16, 2
+    spec = [("512", 2, 64), ("768", 1, 96), ("1024", 1, 128)]
+    lat = {r: torch.randint(-120, 120, (n, C, s, s), generator=g).float() for r, n, s in spec}
+    dev_lat = {r: v.cuda().bfloat16() for r, v in lat.items()}
+    ptrs, desc, off = [], [], 0
+    for r, n, s in spec:
+        for i in range(n):
+            ptrs.append(dev_lat[r][i].data_ptr())
+            desc.append((off, s // p, s // p, 0))
+            off += (s // p) ** 2
+    T = off
+    tokens = torch.zeros(T, C * p * p, device=cuda, dtype=torch.bfloat16)
+    in_ptr = torch.tensor(ptrs, dtype=torch.int64).cuda()
+    d = torch.tensor(desc, dtype=torch.int32).cuda()
+    ops.sd3_patchify(in_ptr, d, len(ptrs), (128 // p) ** 2, C, p, tokens)
+    # oracle: conv im2col order (c, py, px), tokens row-major over (h, w), latents back to back
+    ref = torch.cat([torch.nn.functional.unfold(v, kernel_size=p, stride=p).transpose(1, 2).reshape(-1, C * p * p)
+                     for v in lat.values()])
+    assert torch.equal(tokens.float().cpu(), ref)
+    # reference chunking (split_sample_sd3) of these token rows is a pure reshape of the buffer
+    from oracle import pack as opack
+    per_res = {}
+    o = 0
+    for r, n, s in spec:
+        S = (s // p) ** 2
+        per_res[r] = ref[o:o + n * S].reshape(n, S, -1).numpy()
+        o += n * S
+    chunks, lat_off, _ = opack.split_sample_sd3(per_res)
+    assert np.array_equal(chunks.reshape(T, -1), tokens.float().cpu().numpy())
+    # scatter: unpatchify layout is (py, px, c)
+    tok2 = torch.randint(-120, 120, (T, p * p * C), generator=g).float()
+    outs = {r: torch.zeros_like(v) for r, v in dev_lat.items()}
+    optr = torch.tensor([outs[r][i].data_ptr() for r, n, s in spec for i in range(n)], dtype=torch.int64).cuda()
+    ops.sd3_unpatchify(tok2.cuda().bfloat16(), d, len(ptrs), (128 // p) ** 2, C, p, optr)
+    o = 0
+    for r, n, s in spec:
+        h = s // p
+        x = tok2[o:o + n * h * h].reshape(n, h, h, p, p, C)
+        x = torch.einsum("nhwpqc->nchpwq", x).reshape(n, C, s, s)
+        assert torch.equal(outs[r].float().cpu(), x)
+        o += n * h * h
+
+
+def _desc(shapes):
+    off, rows = 0, []
+    for n in shapes:
+        rows.append((off, n))
+        off += n
+    return rows, off
+
+
+def test_flow_match_step_matches_reference_golden(cuda):
+    from oracle import schedulers as osch
+    from sduss_b200 import ops
+    z = np.load(os.path.join(G, "sched_flow_match.npz"))
+    steps, idx = z["bf16_steps"], z["bf16_idx"]
+    x = torch.from_numpy(z["bf16_x"]).cuda().bfloat16()
+    v = torch.from_numpy(z["bf16_v"]).cuda().bfloat16()
+    R, n = x.shape[0], x[0].numel()
+    tabs = [osch.flow_match_sigmas(int(s))[0] for s in steps]
+    sig = torch.tensor([[t[i], t[i + 1]] for t, i in zip(tabs, idx)], dtype=torch.float32).cuda()
+    desc = torch.tensor([[r * n, n, 0, r * n] for r in range(R)], dtype=torch.int64).cuda()
+    out = torch.empty_like(x)
+    ops.cfg_scheduler_step(v, x, out, desc, sig, R, n, 1.0, False, 0)
+    assert torch.equal(out.float().cpu(), torch.from_numpy(z["bf16_prev"]))
+
+
+def test_euler_step_and_scale_match_reference_golden(cuda):
+    from oracle import schedulers as osch
+    from sduss_b200 import ops
+    z = np.load(os.path.join(G, "sched_euler.npz"))
+    for mode, pt in ((1, "epsilon"), (2, "v_prediction")):
+        tag = pt + "_bf16"
+        steps, idx = z[tag + "_steps"], z[tag + "_idx"]
+        x = torch.from_numpy(z[tag + "_x"]).cuda().bfloat16()
+        e = torch.from_numpy(z[tag + "_eps"]).cuda().bfloat16()
+        R, n = x.shape[0], x[0].numel()
+        tabs = [osch.euler_sigmas(int(s))[0] for s in steps]
+        sig = torch.tensor([[t[i], t[i + 1]] for t, i in zip(tabs, idx)], dtype=torch.float32).cuda()
+        desc = torch.tensor([[r * n, n, 0, r * n] for r in range(R)], dtype=torch.int64).cuda()
+        out = torch.empty_like(x)
+        ops.cfg_scheduler_step(e, x, out, desc, sig, R, n, 1.0, False, mode)
+        assert torch.equal(out.float().cpu(), torch.from_numpy(z[tag + "_prev"])), pt
+        # scale_model_input on the CFG-duplicated batch [x, x]
+        xin = torch.cat([x, x]).contiguous()
+        d2 = torch.tensor([[l * n, n] for l in range(2 * R)], dtype=torch.int64).cuda()
+        s2 = torch.cat([sig[:, 0], sig[:, 0]]).contiguous()
+        y = torch.empty_like(xin)
+        ops.euler_scale_input(xin, y, d2, s2, 2 * R, n)
+        assert torch.equal(y.float().cpu(), torch.from_numpy(z[tag + "_scaled"])), pt
+
+
+def test_cfg_combine_matches_torch_bf16(cuda):
+    from oracle import schedulers as osch
+    from sduss_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    R, n = 3, 16 * 64 * 64
+    eps = torch.randn(2 * R, n, generator=g).cuda().bfloat16()
+    x = torch.randn(R, n, generator=g).cuda().bfloat16()
+    sig = torch.tensor([[1.0, 0.9], [0.5, 0.45], [0.1, 0.0]], dtype=torch.float32).cuda()
+    desc = torch.tensor([[r * n, n, r * n, (R + r) * n] for r in range(R)], dtype=torch.int64).cuda()
+    out = torch.empty_like(x)
+    ops.cfg_scheduler_step(eps, x, out, desc, sig, R, n, 7.0, True, 0)
+    comb = osch.cfg_combine(eps.cpu(), 7.0)  # bf16 tensor ops, as the reference pipeline does
+    ref = osch.flow_match_batch_step(comb, x.cpu(), sig[:, 0].cpu(), sig[:, 1].cpu())
+    assert torch.equal(out.cpu(), ref)
