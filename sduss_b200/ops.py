@@ -13,6 +13,23 @@ from ._lib import AttnSource, EpilogueDesc, check, lib
 EPI_BIAS, EPI_GELU_TANH, EPI_GATE_RESID, EPI_QK_RMSNORM, EPI_GEGLU, EPI_ROWVEC = range(6)
 
 
+# Launch accounting (bench.py reads these): every wrapper below is exactly one kernel launch of
+# libsduss_b200.so. When `profile` is a dict, per-launch CUDA events are recorded by kernel name.
+launch_count = 0
+profile = None
+
+
+def _count(name):
+    global launch_count
+    launch_count += 1
+    if profile is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        profile.setdefault(name, []).append(ev)
+        ev[0].record()
+        return ev[1]
+    return None
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -50,8 +67,11 @@ def gemm(a, w, out=None, *, epi=EPI_BIAS, bias=None, resid=None, gate=None, row_
     d.rms_wq, d.rms_wk = _ptr(rms_wq), _ptr(rms_wk)
     d.rms_q_cols, d.rms_k_cols = rms_q_cols, rms_k_cols
     d.rms_eps, d.q_scale = rms_eps, q_scale
+    _ev = _count("b200_gemm_bf16")
     check(lib.b200_gemm_bf16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), M, N, K, epi,
                              ctypes.byref(d), _stream()), "b200_gemm_bf16")
+    if _ev is not None:
+        _ev.record()
     return out
 
 
@@ -92,10 +112,13 @@ def build_attn_plan(seqs, device):
 
 
 def attn_varlen(src_a, src_b, seq_table, work_items, n_items, n_heads, scale):
+    _ev = _count("b200_attn_varlen_bf16")
     check(lib.b200_attn_varlen_bf16(ctypes.byref(src_a),
                                     ctypes.byref(src_b) if src_b is not None else None,
                                     _ptr(seq_table), _ptr(work_items), n_items, n_heads,
                                     ctypes.c_float(scale), _stream()), "b200_attn_varlen_bf16")
+    if _ev is not None:
+        _ev.record()
 
 
 # ------------------------------------------------------------------ HBM-bound kernels
@@ -104,11 +127,14 @@ def layernorm_mod(x, y, *, eps, gamma=None, beta=None, mod=None, row_group=None,
     """y = LN(x)[*gamma+beta][*(1+mod[g,scale_col:])+mod[g,shift_col:]]; optional y2."""
     _req(x), _req(y)
     T, D = x.shape
+    _ev = _count("b200_layernorm_mod_bf16")
     check(lib.b200_layernorm_mod_bf16(
         _ptr(x), x.stride(0), T, D, ctypes.c_float(eps), _ptr(gamma), _ptr(beta), _ptr(mod),
         (mod.stride(0) if mod is not None else 0), _ptr(row_group), shift_col, scale_col,
         _ptr(y), y.stride(0), shift2_col, scale2_col, _ptr(y2),
         (y2.stride(0) if y2 is not None else 0), _stream()), "b200_layernorm_mod_bf16")
+    if _ev is not None:
+        _ev.record()
     return y
 
 
@@ -116,7 +142,10 @@ def silu(x, y=None):
     _req(x)
     assert x.is_contiguous()
     y = torch.empty_like(x) if y is None else y
+    _ev = _count("b200_silu_bf16")
     check(lib.b200_silu_bf16(_ptr(x), _ptr(y), x.numel(), _stream()), "b200_silu_bf16")
+    if _ev is not None:
+        _ev.record()
     return y
 
 
@@ -125,28 +154,41 @@ def timestep_embedding(t, dim, out=None):
     _req(t, torch.float32)
     n = t.numel()
     out = torch.empty((n, dim), device=t.device, dtype=torch.bfloat16) if out is None else out
-    check(lib.b200_timestep_embedding(_ptr(t), n, dim, _ptr(out), out.stride(0), _stream()),
-          "b200_timestep_embedding")
+    _ev = _count("b200_timestep_embedding")
+    check(lib.b200_timestep_embedding(_ptr(t), n, dim, _ptr(out), out.stride(0), _stream()), "b200_timestep_embedding")
+    if _ev is not None:
+        _ev.record()
     return out
 
 
 def sd3_patchify(lat_ptr, desc, n_latents, max_tokens, C, p, tokens):
+    _ev = _count("b200_sd3_patchify")
     check(lib.b200_sd3_patchify(_ptr(lat_ptr), _ptr(desc), n_latents, max_tokens, C, p,
                                 _ptr(tokens), tokens.stride(0), _stream()), "b200_sd3_patchify")
+    if _ev is not None:
+        _ev.record()
 
 
 def sd3_unpatchify(tokens, desc, n_latents, max_tokens, C, p, out_ptr):
+    _ev = _count("b200_sd3_unpatchify")
     check(lib.b200_sd3_unpatchify(_ptr(tokens), tokens.stride(0), _ptr(desc), n_latents,
-                                  max_tokens, C, p, _ptr(out_ptr), _stream()),
-          "b200_sd3_unpatchify")
+                                  max_tokens, C, p, _ptr(out_ptr), _stream()), "b200_sd3_unpatchify")
+    if _ev is not None:
+        _ev.record()
 
 
 def cfg_scheduler_step(eps, x, out, desc, sigmas, n_requests, max_elems, guidance, cfg, mode):
+    _ev = _count("b200_cfg_scheduler_step")
     check(lib.b200_cfg_scheduler_step(_ptr(eps), _ptr(x), _ptr(out), _ptr(desc), _ptr(sigmas),
                                       n_requests, max_elems, ctypes.c_float(guidance), int(cfg),
                                       mode, _stream()), "b200_cfg_scheduler_step")
+    if _ev is not None:
+        _ev.record()
 
 
 def euler_scale_input(x, y, desc, sigmas, n_latents, max_elems):
+    _ev = _count("b200_euler_scale_input")
     check(lib.b200_euler_scale_input(_ptr(x), _ptr(y), _ptr(desc), _ptr(sigmas), n_latents,
                                      max_elems, _stream()), "b200_euler_scale_input")
+    if _ev is not None:
+        _ev.record()

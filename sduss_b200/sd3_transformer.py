@@ -74,8 +74,19 @@ class _Plan:
         self.max_tokens = max(S)
         bf = dict(device=dev, dtype=torch.bfloat16)
         # static input / output staging per resolution (stable pointers -> graph-capturable)
-        self.stage_in = {res: torch.empty((n, cfg.in_channels, h, w), **bf) for res, n, h, w in comp}
-        self.stage_out = {res: torch.empty((n, cfg.out_channels, h, w), **bf) for res, n, h, w in comp}
+        # (one flat allocation each, per-resolution views: the fused CFG + scheduler kernel
+        # addresses predictions by element offset from flat_out)
+        numel_in = [n * cfg.in_channels * h * w for _, n, h, w in comp]
+        numel_out = [n * cfg.out_channels * h * w for _, n, h, w in comp]
+        self.flat_in = torch.empty((sum(numel_in),), **bf)
+        self.flat_out = torch.empty((sum(numel_out),), **bf)
+        self.stage_in, self.stage_out, self.out_elem_off = {}, {}, {}
+        oi = oo = 0
+        for (res, n, h, w), ni, no in zip(comp, numel_in, numel_out):
+            self.stage_in[res] = self.flat_in[oi:oi + ni].view(n, cfg.in_channels, h, w)
+            self.stage_out[res] = self.flat_out[oo:oo + no].view(n, cfg.out_channels, h, w)
+            self.out_elem_off[res] = oo
+            oi, oo = oi + ni, oo + no
         in_ptr, out_ptr, desc = [], [], []
         for l, (res, i, ht, wt) in enumerate(lat):
             in_ptr.append(self.stage_in[res][i].data_ptr())

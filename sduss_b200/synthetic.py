@@ -1,0 +1,145 @@
+"""Synthetic requests shaped like sduss' RunnerRequest (worker/runner/wrappers.py:19-36) for
+tests, smoke() and bench.py: random latents / prompt embeddings (no text encoders, no VAE --
+prepare and post stages are out of scope), per-request scheduler state."""
+from types import SimpleNamespace
+from typing import Dict, List
+
+import torch
+
+
+def make_sd3_requests(cfg, spec: Dict[str, int], steps: int, scheduler, device, ctx_len=333,
+                      seed=0, dtype=torch.bfloat16, pin_host=False) -> Dict[str, List]:
+    """spec: resolution -> number of requests. Returns dict resolution -> [request]."""
+    g = torch.Generator().manual_seed(seed)
+    reqs, all_reqs, rid = {}, [], 0
+    for res, n in spec.items():
+        side = int(res) // 8
+        reqs[res] = []
+        for _ in range(n):
+            def rnd(*shape):
+                t = torch.randn(*shape, generator=g).to(dtype)
+                if pin_host:
+                    return t.pin_memory()
+                return t.to(device)
+            r = SimpleNamespace(
+                request_id=rid,
+                sampling_params=SimpleNamespace(
+                    num_inference_steps=steps, resolution=int(res),
+                    latents=rnd(1, cfg.in_channels, side, side),
+                    prompt_embeds=rnd(1, ctx_len, cfg.joint_attention_dim),
+                    negative_prompt_embeds=rnd(1, ctx_len, cfg.joint_attention_dim)),
+                prepare_output=SimpleNamespace(
+                    pooled_prompt_embeds=rnd(1, cfg.pooled_projection_dim),
+                    negative_pooled_prompt_embeds=rnd(1, cfg.pooled_projection_dim)),
+                scheduler_states=None)
+            rid += 1
+            reqs[res].append(r)
+            all_reqs.append(r)
+    scheduler.batch_set_timesteps(all_reqs, device=device)
+    return reqs
+
+
+def make_sdxl_requests(cfg, spec: Dict[str, int], steps: int, scheduler, device, seed=0,
+                       dtype=torch.bfloat16, pin_host=False) -> Dict[str, List]:
+    g = torch.Generator().manual_seed(seed)
+    reqs, all_reqs, rid = {}, [], 0
+    for res, n in spec.items():
+        side = int(res) // 8
+        reqs[res] = []
+        for _ in range(n):
+            def rnd(*shape):
+                t = torch.randn(*shape, generator=g).to(dtype)
+                if pin_host:
+                    return t.pin_memory()
+                return t.to(device)
+            ids = torch.tensor([[1024., 1024., 0., 0., 1024., 1024.]]).to(dtype)  # deviation D3
+            ids = ids.pin_memory() if pin_host else ids.to(device)
+            r = SimpleNamespace(
+                request_id=rid,
+                sampling_params=SimpleNamespace(
+                    num_inference_steps=steps, resolution=int(res),
+                    latents=rnd(1, cfg.in_channels, side, side),
+                    prompt_embeds=rnd(1, cfg.context_len, cfg.cross_attention_dim),
+                    negative_prompt_embeds=rnd(1, cfg.context_len, cfg.cross_attention_dim)),
+                prepare_output=SimpleNamespace(
+                    pooled_prompt_embeds=rnd(1, cfg.pooled_dim),
+                    negative_pooled_prompt_embeds=rnd(1, cfg.pooled_dim),
+                    add_time_ids=ids, negative_add_time_ids=ids.clone()),
+                scheduler_states=None)
+            rid += 1
+            reqs[res].append(r)
+            all_reqs.append(r)
+    scheduler.batch_set_timesteps(all_reqs, device=device)
+    # SDXL pipelines scale the initial noise by init_noise_sigma (prepare stage)
+    for r in all_reqs:
+        r.sampling_params.latents = (r.sampling_params.latents.float() * scheduler.init_noise_sigma).to(dtype)
+        if pin_host:
+            r.sampling_params.latents = r.sampling_params.latents.pin_memory()
+    return reqs
+
+
+# ---------------------------------------------------------------------------------------
+# Random-init weights under diffusers' state-dict names, generated on `device` (there is no
+# network for checkpoints). Matrices ~ N(0, 1/fan_in) so activations stay O(1).
+# ---------------------------------------------------------------------------------------
+def _sincos_2d(embed_dim, grid_size, base_size, device):
+    coords = torch.arange(grid_size, dtype=torch.float64, device=device) / (grid_size / base_size)
+    gw, gh = torch.meshgrid(coords, coords, indexing="xy")
+
+    def one(pos, dim):
+        omega = torch.arange(dim // 2, dtype=torch.float64, device=device) / (dim / 2.0)
+        out = pos.reshape(-1)[:, None] * (1.0 / 10000 ** omega)[None]
+        return torch.cat([torch.sin(out), torch.cos(out)], dim=1)
+    return torch.cat([one(gw, embed_dim // 2), one(gh, embed_dim // 2)], dim=1).float()
+
+
+def random_sd3_state_dict(cfg, device, seed=0, dtype=torch.bfloat16):
+    g = torch.Generator(device=device).manual_seed(seed)
+    sd = {}
+    D = cfg.inner_dim
+    hd = cfg.attention_head_dim
+
+    def lin(name, fin, fout, gain=1.0):
+        sd[name + ".weight"] = (torch.randn(fout, fin, generator=g, device=device) * (gain / fin ** 0.5)).to(dtype)
+        sd[name + ".bias"] = (torch.randn(fout, generator=g, device=device) * 0.02).to(dtype)
+
+    def rms(name):
+        sd[name + ".weight"] = (1.0 + 0.1 * torch.randn(hd, generator=g, device=device)).to(dtype)
+
+    p = cfg.patch_size
+    sd["pos_embed.proj.weight"] = (torch.randn(D, cfg.in_channels, p, p, generator=g, device=device)
+                                   / (cfg.in_channels * p * p) ** 0.5).to(dtype)
+    sd["pos_embed.proj.bias"] = (torch.randn(D, generator=g, device=device) * 0.02).to(dtype)
+    sd["pos_embed.pos_embed"] = _sincos_2d(D, cfg.pos_embed_max_size, cfg.sample_size // p, device).unsqueeze(0)
+    lin("time_text_embed.timestep_embedder.linear_1", 256, D)
+    lin("time_text_embed.timestep_embedder.linear_2", D, D)
+    lin("time_text_embed.text_embedder.linear_1", cfg.pooled_projection_dim, D)
+    lin("time_text_embed.text_embedder.linear_2", D, D)
+    lin("context_embedder", cfg.joint_attention_dim, cfg.caption_projection_dim)
+    for i in range(cfg.num_layers):
+        b = f"transformer_blocks.{i}"
+        dual = i in cfg.dual_attention_layers
+        last = i == cfg.num_layers - 1
+        lin(b + ".norm1.linear", D, (9 if dual else 6) * D, 0.5)
+        lin(b + ".norm1_context.linear", D, (2 if last else 6) * D, 0.5)
+        for n in ("to_q", "to_k", "to_v", "add_q_proj", "add_k_proj", "add_v_proj"):
+            lin(f"{b}.attn.{n}", D, D)
+        lin(b + ".attn.to_out.0", D, D)
+        if not last:
+            lin(b + ".attn.to_add_out", D, D)
+        for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"):
+            rms(f"{b}.attn.{n}")
+        if dual:
+            for n in ("to_q", "to_k", "to_v"):
+                lin(f"{b}.attn2.{n}", D, D)
+            lin(b + ".attn2.to_out.0", D, D)
+            rms(b + ".attn2.norm_q")
+            rms(b + ".attn2.norm_k")
+        lin(b + ".ff.net.0.proj", D, 4 * D)
+        lin(b + ".ff.net.2", 4 * D, D)
+        if not last:
+            lin(b + ".ff_context.net.0.proj", D, 4 * D)
+            lin(b + ".ff_context.net.2", 4 * D, D)
+    lin("norm_out.linear", D, 2 * D, 0.5)
+    lin("proj_out", D, p * p * cfg.out_channels)
+    return sd
