@@ -157,6 +157,65 @@ int b200_cfg_scheduler_step(const void* eps, const void* x, void* out, const int
 int b200_euler_scale_input(const void* x, void* y, const int64_t* desc, const float* sigmas,
                            int n_latents, long long max_elems, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * SDXL UNet path, packed NHWC layout [sum_i H_i*W_i, C] bf16.
+ * ---------------------------------------------------------------------------------------- */
+
+/* 3x3 convolution, padding 1, stride 1 or 2, as an implicit GEMM on tcgen05 (TMA box loads
+ * with out-of-bounds zero fill provide the padding: no halo exchange). Replaces F.conv2d on
+ * haloed patches + the halo kernels: sduss modules/resnet.py:102-133,262-278,350-378 and
+ * kernels/norm_silu_concat.cu:248 (MockNormSiluConcat / get_adjacency).
+ * Step 1 (once per batch composition, host): encode one input tensor map per latent.
+ *   in_desc_host: HOST int32 [n][4] = {input row offset, Hin, Win, 0}; maps_host: HOST buffer
+ *   of n * 128 bytes, to be uploaded to a 64-byte-aligned device buffer. */
+int b200_conv3x3_encode_maps(const void* x, int ldx, int Cin, const int32_t* in_desc_host,
+                             int n_latents, int stride, void* maps_host);
+/* Step 2 (per call): tiles_dev int32 [n_mtiles][4] = {latent, y0, x0, 0}: 16x8 (rows x cols)
+ * OUTPUT pixel blocks; out_lat_dev int32 [n][4] = {output row offset, Hout, Wout, 0};
+ * Wt: [Cout, 9*Cin] bf16 with K index = (ky*3 + kx)*Cin + c; M_total = rows of the output
+ * buffer. Epilogue modes: B200_EPI_BIAS, B200_EPI_ROWVEC (+ time-embedding vector of the
+ * request), B200_EPI_GATE_RESID (+ residual). Cin % 64 == 0, Cout % 8 == 0. */
+int b200_conv3x3_bf16(const void* in_maps_dev, const int32_t* tiles_dev, int n_mtiles,
+                      const int32_t* out_lat_dev, int Cin, int Cout, int stride, const void* Wt,
+                      int M_total, int epi_mode, const B200EpilogueDesc* ep, void* stream);
+
+/* Per-request GroupNorm (+ optional SiLU) with exact whole-latent statistics. Supersedes the
+ * reference's native kernels RowwiseMoments / GetFullMeanAndRstd / NormSiluConcat
+ * (kernels/norm_silu_concat.cu:41,361,87; pybind `groupnorm`, norm_silu_concat.cpp:66-86)
+ * without their approximated variance (D1), in-place race and per-call device syncs.
+ * Every latent's pixel count must be a multiple of 64. lat_chunks: int32 [n][4] = {first
+ * 64-row chunk, number of chunks, 0, 0}; workspace: b200_groupnorm_workspace_bytes() bytes. */
+long long b200_groupnorm_workspace_bytes(long long total_rows, int n_latents);
+int b200_groupnorm_nhwc_bf16(const void* x, int ldx, long long T, int C, int groups, float eps,
+                             const void* gamma, const void* beta, const int32_t* row_group,
+                             const int32_t* lat_chunks, int n_latents, int silu, void* y, int ldy,
+                             void* workspace, void* stream);
+
+/* SDXL pack: NCHW latents -> im2col rows of the 3x3/pad-1 conv_in (K = 9*C padded to ldo with
+ * zeros): out[row_i + y*W + x, c*9 + ky*3 + kx]. Replaces split_sample's haloed windows
+ * (modules/unet.py:104-184). desc int32 [n][4] = {row offset, H, W, 0}. */
+int b200_pack_im2col3x3(const uint64_t* lat_ptr, const int32_t* desc, int n_latents,
+                        int max_pixels, int C, void* out, int ldo, void* stream);
+/* SDXL scatter: NHWC rows (first C columns of x) -> NCHW latents (concat_sample,
+ * modules/unet.py:187-202). */
+int b200_scatter_nchw(const void* x, int ldx, const int32_t* desc, int n_latents, int max_pixels,
+                      int C, const uint64_t* out_ptr, void* stream);
+/* Nearest 2x upsample on the packed layout (modules/resnet.py:316). */
+int b200_upsample2x_nhwc(const void* x, int ldx, const int32_t* in_desc, const int32_t* out_desc,
+                         int n_latents, int max_out_pixels, int C, void* y, int ldy, void* stream);
+/* dst[:, :cols] = src[:, :cols] with independent row strides (skip-connection concat). */
+int b200_copy_cols_bf16(const void* src, int lds, void* dst, int ldd, long long T, int cols,
+                        void* stream);
+
+/* The reference's own patch format, index-exact (interoperability / parity fixtures):
+ * split_sample (modules/unet.py:104-184): NCHW latents -> [P, C, ps+2, ps+2] haloed windows;
+ * concat_sample (modules/unet.py:187-202): [P, C, ps, ps] -> NCHW latents.
+ * ldesc int32 [n][4] = {0, H, W, 0}; pdesc int32 [P][4] = {latent, patch row, patch col, 0}. */
+int b200_split_patches(const uint64_t* lat_ptr, const int32_t* ldesc, const int32_t* pdesc,
+                       int n_patches, int C, int ps, void* out, void* stream);
+int b200_concat_patches(const void* patches, const int32_t* ldesc, const int32_t* pdesc,
+                        int n_patches, int C, int ps, const uint64_t* out_ptr, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

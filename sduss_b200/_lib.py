@@ -80,6 +80,20 @@ SIGNATURES = {
                                 ctypes.c_longlong, c_float, c_int, c_int, c_void_p],
     "b200_euler_scale_input": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, ctypes.c_longlong,
                                c_void_p],
+    "b200_conv3x3_encode_maps": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p],
+    "b200_conv3x3_bf16": [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
+                          c_int, c_int, ctypes.POINTER(EpilogueDesc), c_void_p],
+    "b200_groupnorm_nhwc_bf16": [c_void_p, c_int, ctypes.c_longlong, c_int, c_int, c_float,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                 c_int, c_void_p, c_void_p],
+    "b200_pack_im2col3x3": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
+    "b200_scatter_nchw": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "b200_upsample2x_nhwc": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                             c_int, c_void_p],
+    "b200_copy_cols_bf16": [c_void_p, c_int, c_void_p, c_int, ctypes.c_longlong, c_int, c_void_p],
+    "b200_split_patches": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "b200_concat_patches": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                            c_void_p],
 }
 
 
@@ -88,6 +102,8 @@ def _bind():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = c_int
+    lib.b200_groupnorm_workspace_bytes.argtypes = [ctypes.c_longlong, c_int]
+    lib.b200_groupnorm_workspace_bytes.restype = ctypes.c_longlong
 
 
 _bind()

@@ -1,0 +1,275 @@
+// 3x3 convolution (padding 1, stride 1 or 2) over packed NHWC activations of a mixed-resolution
+// batch as an implicit GEMM on tcgen05 tensor cores. Replaces F.conv2d on haloed 32x32 patches
+// plus the halo-exchange kernels of the reference (sduss/model_executor/modules/resnet.py:
+// 102-133,262-278,350-378 and kernels/norm_silu_concat.cu:248 "get_adjacency").
+//
+// Layout: activations are [sum_i H_i*W_i, C] bf16 (pixel rows of all latents back to back).
+// One 128-row M tile = a 16x8 (rows x cols) pixel block of ONE latent. For filter tap (dy,dx)
+// and channel block c0 the A tile is ONE TMA box load {64 ch, 8 px, 16 rows} from that
+// latent's tensor map at coordinates (c0, x0+dx-1, y0+dy-1); TMA zero-fills out-of-bounds
+// pixels, which IS the conv padding -- no halo exchange, no padded copies, exact corners.
+// K loop = 9 taps x Cin/64 channel blocks, accumulating in TMEM. The stride-2 variant views the
+// input as [H/2, 2, W/2, 2, C] through a 5-D tensor map so each tap is again a dense box.
+// Same warp roles / pipeline / epilogues as gemm_sm100.cu.
+#include "../../include/sduss_b200.h"
+#include "epilogue.cuh"
+#include "host_util.h"
+
+namespace b200 {
+
+constexpr int CV_BM = 128, CV_BK = 64, CV_TW = 8, CV_TH = 16, CV_THREADS = 256;
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = CV_BM * CV_BK * 2;
+  static constexpr int kBBytes = BN * CV_BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kTmemCols = 2 * BN;
+};
+
+struct ConvArgs {
+  const CUtensorMap* in_maps;  // [n_latents] device array, 64-byte aligned entries
+  const int4* tiles;           // [n_mtiles] {latent, y0, x0, 0} in OUTPUT pixel coordinates
+  const int4* lat;             // [n_latents] {output row offset, Hout, Wout, 0}
+  int n_mtiles, Cin, Cout, stride;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, int M_total) {
+  using Cfg = ConvCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* smemA = smem;
+  uint8_t* smemB = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::kStages;
+  uint64_t* tfull = bars + 2 * Cfg::kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_n = (a.Cout + BN - 1) / BN;
+  const int num_tiles = a.n_mtiles * tiles_n;
+  const int cblocks = a.Cin / CV_BK;
+  const int num_kb = 9 * cblocks;
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmW);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int4 tl = a.tiles[t / tiles_n];
+      const int n0 = (t % tiles_n) * BN;
+      const CUtensorMap* im = a.in_maps + tl.x;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * CV_BK;
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (lane == 0) {
+          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+          void* dstA = smemA + stage * Cfg::kABytes;
+          if (a.stride == 1) {
+            tma_load_3d(dstA, im, &full[stage], c0, tl.z + dx, tl.y + dy);
+          } else {
+            // input pixel (2y+dy, 2x+dx) = (parity, half index): -1 -> (1, i-1); 0 -> (0, i); 1 -> (1, i)
+            const int py = dy == 0 ? 0 : 1, px = dx == 0 ? 0 : 1;
+            tma_load_5d(dstA, im, &full[stage], c0, px, tl.z + (dx < 0 ? -1 : 0), py,
+                        tl.y + (dy < 0 ? -1 : 0));
+          }
+          tma_load_2d(smemB + stage * Cfg::kBBytes, &tmW, &full[stage], kb * CV_BK, n0);
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(CV_BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t da = make_sdesc_sw128(smem_u32(smemA + stage * Cfg::kABytes));
+          const uint64_t db = make_sdesc_sw128(smem_u32(smemB + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < CV_BK / 16; ++k)
+            umma_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc,
+                    (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (kb == num_kb - 1) umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int4 tl = a.tiles[t / tiles_n];
+      const int4 ld = a.lat[tl.x];
+      const int n0 = (t % tiles_n) * BN;
+      mbar_wait(&tfull[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const int r = q * 32 + lane;              // row in tile: (r / 8, r % 8) pixel in the block
+      const int y = tl.y + r / CV_TW, x = tl.z + r % CV_TW;
+      const int row = (y < ld.y && x < ld.z) ? ld.x + y * ld.z + x : M_total;
+      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        float v[64];
+        tmem_ld32(t_row + c * 64, reinterpret_cast<uint32_t*>(v));
+        tmem_ld32(t_row + c * 64 + 32, reinterpret_cast<uint32_t*>(v) + 32);
+        tmem_wait_ld();
+        epilogue_chunk64<EPI>(e, v, row, n0 + c * 64, M_total, a.Cout);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN, int EPI>
+static int launch_conv(const CUtensorMap& tmW, const ConvArgs& a, const EpiArgs& e, int M_total,
+                       int num_sms, cudaStream_t stream) {
+  using Cfg = ConvCfg<BN>;
+  auto kern = conv3x3_kernel<BN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t err =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (err != cudaSuccess) return static_cast<int>(err);
+    configured = true;
+  }
+  const int tiles = a.n_mtiles * ((a.Cout + BN - 1) / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, CV_THREADS, Cfg::kSmemBytes, stream>>>(tmW, a, e, M_total);
+  return launch_status();
+}
+
+template <int BN>
+static int dispatch_conv(int epi, const CUtensorMap& tmW, const ConvArgs& a, const EpiArgs& e,
+                         int M_total, int sms, cudaStream_t st) {
+  switch (epi) {
+    case EPI_BIAS: return launch_conv<BN, EPI_BIAS>(tmW, a, e, M_total, sms, st);
+    case EPI_GATE_RESID: return launch_conv<BN, EPI_GATE_RESID>(tmW, a, e, M_total, sms, st);
+    case EPI_ROWVEC: return launch_conv<BN, EPI_ROWVEC>(tmW, a, e, M_total, sms, st);
+    default: return B200_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// Encodes one input tensor map per latent into `maps_host` (host memory, n_latents entries of
+// 128 bytes); the caller uploads them to a 64-byte-aligned device buffer once per batch
+// composition. in_desc: int32 [n][4] = {input row offset, Hin, Win, 0}.
+extern "C" int b200_conv3x3_encode_maps(const void* x, int ldx, int Cin, const int32_t* in_desc_host,
+                                        int n_latents, int stride, void* maps_host) {
+  if (!x || !in_desc_host || !maps_host || n_latents <= 0 || (Cin % CV_BK) || (ldx & 7) ||
+      (stride != 1 && stride != 2))
+    return B200_ERR_INVALID;
+  CUtensorMap* out = static_cast<CUtensorMap*>(maps_host);
+  for (int i = 0; i < n_latents; ++i) {
+    const int row0 = in_desc_host[4 * i], H = in_desc_host[4 * i + 1], W = in_desc_host[4 * i + 2];
+    const char* base = static_cast<const char*>(x) + size_t(row0) * ldx * 2;
+    int rc;
+    if (stride == 1) {
+      uint64_t d[3] = {uint64_t(Cin), uint64_t(W), uint64_t(H)};
+      uint64_t s[2] = {uint64_t(ldx) * 2, uint64_t(ldx) * 2 * W};
+      uint32_t b[3] = {CV_BK, CV_TW, CV_TH};
+      rc = get_tmap_bf16_sw128(&out[i], base, 3, d, s, b);
+    } else {
+      if ((H & 1) || (W & 1)) return B200_ERR_INVALID;
+      uint64_t d[5] = {uint64_t(Cin), 2, uint64_t(W / 2), 2, uint64_t(H / 2)};
+      uint64_t s[4] = {uint64_t(ldx) * 2, uint64_t(ldx) * 4, uint64_t(ldx) * 2 * W,
+                       uint64_t(ldx) * 4 * W};
+      uint32_t b[5] = {CV_BK, 1, CV_TW, 1, CV_TH};
+      rc = get_tmap_bf16_sw128(&out[i], base, 5, d, s, b);
+    }
+    if (rc) return rc;
+  }
+  return B200_OK;
+}
+
+extern "C" int b200_conv3x3_bf16(const void* in_maps_dev, const int32_t* tiles_dev, int n_mtiles,
+                                 const int32_t* out_lat_dev, int Cin, int Cout, int stride,
+                                 const void* Wt, int M_total, int epi_mode,
+                                 const B200EpilogueDesc* ep, void* stream_) {
+  if (!in_maps_dev || !tiles_dev || !out_lat_dev || !Wt || !ep || !ep->C || n_mtiles <= 0)
+    return B200_ERR_INVALID;
+  if ((Cin % CV_BK) || (Cout & 7) || (ep->ldc & 7) || (stride != 1 && stride != 2))
+    return B200_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(in_maps_dev) & 63) != 0) return B200_ERR_INVALID;
+  if (epi_mode == EPI_ROWVEC && (!ep->rowvec || !ep->row_group)) return B200_ERR_INVALID;
+  const int sms = device_sm_count();
+  if (sms <= 0) return B200_ERR_DRIVER;
+  const long tiles256 = long(n_mtiles) * ((Cout + 255) / 256);
+  const bool bn256 = (Cout >= 256) && (tiles256 >= sms);
+  const int BN = bn256 ? 256 : 128;
+  CUtensorMap tmW;
+  uint64_t d[2] = {uint64_t(9) * Cin, uint64_t(Cout)}, s[1] = {uint64_t(9) * Cin * 2};
+  uint32_t b[2] = {CV_BK, uint32_t(BN)};
+  int rc = get_tmap_bf16_sw128(&tmW, Wt, 2, d, s, b);
+  if (rc) return rc;
+  ConvArgs a{static_cast<const CUtensorMap*>(in_maps_dev), reinterpret_cast<const int4*>(tiles_dev),
+             reinterpret_cast<const int4*>(out_lat_dev), n_mtiles, Cin, Cout, stride};
+  EpiArgs e;
+  e.C = ep->C; e.ldc = ep->ldc; e.out_fp32 = ep->out_fp32;
+  e.bias = static_cast<const __nv_bfloat16*>(ep->bias);
+  e.resid = static_cast<const __nv_bfloat16*>(ep->resid); e.ldr = ep->ldr;
+  e.gate = static_cast<const __nv_bfloat16*>(ep->gate); e.ldg = ep->ldg;
+  e.row_group = ep->row_group;
+  e.rowvec = static_cast<const __nv_bfloat16*>(ep->rowvec); e.ldv = ep->ldv;
+  e.rms_wq = nullptr; e.rms_wk = nullptr; e.rms_q_cols = 0; e.rms_k_cols = 0;
+  e.rms_eps = 0.f; e.q_scale = 1.f;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  return bn256 ? dispatch_conv<256>(epi_mode, tmW, a, e, M_total, sms, st)
+               : dispatch_conv<128>(epi_mode, tmW, a, e, M_total, sms, st);
+}

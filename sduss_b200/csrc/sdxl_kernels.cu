@@ -1,0 +1,330 @@
+// HBM-bound kernels of the SDXL UNet path on the packed NHWC layout [sum_i H_i*W_i, C]:
+// per-request GroupNorm(+SiLU), latent pack (NCHW -> im2col rows for conv_in), noise scatter
+// (NHWC -> NCHW), nearest 2x upsample, column-block copy (skip concat), and the reference's own
+// patch pack/scatter format (split_sample / concat_sample) for index-exact interoperability.
+#include "../../include/sduss_b200.h"
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ void unpack8s(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8s(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]);
+  u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]);
+  u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+// ------------------------------------------------------------------ GroupNorm
+// Exact per-request statistics over the WHOLE latent (the reference approximates the variance by
+// the mean of per-patch variances and races while doing so: kernels/norm_silu_concat.cu:361-386,
+// deviations D1 and the in-place race). Three launches:
+//   stats   : one CTA per 64-pixel chunk -> partial (sum, sumsq) per group      [chunks][G][2]
+//   finalize: one thread per (latent, group): fixed-order fp64 reduction         [L][G][2]
+//   apply   : y = (x - mean) * rstd * gamma + beta, optional SiLU, bf16
+constexpr int GN_CHUNK = 64;
+constexpr int GN_MAXG = 32;
+
+constexpr int GN_MAXC = 2560;
+
+// Deterministic: every channel's column sum over the 64 rows is owned by one lane (fixed order),
+// then one thread per group adds its channels in index order. No atomics anywhere.
+__global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* x, int ldx, int C,
+                                                       int cpg, int G, float* partial) {
+  __shared__ float ch_sum[GN_MAXC], ch_sq[GN_MAXC];
+  const int chunk = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = C >> 3;
+  const __nv_bfloat16* base = x + size_t(chunk) * GN_CHUNK * ldx;
+  for (int slot = warp; slot * 32 < nvec; slot += 8) {
+    const int vc = slot * 32 + lane;
+    if (vc < nvec) {
+      float sum[8], sq[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
+#pragma unroll 4
+      for (int r = 0; r < GN_CHUNK; ++r) {
+        float f[8];
+        unpack8s(*reinterpret_cast<const uint4*>(base + size_t(r) * ldx + vc * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          sum[j] += f[j];
+          sq[j] += f[j] * f[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ch_sum[vc * 8 + j] = sum[j];
+        ch_sq[vc * 8 + j] = sq[j];
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    float s = 0.f, q = 0.f;
+    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
+      s += ch_sum[c];
+      q += ch_sq[c];
+    }
+    partial[(size_t(chunk) * GN_MAXG + threadIdx.x) * 2] = s;
+    partial[(size_t(chunk) * GN_MAXG + threadIdx.x) * 2 + 1] = q;
+  }
+}
+
+// lat: [L][4] = {first chunk, number of chunks, 0, 0}
+__global__ void gn_finalize_kernel(const float* partial, const int4* lat, int L, int G, int cpg,
+                                   float eps, float* stats) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= L * G) return;
+  const int l = idx / G, g = idx % G;
+  const int4 d = lat[l];
+  double s = 0.0, q = 0.0;
+  for (int c = 0; c < d.y; ++c) {
+    s += double(partial[(size_t(d.x + c) * GN_MAXG + g) * 2]);
+    q += double(partial[(size_t(d.x + c) * GN_MAXG + g) * 2 + 1]);
+  }
+  const double n = double(d.y) * GN_CHUNK * cpg;
+  const double mean = s / n;
+  double var = q / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[idx * 2] = float(mean);
+  stats[idx * 2 + 1] = float(1.0 / sqrt(var + double(eps)));
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* x, int ldx, long T,
+                                                       int C, int cpg, int G, const float* stats,
+                                                       const int* row_group,
+                                                       const __nv_bfloat16* gamma,
+                                                       const __nv_bfloat16* beta, int silu,
+                                                       __nv_bfloat16* y, int ldy) {
+  const int nvec = C >> 3;
+  const long i = blockIdx.x * long(blockDim.x) + threadIdx.x;
+  if (i >= T * nvec) return;
+  const long row = i / nvec;
+  const int vc = int(i - row * nvec);
+  const float* st = stats + size_t(row_group[row]) * G * 2;
+  float f[8], ga[8], be[8];
+  unpack8s(*reinterpret_cast<const uint4*>(x + row * ldx + vc * 8), f);
+  unpack8s(*reinterpret_cast<const uint4*>(gamma + vc * 8), ga);
+  unpack8s(*reinterpret_cast<const uint4*>(beta + vc * 8), be);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (vc * 8 + j) / cpg;
+    const float mean = st[g * 2], rstd = st[g * 2 + 1];
+    float v = (f[j] - mean) * rstd * ga[j] + be[j];
+    if (silu) v = v / (1.f + __expf(-v));
+    f[j] = v;
+  }
+  *reinterpret_cast<uint4*>(y + row * ldy + vc * 8) = pack8s(f);
+}
+
+// ------------------------------------------------------------------ latent pack for conv_in
+// NCHW latent [C, H, W] bf16 -> im2col rows of the 3x3/pad-1 conv: out[row0 + y*W + x,
+// c*9 + ky*3 + kx] = lat[c, y+ky-1, x+kx-1] (0 outside), columns >= 9C are zero (K padded to
+// ldo). conv_in then is one GEMM with the [Cout, C*9] weight matrix of diffusers as is.
+// Replaces split_sample's halo windows + F.conv2d(padding=0) (modules/unet.py:104-184,344).
+// desc: [n][4] = {row offset, H, W, 0}
+__global__ void pack_im2col3x3_kernel(const unsigned long long* lat_ptr, const int4* desc, int C,
+                                      __nv_bfloat16* out, int ldo) {
+  const int l = blockIdx.y;
+  const int4 d = desc[l];
+  const int H = d.y, W = d.z;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= H * W * ldo) return;
+  const int pix = idx / ldo, k = idx % ldo;
+  float v = 0.f;
+  if (k < C * 9) {
+    const int c = k / 9, ky = (k % 9) / 3, kx = k % 3;
+    const int y = pix / W + ky - 1, x = pix % W + kx - 1;
+    if (y >= 0 && y < H && x >= 0 && x < W)
+      v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(lat_ptr[l])[(size_t(c) * H + y) * W + x]);
+  }
+  out[size_t(d.x + pix) * ldo + k] = __float2bfloat16(v);
+}
+
+// NHWC rows [T, ldx] (first C columns) -> NCHW latents (scatter of the noise prediction;
+// replaces concat_sample, modules/unet.py:187-202).
+__global__ void scatter_nchw_kernel(const __nv_bfloat16* x, int ldx, const int4* desc, int C,
+                                    const unsigned long long* out_ptr) {
+  const int l = blockIdx.y;
+  const int4 d = desc[l];
+  const int HW = d.y * d.z;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * HW) return;
+  const int c = idx / HW, pix = idx % HW;
+  reinterpret_cast<__nv_bfloat16*>(out_ptr[l])[idx] = x[size_t(d.x + pix) * ldx + c];
+}
+
+// Nearest-neighbour 2x upsample on the packed NHWC layout (F.interpolate(scale_factor=2,
+// mode="nearest"), modules/resnet.py:316). in_desc/out_desc: [n][4] = {row offset, H, W, 0}.
+__global__ void upsample2x_kernel(const __nv_bfloat16* x, int ldx, const int4* in_desc,
+                                  const int4* out_desc, int C, __nv_bfloat16* y, int ldy) {
+  const int l = blockIdx.y;
+  const int4 di = in_desc[l], dout = out_desc[l];
+  const int nvec = C >> 3;
+  const long idx = blockIdx.x * long(blockDim.x) + threadIdx.x;
+  if (idx >= long(dout.y) * dout.z * nvec) return;
+  const int pix = int(idx / nvec), vc = int(idx % nvec);
+  const int oy = pix / dout.z, ox = pix % dout.z;
+  const uint4 v = *reinterpret_cast<const uint4*>(
+      x + size_t(di.x + (oy >> 1) * di.z + (ox >> 1)) * ldx + vc * 8);
+  *reinterpret_cast<uint4*>(y + size_t(dout.x + pix) * ldy + vc * 8) = v;
+}
+
+// dst[:, dst_col : dst_col + cols] = src[:, src_col : src_col + cols]  (skip-connection concat)
+__global__ void copy_cols_kernel(const __nv_bfloat16* src, int lds, __nv_bfloat16* dst, int ldd,
+                                 long T, int cols) {
+  const int nvec = cols >> 3;
+  const long idx = blockIdx.x * long(blockDim.x) + threadIdx.x;
+  if (idx >= T * nvec) return;
+  const long row = idx / nvec;
+  const int vc = int(idx - row * nvec);
+  *reinterpret_cast<uint4*>(dst + row * ldd + vc * 8) =
+      *reinterpret_cast<const uint4*>(src + row * lds + vc * 8);
+}
+
+// ------------------------------------------------------------------ reference patch format
+// split_sample (modules/unet.py:104-184): NCHW latents -> [P, C, ps+2, ps+2] haloed windows
+// (zero outside the image), patches of a latent in row-major (h, w) order.
+// pdesc: [P][4] = {latent, patch row h, patch col w, 0}; ldesc: [n][4] = {0, H, W, 0}
+__global__ void split_patches_kernel(const unsigned long long* lat_ptr, const int4* ldesc,
+                                     const int4* pdesc, int C, int ps, __nv_bfloat16* out) {
+  const int p = blockIdx.y;
+  const int4 pd = pdesc[p];
+  const int4 ld = ldesc[pd.x];
+  const int H = ld.y, W = ld.z, pw = ps + 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * pw * pw) return;
+  const int c = idx / (pw * pw), yy = (idx / pw) % pw, xx = idx % pw;
+  const int y = pd.y * ps + yy - 1, x = pd.z * ps + xx - 1;
+  __nv_bfloat16 v = __float2bfloat16(0.f);
+  if (y >= 0 && y < H && x >= 0 && x < W)
+    v = reinterpret_cast<const __nv_bfloat16*>(lat_ptr[pd.x])[(size_t(c) * H + y) * W + x];
+  out[size_t(p) * C * pw * pw + idx] = v;
+}
+
+// concat_sample (modules/unet.py:187-202): [P, C, ps, ps] -> NCHW latents.
+__global__ void concat_patches_kernel(const __nv_bfloat16* patches, const int4* ldesc,
+                                      const int4* pdesc, int C, int ps,
+                                      const unsigned long long* out_ptr) {
+  const int p = blockIdx.y;
+  const int4 pd = pdesc[p];
+  const int4 ld = ldesc[pd.x];
+  const int H = ld.y, W = ld.z;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * ps * ps) return;
+  const int c = idx / (ps * ps), yy = (idx / ps) % ps, xx = idx % ps;
+  reinterpret_cast<__nv_bfloat16*>(out_ptr[pd.x])[(size_t(c) * H + pd.y * ps + yy) * W + pd.z * ps + xx] =
+      patches[size_t(p) * C * ps * ps + idx];
+}
+
+}  // namespace b200
+
+using namespace b200;
+typedef __nv_bfloat16 bf16;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" long long b200_groupnorm_workspace_bytes(long long total_rows, int n_latents) {
+  return (total_rows / GN_CHUNK) * GN_MAXG * 2 * 4 + (long long)n_latents * GN_MAXG * 2 * 4;
+}
+
+extern "C" int b200_groupnorm_nhwc_bf16(const void* x, int ldx, long long T, int C, int groups,
+                                        float eps, const void* gamma, const void* beta,
+                                        const int32_t* row_group, const int32_t* lat_chunks,
+                                        int n_latents, int silu, void* y, int ldy, void* workspace,
+                                        void* stream) {
+  if (!x || !y || !gamma || !beta || !row_group || !lat_chunks || !workspace || T <= 0 ||
+      (T % GN_CHUNK) || groups <= 0 || groups > GN_MAXG || (C % groups) || (C & 7) || C > GN_MAXC || (ldx & 7) ||
+      (ldy & 7))
+    return B200_ERR_INVALID;
+  const int cpg = C / groups;
+  const int chunks = int(T / GN_CHUNK);
+  float* partial = static_cast<float*>(workspace);
+  float* stats = partial + size_t(chunks) * GN_MAXG * 2;
+  gn_stats_kernel<<<chunks, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), ldx, C, cpg, groups, partial);
+  gn_finalize_kernel<<<(n_latents * groups + 127) / 128, 128, 0, ST(stream)>>>(
+      partial, reinterpret_cast<const int4*>(lat_chunks), n_latents, groups, cpg, eps, stats);
+  const long total = T * (C >> 3);
+  gn_apply_kernel<<<unsigned((total + 255) / 256), 256, 0, ST(stream)>>>(
+      static_cast<const bf16*>(x), ldx, T, C, cpg, groups, stats, row_group,
+      static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta), silu, static_cast<bf16*>(y),
+      ldy);
+  return launch_status();
+}
+
+extern "C" int b200_pack_im2col3x3(const uint64_t* lat_ptr, const int32_t* desc, int n_latents,
+                                   int max_pixels, int C, void* out, int ldo, void* stream) {
+  if (!lat_ptr || !desc || !out || n_latents <= 0 || max_pixels <= 0 || ldo < 9 * C || (ldo & 7))
+    return B200_ERR_INVALID;
+  dim3 grid((unsigned(max_pixels) * ldo + 255) / 256, n_latents);
+  pack_im2col3x3_kernel<<<grid, 256, 0, ST(stream)>>>(
+      reinterpret_cast<const unsigned long long*>(lat_ptr), reinterpret_cast<const int4*>(desc), C,
+      static_cast<bf16*>(out), ldo);
+  return launch_status();
+}
+
+extern "C" int b200_scatter_nchw(const void* x, int ldx, const int32_t* desc, int n_latents,
+                                 int max_pixels, int C, const uint64_t* out_ptr, void* stream) {
+  if (!x || !desc || !out_ptr || n_latents <= 0 || max_pixels <= 0) return B200_ERR_INVALID;
+  dim3 grid((unsigned(max_pixels) * C + 255) / 256, n_latents);
+  scatter_nchw_kernel<<<grid, 256, 0, ST(stream)>>>(
+      static_cast<const bf16*>(x), ldx, reinterpret_cast<const int4*>(desc), C,
+      reinterpret_cast<const unsigned long long*>(out_ptr));
+  return launch_status();
+}
+
+extern "C" int b200_upsample2x_nhwc(const void* x, int ldx, const int32_t* in_desc,
+                                    const int32_t* out_desc, int n_latents, int max_out_pixels,
+                                    int C, void* y, int ldy, void* stream) {
+  if (!x || !y || !in_desc || !out_desc || n_latents <= 0 || (C & 7) || (ldx & 7) || (ldy & 7))
+    return B200_ERR_INVALID;
+  dim3 grid(unsigned((long(max_out_pixels) * (C >> 3) + 255) / 256), n_latents);
+  upsample2x_kernel<<<grid, 256, 0, ST(stream)>>>(
+      static_cast<const bf16*>(x), ldx, reinterpret_cast<const int4*>(in_desc),
+      reinterpret_cast<const int4*>(out_desc), C, static_cast<bf16*>(y), ldy);
+  return launch_status();
+}
+
+extern "C" int b200_copy_cols_bf16(const void* src, int lds, void* dst, int ldd, long long T,
+                                   int cols, void* stream) {
+  if (!src || !dst || T <= 0 || cols <= 0 || (cols & 7) || (lds & 7) || (ldd & 7))
+    return B200_ERR_INVALID;
+  const long total = T * (cols >> 3);
+  copy_cols_kernel<<<unsigned((total + 255) / 256), 256, 0, ST(stream)>>>(
+      static_cast<const bf16*>(src), lds, static_cast<bf16*>(dst), ldd, T, cols);
+  return launch_status();
+}
+
+extern "C" int b200_split_patches(const uint64_t* lat_ptr, const int32_t* ldesc,
+                                  const int32_t* pdesc, int n_patches, int C, int ps, void* out,
+                                  void* stream) {
+  if (!lat_ptr || !ldesc || !pdesc || !out || n_patches <= 0) return B200_ERR_INVALID;
+  dim3 grid((unsigned(C) * (ps + 2) * (ps + 2) + 255) / 256, n_patches);
+  split_patches_kernel<<<grid, 256, 0, ST(stream)>>>(
+      reinterpret_cast<const unsigned long long*>(lat_ptr), reinterpret_cast<const int4*>(ldesc),
+      reinterpret_cast<const int4*>(pdesc), C, ps, static_cast<bf16*>(out));
+  return launch_status();
+}
+
+extern "C" int b200_concat_patches(const void* patches, const int32_t* ldesc, const int32_t* pdesc,
+                                   int n_patches, int C, int ps, const uint64_t* out_ptr,
+                                   void* stream) {
+  if (!patches || !ldesc || !pdesc || !out_ptr || n_patches <= 0) return B200_ERR_INVALID;
+  dim3 grid((unsigned(C) * ps * ps + 255) / 256, n_patches);
+  concat_patches_kernel<<<grid, 256, 0, ST(stream)>>>(
+      static_cast<const bf16*>(patches), reinterpret_cast<const int4*>(ldesc),
+      reinterpret_cast<const int4*>(pdesc), C, ps,
+      reinterpret_cast<const unsigned long long*>(out_ptr));
+  return launch_status();
+}

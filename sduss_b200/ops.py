@@ -192,3 +192,120 @@ def euler_scale_input(x, y, desc, sigmas, n_latents, max_elems):
                                      max_elems, _stream()), "b200_euler_scale_input")
     if _ev is not None:
         _ev.record()
+
+
+# ------------------------------------------------------------------ SDXL path
+def _epi_desc(out, bias=None, resid=None, gate=None, row_group=None, rowvec=None):
+    d = EpilogueDesc()
+    d.C, d.ldc, d.out_fp32 = _ptr(out), out.stride(0), 0
+    d.bias = _ptr(bias)
+    d.resid, d.ldr = _ptr(resid), (resid.stride(0) if resid is not None else 0)
+    d.gate, d.ldg = _ptr(gate), (gate.stride(0) if gate is not None else 0)
+    d.row_group = _ptr(row_group)
+    d.rowvec, d.ldv = _ptr(rowvec), (rowvec.stride(0) if rowvec is not None else 0)
+    d.rms_eps, d.q_scale = 1e-6, 1.0
+    return d
+
+
+def conv3x3_encode_maps(x, cin, in_desc_host, stride):
+    """x: packed NHWC buffer [rows, ld] (only the first `cin` columns are read).
+    in_desc_host: int32 numpy [n,4] = {input row offset, Hin, Win, 0}. Returns a device uint8
+    buffer holding n CUtensorMaps (64-byte aligned)."""
+    _req(x)
+    n = in_desc_host.shape[0]
+    host = np.zeros(n * 128, dtype=np.uint8)
+    desc = np.ascontiguousarray(in_desc_host, dtype=np.int32)
+    check(lib.b200_conv3x3_encode_maps(_ptr(x), x.stride(0), cin,
+                                       desc.ctypes.data_as(ctypes.c_void_p), n, stride,
+                                       host.ctypes.data_as(ctypes.c_void_p)),
+          "b200_conv3x3_encode_maps")
+    dev = torch.empty(n * 128 + 64, dtype=torch.uint8, device=x.device)
+    off = (-dev.data_ptr()) % 64
+    dev = dev[off:off + n * 128]
+    dev.copy_(torch.from_numpy(host))
+    return dev
+
+
+def conv3x3(maps_dev, tiles, n_mtiles, out_lat, cin, cout, stride, weight, out, *, epi=EPI_BIAS,
+            bias=None, resid=None, rowvec=None, row_group=None):
+    """out[M_total, cout] = conv3x3(x) through the implicit-GEMM kernel (see conv_sm100.cu)."""
+    _req(weight), _req(out)
+    d = _epi_desc(out, bias=bias, resid=resid, rowvec=rowvec, row_group=row_group)
+    _ev = _count("b200_conv3x3_bf16")
+    check(lib.b200_conv3x3_bf16(_ptr(maps_dev), _ptr(tiles), n_mtiles, _ptr(out_lat), cin, cout,
+                                stride, _ptr(weight), out.shape[0], epi, ctypes.byref(d),
+                                _stream()), "b200_conv3x3_bf16")
+    if _ev is not None:
+        _ev.record()
+    return out
+
+
+def groupnorm_workspace(total_rows, n_latents, device):
+    n = lib.b200_groupnorm_workspace_bytes(total_rows, n_latents)
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def groupnorm_nhwc(x, y, gamma, beta, row_group, lat_chunks, n_latents, workspace, *, groups=32,
+                   eps=1e-5, silu=False, channels=None):
+    _req(x), _req(y)
+    T = x.shape[0]
+    C = channels if channels is not None else x.shape[1]
+    _ev = _count("b200_groupnorm_nhwc_bf16")
+    check(lib.b200_groupnorm_nhwc_bf16(_ptr(x), x.stride(0), T, C, groups, ctypes.c_float(eps),
+                                       _ptr(gamma), _ptr(beta), _ptr(row_group), _ptr(lat_chunks),
+                                       n_latents, int(silu), _ptr(y), y.stride(0),
+                                       _ptr(workspace), _stream()), "b200_groupnorm_nhwc_bf16")
+    if _ev is not None:
+        _ev.record()
+    return y
+
+
+def pack_im2col3x3(lat_ptr, desc, n_latents, max_pixels, C, out):
+    _ev = _count("b200_pack_im2col3x3")
+    check(lib.b200_pack_im2col3x3(_ptr(lat_ptr), _ptr(desc), n_latents, max_pixels, C, _ptr(out),
+                                  out.stride(0), _stream()), "b200_pack_im2col3x3")
+    if _ev is not None:
+        _ev.record()
+
+
+def scatter_nchw(x, desc, n_latents, max_pixels, C, out_ptr):
+    _ev = _count("b200_scatter_nchw")
+    check(lib.b200_scatter_nchw(_ptr(x), x.stride(0), _ptr(desc), n_latents, max_pixels, C,
+                                _ptr(out_ptr), _stream()), "b200_scatter_nchw")
+    if _ev is not None:
+        _ev.record()
+
+
+def upsample2x(x, in_desc, out_desc, n_latents, max_out_pixels, C, y):
+    _ev = _count("b200_upsample2x_nhwc")
+    check(lib.b200_upsample2x_nhwc(_ptr(x), x.stride(0), _ptr(in_desc), _ptr(out_desc), n_latents,
+                                   max_out_pixels, C, _ptr(y), y.stride(0), _stream()),
+          "b200_upsample2x_nhwc")
+    if _ev is not None:
+        _ev.record()
+
+
+def copy_cols(src, dst, cols):
+    """dst[:, :cols] = src[:, :cols]; src / dst are 2-D views (any row stride)."""
+    _req(src), _req(dst)
+    _ev = _count("b200_copy_cols_bf16")
+    check(lib.b200_copy_cols_bf16(_ptr(src), src.stride(0), _ptr(dst), dst.stride(0),
+                                  src.shape[0], cols, _stream()), "b200_copy_cols_bf16")
+    if _ev is not None:
+        _ev.record()
+
+
+def split_patches(lat_ptr, ldesc, pdesc, n_patches, C, ps, out):
+    _ev = _count("b200_split_patches")
+    check(lib.b200_split_patches(_ptr(lat_ptr), _ptr(ldesc), _ptr(pdesc), n_patches, C, ps,
+                                 _ptr(out), _stream()), "b200_split_patches")
+    if _ev is not None:
+        _ev.record()
+
+
+def concat_patches(patches, ldesc, pdesc, n_patches, C, ps, out_ptr):
+    _ev = _count("b200_concat_patches")
+    check(lib.b200_concat_patches(_ptr(patches), _ptr(ldesc), _ptr(pdesc), n_patches, C, ps,
+                                  _ptr(out_ptr), _stream()), "b200_concat_patches")
+    if _ev is not None:
+        _ev.record()
