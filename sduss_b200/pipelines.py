@@ -137,3 +137,59 @@ class B200StableDiffusion3Pipeline(B200DenoisingPipelineBase):
                    is_sliced=is_sliced, patch_size=patch_size, input_indices=ids, _borrow=True)
         plan = self.model._plan(lat_in, embeds[0].shape[1])
         self._finish(plan, [(res, runner_reqs[res]) for res in res_list], cfg, guidance_scale)
+
+
+class B200StableDiffusionXLPipeline(B200DenoisingPipelineBase):
+    """SDXL-base: Euler discrete (epsilon), guidance 5.0 (…_xl_esymred_utils.py:197)."""
+    step_mode = 1
+    default_guidance = 5.0
+
+    @property
+    def unet(self):
+        return self.model
+
+    @torch.inference_mode()
+    def denoising_step(self, worker_reqs: Dict[str, List], do_classifier_free_guidance: bool = True,
+                       guidance_rescale: float = 0.0, guidance_scale: float = 5.0,
+                       timestep_cond=None, extra_step_kwargs: Dict = None,
+                       cross_attention_kwargs=None, ip_adapter_image=None,
+                       ip_adapter_image_embeds=None, is_sliced: bool = True,
+                       patch_size: int = 256) -> None:
+        if guidance_rescale > 0.0:
+            raise NotImplementedError("guidance_rescale > 0 is not fused (reference default is 0.0)")
+        assert timestep_cond is None and cross_attention_kwargs is None
+        res_list = self._sorted_res(worker_reqs)
+        cfg = do_classifier_free_guidance
+        lat_in, embeds, pooled, ids, ts = {}, [], [], [], []
+        pt = getattr(getattr(self.scheduler, "config", None), "prediction_type",
+                     getattr(self.scheduler, "prediction_type", "epsilon"))
+        self.step_mode = 1 if pt == "epsilon" else 2
+        for res in res_list:
+            reqs = worker_reqs[res]
+            lat = torch.cat([r.sampling_params.latents for r in reqs], dim=0)
+            t = [_next_timestep(r.scheduler_states) for r in reqs]
+            if cfg:
+                lat = torch.cat([lat, lat], dim=0)
+                embeds += [r.sampling_params.negative_prompt_embeds for r in reqs]
+                embeds += [r.sampling_params.prompt_embeds for r in reqs]
+                pooled += [r.prepare_output.negative_pooled_prompt_embeds for r in reqs]
+                pooled += [r.prepare_output.pooled_prompt_embeds for r in reqs]
+                for r in reqs:  # reference interleaves (neg, pos) per request here: deviation D4
+                    ids += [r.prepare_output.negative_add_time_ids, r.prepare_output.add_time_ids]
+                ts += t + t
+            else:
+                embeds += [r.sampling_params.prompt_embeds for r in reqs]
+                pooled += [r.prepare_output.pooled_prompt_embeds for r in reqs]
+                ids += [r.prepare_output.add_time_ids for r in reqs]
+                ts += t
+            # scale_model_input: x / sqrt(sigma^2 + 1) per request (one launch per resolution)
+            lat_in[res] = self.scheduler.batch_scale_model_input(reqs, lat, None)
+        index = {res: [str(r.request_id) for r in worker_reqs[res]] for res in res_list}
+        t_dev = torch.tensor(ts, dtype=torch.float32).to(self.model.device, non_blocking=True)
+        self.model(lat_in, t_dev, encoder_hidden_states=torch.cat(embeds, dim=0),
+                   added_cond_kwargs={"text_embeds": torch.cat(pooled, dim=0),
+                                      "time_ids": torch.cat(ids, dim=0)},
+                   return_dict=False, is_sliced=is_sliced, patch_size=patch_size,
+                   input_indices=index, _borrow=True)
+        plan = self.model._plan(lat_in, embeds[0].shape[1])
+        self._finish(plan, [(res, worker_reqs[res]) for res in res_list], cfg, guidance_scale)

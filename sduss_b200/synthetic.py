@@ -143,3 +143,89 @@ def random_sd3_state_dict(cfg, device, seed=0, dtype=torch.bfloat16):
     lin("norm_out.linear", D, 2 * D, 0.5)
     lin("proj_out", D, p * p * cfg.out_channels)
     return sd
+
+
+def random_unet_state_dict(cfg, device, seed=0, dtype=torch.bfloat16):
+    """SDXL UNet2DConditionModel state dict (diffusers names), random-init on `device`."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    sd = {}
+    T = cfg.block_out_channels[0] * 4
+    add_in = cfg.pooled_dim + 6 * cfg.addition_time_embed_dim
+
+    def lin(name, fin, fout, bias=True, gain=1.0):
+        sd[name + ".weight"] = (torch.randn(fout, fin, generator=g, device=device) * (gain / fin ** 0.5)).to(dtype)
+        if bias:
+            sd[name + ".bias"] = (torch.randn(fout, generator=g, device=device) * 0.02).to(dtype)
+
+    def conv(name, cin, cout, k, gain=1.0):
+        sd[name + ".weight"] = (torch.randn(cout, cin, k, k, generator=g, device=device)
+                                * (gain / (cin * k * k) ** 0.5)).to(dtype)
+        sd[name + ".bias"] = (torch.randn(cout, generator=g, device=device) * 0.02).to(dtype)
+
+    def norm(name, c):
+        sd[name + ".weight"] = (1.0 + 0.1 * torch.randn(c, generator=g, device=device)).to(dtype)
+        sd[name + ".bias"] = (0.05 * torch.randn(c, generator=g, device=device)).to(dtype)
+
+    def resnet(name, cin, cout):
+        norm(name + ".norm1", cin)
+        conv(name + ".conv1", cin, cout, 3)
+        lin(name + ".time_emb_proj", T, cout)
+        norm(name + ".norm2", cout)
+        conv(name + ".conv2", cout, cout, 3, 0.5)
+        if cin != cout:
+            conv(name + ".conv_shortcut", cin, cout, 1)
+
+    def transformer(name, c, layers):
+        norm(name + ".norm", c)
+        lin(name + ".proj_in", c, c)
+        for j in range(layers):
+            b = f"{name}.transformer_blocks.{j}"
+            norm(b + ".norm1", c)
+            for n in ("to_q", "to_k", "to_v"):
+                lin(f"{b}.attn1.{n}", c, c, bias=False)
+            lin(b + ".attn1.to_out.0", c, c, gain=0.5)
+            norm(b + ".norm2", c)
+            lin(b + ".attn2.to_q", c, c, bias=False)
+            lin(b + ".attn2.to_k", cfg.cross_attention_dim, c, bias=False)
+            lin(b + ".attn2.to_v", cfg.cross_attention_dim, c, bias=False)
+            lin(b + ".attn2.to_out.0", c, c, gain=0.5)
+            norm(b + ".norm3", c)
+            lin(b + ".ff.net.0.proj", c, 8 * c)
+            lin(b + ".ff.net.2", 4 * c, c, gain=0.5)
+        lin(name + ".proj_out", c, c, gain=0.5)
+
+    ch = cfg.block_out_channels
+    conv("conv_in", cfg.in_channels, ch[0], 3)
+    lin("time_embedding.linear_1", ch[0], T)
+    lin("time_embedding.linear_2", T, T)
+    lin("add_embedding.linear_1", add_in, T)
+    lin("add_embedding.linear_2", T, T)
+    out_c = ch[0]
+    for i, c in enumerate(ch):
+        in_c, out_c = out_c, c
+        for j in range(cfg.layers_per_block):
+            resnet(f"down_blocks.{i}.resnets.{j}", in_c if j == 0 else out_c, out_c)
+            if cfg.down_has_attn[i]:
+                transformer(f"down_blocks.{i}.attentions.{j}", out_c, cfg.transformer_layers_per_block[i])
+        if i != len(ch) - 1:
+            conv(f"down_blocks.{i}.downsamplers.0.conv", out_c, out_c, 3)
+    resnet("mid_block.resnets.0", ch[-1], ch[-1])
+    transformer("mid_block.attentions.0", ch[-1], cfg.transformer_layers_per_block[-1])
+    resnet("mid_block.resnets.1", ch[-1], ch[-1])
+    rev = list(reversed(ch))
+    rev_layers = list(reversed(cfg.transformer_layers_per_block))
+    rev_attn = list(reversed(cfg.down_has_attn))
+    out_c = rev[0]
+    for i, c in enumerate(rev):
+        prev_out, out_c = out_c, c
+        in_c = rev[min(i + 1, len(ch) - 1)]
+        for j in range(cfg.layers_per_block + 1):
+            skip_c = in_c if j == cfg.layers_per_block else out_c
+            resnet(f"up_blocks.{i}.resnets.{j}", (prev_out if j == 0 else out_c) + skip_c, out_c)
+            if rev_attn[i]:
+                transformer(f"up_blocks.{i}.attentions.{j}", out_c, rev_layers[i])
+        if i != len(ch) - 1:
+            conv(f"up_blocks.{i}.upsamplers.0.conv", out_c, out_c, 3)
+    norm("conv_norm_out", ch[0])
+    conv("conv_out", ch[0], cfg.out_channels, 3)
+    return sd

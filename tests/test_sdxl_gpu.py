@@ -1,0 +1,105 @@
+"""B200 SDXL UNet forward + denoising step vs the fp32 CPU oracle on identical random-init
+weights. Tolerance (bf16 kernels vs fp32 oracle): cosine >= 0.999 per latent, max-abs error
+<= 6% of the output's max-abs."""
+from dataclasses import asdict
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg_pair():
+    from oracle import sdxl_unet as ox
+    from sduss_b200.unet import UNetConfig
+    oc = ox.sdxl_tiny_config()
+    d = asdict(oc)
+    d.pop("context_len")
+    return oc, UNetConfig(**d)
+
+
+def _inputs(oc, spec, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    s = {r: torch.randn(n, 4, int(r) // 8, int(r) // 8, generator=g) for r, n in spec.items()}
+    L = sum(spec.values())
+    ehs = torch.randn(L, oc.context_len, oc.cross_attention_dim, generator=g)
+    te = torch.randn(L, oc.pooled_dim, generator=g)
+    ids = torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * L)
+    t = torch.tensor([981.0, 961.0, 500.0, 1.0, 41.0, 741.0][:L])
+    return s, ehs, te, ids, t
+
+
+def _compare(out, ref):
+    for r in ref:
+        a, b = out[r].float().cpu(), ref[r]
+        for i in range(a.shape[0]):
+            cos = torch.nn.functional.cosine_similarity(a[i].flatten(), b[i].flatten(), dim=0).item()
+            err = (a[i] - b[i]).abs().max().item() / b[i].abs().max().item()
+            assert cos >= 0.999, (r, i, cos)
+            assert err <= 0.06, (r, i, err)
+
+
+@pytest.mark.parametrize("spec", [{"256": 2}, {"256": 1, "512": 2, "768": 1}])
+def test_tiny_unet_matches_oracle(cuda, spec):
+    from oracle import sdxl_unet as ox
+    from sduss_b200.unet import B200UNet
+    oc, pc = _cfg_pair()
+    sd = {k: v.to(torch.bfloat16).float() for k, v in ox.init_unet_weights(oc, 0).items()}
+    model = B200UNet(sd, pc, device="cuda")
+    s, ehs, te, ids, t = _inputs(oc, spec)
+    q = lambda x: x.to(torch.bfloat16).float()
+    ref = ox.unet_forward(sd, oc, {k: q(v) for k, v in s.items()}, t, q(ehs), q(te), ids)
+    d = lambda x: x.cuda().bfloat16()
+    out = model({k: d(v) for k, v in s.items()}, t.cuda(), encoder_hidden_states=d(ehs),
+                added_cond_kwargs={"text_embeds": d(te), "time_ids": d(ids)}, return_dict=False,
+                is_sliced=True, patch_size=256)[0]
+    assert list(out.keys()) == list(ref.keys())
+    _compare(out, ref)
+
+
+def test_unet_batch_invariance(cuda):
+    from oracle import sdxl_unet as ox
+    from sduss_b200.unet import B200UNet
+    oc, pc = _cfg_pair()
+    sd = ox.init_unet_weights(oc, 0)
+    model = B200UNet(sd, pc, device="cuda")
+    s, ehs, te, ids, t = _inputs(oc, {"256": 2, "512": 1})
+    d = lambda x: x.cuda().bfloat16()
+    kw = lambda sl: dict(encoder_hidden_states=d(ehs[sl]), added_cond_kwargs={"text_embeds": d(te[sl]), "time_ids": d(ids[sl])})
+    full = model({k: d(v) for k, v in s.items()}, t.cuda(), **kw(slice(0, 3)))[0]
+    solo = model({"512": d(s["512"])}, t[2:3].cuda(), **kw(slice(2, 3)))[0]
+    assert torch.equal(full["512"], solo["512"])
+
+
+def test_sdxl_denoising_step_matches_oracle(cuda):
+    """Whole drop-in step: scale input, UNet with CFG, combine, Euler update, state advance."""
+    from oracle import schedulers as osch
+    from oracle import sdxl_unet as ox
+    from sduss_b200.pipelines import B200StableDiffusionXLPipeline
+    from sduss_b200.schedulers import B200EulerDiscreteScheduler
+    from sduss_b200.synthetic import make_sdxl_requests
+    from sduss_b200.unet import B200UNet
+    oc, pc = _cfg_pair()
+    sd = {k: v.to(torch.bfloat16).float() for k, v in ox.init_unet_weights(oc, 0).items()}
+    model = B200UNet(sd, pc, device="cuda")
+    sched = B200EulerDiscreteScheduler()
+    pipe = B200StableDiffusionXLPipeline(model, sched)
+    reqs = make_sdxl_requests(oc, {"256": 1, "512": 1}, 50, sched, torch.device("cuda"), seed=0)
+    flat = [r for rs in reqs.values() for r in rs]
+    before = [r.sampling_params.latents.float().cpu() for r in flat]
+    pipe.denoising_step(reqs, True, 0.0, 5.0, None, {}, None, None, None, True, 256)
+    torch.cuda.synchronize()
+    sig, ts, _ = osch.euler_sigmas(50)
+    f = lambda t: t.float().cpu()
+    for r, x in zip(flat, before):
+        xin = osch.batch_scale_model_input(torch.cat([x, x]).to(torch.bfloat16), [sig[0]]).float()
+        ehs = torch.cat([f(r.sampling_params.negative_prompt_embeds), f(r.sampling_params.prompt_embeds)])
+        te = torch.cat([f(r.prepare_output.negative_pooled_prompt_embeds), f(r.prepare_output.pooled_prompt_embeds)])
+        ids = torch.cat([f(r.prepare_output.negative_add_time_ids), f(r.prepare_output.add_time_ids)])
+        out = ox.unet_forward(sd, oc, {"x": xin}, ts[:1].repeat(2), ehs, te, ids)["x"]
+        eps = osch.cfg_combine(out, 5.0)
+        ref = osch.euler_batch_step(eps, x, [sig[0]], [sig[1]])
+        got = f(r.sampling_params.latents)
+        cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
+        assert cos > 0.999, cos
+        assert r.scheduler_states._step_index == 1 and r.scheduler_states.timestep_idx == 1
