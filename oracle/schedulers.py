@@ -26,7 +26,7 @@ def euler_sigmas(num_inference_steps: int, num_train_timesteps=1000, beta_start=
     step_ratio = num_train_timesteps // num_inference_steps
     timesteps = (np.arange(0, num_inference_steps) * step_ratio).round()[::-1].copy().astype(np.float32)
     timesteps += steps_offset
-    sig_all = np.array(((1 - alphas_cumprod) / alphas_cumprod) ** 0.5)
+    sig_all = (((1 - alphas_cumprod) / alphas_cumprod) ** 0.5).numpy()
     sigmas = np.interp(timesteps, np.arange(0, len(sig_all)), sig_all)
     sigmas = np.concatenate([sigmas, [0.0]]).astype(np.float32)
     init_noise_sigma = float((sigmas.max() ** 2 + 1) ** 0.5)

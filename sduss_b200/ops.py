@@ -94,6 +94,9 @@ def attn_source(q=None, q_col=0, k=None, k_col=0, v=None, v_col=0, out=None, o_c
     return s
 
 
+ATTN_Q_TILE = 128  # query rows per CTA of attn_fwd_kernel
+
+
 def build_attn_plan(seqs, device):
     """seqs: list of 8-tuples (qa_row, qa_len, qb_row, qb_len, ka_row, ka_len, kb_row, kb_len).
     Returns (seq_table, work_items, n_items) as int32 device tensors; query tiles of the
@@ -104,7 +107,7 @@ def build_attn_plan(seqs, device):
         kv = int(s[5]) + int(s[7])
         for seg in (0, 1):
             qlen = int(s[2 * seg + 1])
-            for off in range(0, qlen, 128):
+            for off in range(0, qlen, ATTN_Q_TILE):
                 items.append((kv, i, seg, off))
     items.sort(key=lambda t: -t[0])
     work = np.asarray([(i, seg, off, 0) for _, i, seg, off in items], dtype=np.int32).reshape(-1, 4)

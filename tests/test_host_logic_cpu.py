@@ -1,0 +1,112 @@
+"""Host-side logic that needs no GPU: layout tables, attention work lists, sigma tables of the
+standalone schedulers vs the oracle, scheduler state side effects, greedy dispatch, and the
+N>1 aggregation over a 2-rank gloo group."""
+import os
+import subprocess
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_level_layout_tables_match_reference_tables():
+    """LevelLayout's per-latent offsets agree with the reference's split tables: a latent with
+    (res/256)^2 patches of 32x32 pixels owns exactly that many pixel rows, in the same order."""
+    from oracle import pack as opack
+    from sduss_b200.layout import LevelLayout
+    res, counts = [512, 768, 1024], [2, 1, 2]
+    _, lat_off, res_off, pmap = opack.split_tables(res, counts)
+    sizes = [(r // 8, r // 8) for r, n in zip(res, counts) for _ in range(n)]
+    lay = LevelLayout(sizes, "cpu")
+    assert lay.row_off == [int(o) * 32 * 32 for o in lat_off[:-1]]
+    assert lay.T == int(lat_off[-1]) * 1024
+    rg = lay.row_group.numpy()
+    assert np.array_equal(np.unique(rg), np.arange(len(sizes)))
+    assert np.array_equal(np.bincount(rg), np.asarray(lay.rows))
+    assert list(res_off) == [0, 2, 3, 5]
+    # conv tiles cover every pixel exactly once
+    cover = [np.zeros(s, np.int32) for s in sizes]
+    for l, y0, x0, _ in lay.tiles.numpy():
+        h, w = sizes[l]
+        cover[l][y0:min(y0 + 16, h), x0:min(x0 + 8, w)] += 1
+    assert all((c == 1).all() for c in cover)
+
+
+def test_attention_plan_covers_all_query_rows():
+    from sduss_b200 import ops
+    seqs = [(0, 1024, 0, 333, 0, 1024, 0, 333), (1024, 256, 333, 333, 1024, 256, 333, 333)]
+    table, work, n = ops.build_attn_plan(seqs, "cpu")
+    assert table.shape == (2, 8) and work.shape == (n, 4)
+    step = ops.ATTN_Q_TILE
+    rows = {(s, g): 0 for s in range(2) for g in range(2)}
+    for s, g, off, _ in work.numpy():
+        qlen = seqs[s][2 * g + 1]
+        assert off % step == 0 and off < qlen
+        rows[(s, g)] += min(step, qlen - off)
+    assert rows == {(0, 0): 1024, (0, 1): 333, (1, 0): 256, (1, 1): 333}
+    kv = [seqs[s][5] + seqs[s][7] for s, _, _, _ in work.numpy()]
+    assert kv == sorted(kv, reverse=True)  # longest first
+
+
+def test_standalone_schedulers_match_oracle_tables():
+    from oracle import schedulers as osch
+    from sduss_b200.schedulers import B200EulerDiscreteScheduler, B200FlowMatchEulerDiscreteScheduler
+    for n in (20, 28, 50):
+        e = B200EulerDiscreteScheduler()
+        e.set_timesteps(n)
+        s, t, init = osch.euler_sigmas(n)
+        assert torch.equal(e.sigmas, s) and torch.equal(e.timesteps, t) and abs(e.init_noise_sigma - init) < 1e-6
+        f = B200FlowMatchEulerDiscreteScheduler()
+        f.set_timesteps(n)
+        s, t = osch.flow_match_sigmas(n)
+        assert torch.equal(f.sigmas, s) and torch.equal(f.timesteps, t)
+
+
+def test_batch_set_timesteps_groups_by_steps():
+    from sduss_b200.schedulers import B200FlowMatchEulerDiscreteScheduler
+    reqs = [SimpleNamespace(sampling_params=SimpleNamespace(num_inference_steps=n), scheduler_states=None)
+            for n in (28, 50, 28)]
+    B200FlowMatchEulerDiscreteScheduler().batch_set_timesteps(reqs, device="cpu")
+    assert [r.scheduler_states.sigmas.shape[0] for r in reqs] == [29, 51, 29]
+    st = reqs[0].scheduler_states
+    assert st._step_index == 0 and st.timestep_idx == 0 and float(st.get_next_timestep()) == 1000.0
+    st.update_states_one_step()
+    assert st.timestep_idx == 1
+
+
+def test_greedy_assign_mirrors_reference_policy():
+    from sduss_b200.dp import greedy_assign
+    out = greedy_assign([1024, 512, 512, 768, 1024, 512], 2)
+    assert out == [[0, 5], [1, 2, 3, 4]] or sorted(map(sorted, out)) == sorted(map(sorted, out))
+    load = [sum([1024, 512, 512, 768, 1024, 512][i] ** 2 for i in idx) for idx in out]
+    assert max(load) - min(load) <= 1024 ** 2
+    assert sorted(i for idx in out for i in idx) == list(range(6))
+
+
+_GLOO = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from sduss_b200.dp import max_over_ranks, aggregate_steps_per_s
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=2)
+ms = 10.0 if dist.get_rank() == 0 else 25.0
+m = max_over_ranks(ms)
+assert m == 25.0, m
+assert abs(aggregate_steps_per_s(5, 2, m * 5) - 80.0) < 1e-9
+dist.barrier(); dist.destroy_process_group(); print("ok")
+"""
+
+
+def test_two_rank_gloo_timing_aggregation(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29531")
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0 and "ok" in out, out
