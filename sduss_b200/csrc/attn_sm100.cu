@@ -9,25 +9,28 @@
 // This replaces the per-resolution Python loops around xformers / SDPA in the reference
 // (sduss/model_executor/modules/attention.py:155-203 self, :59-110 cross, :297-368 joint).
 //
-// CTA = one 128-row query tile of one (sequence, head). Warp 0: TMA producer (Q once, K and V
-// rings). Warp 1: tcgen05.mma issuer: S = Q K^T into a double-buffered TMEM tile, then
-// O_j = P_j V_j with P read back from TMEM (A-from-TMEM MMA). Warps 2-5: online softmax, one
-// thread per query row (TMEM lane), P written to TMEM as packed bf16 over the S tile; the
-// per-tile PV result is folded into a register accumulator with the usual rescale.
+// CTA = TWO 128-row query tiles (A, B) of one (sequence, head), so the tensor pipe works on one
+// tile while the other is in softmax. Warp 0: TMA producer (Q once, K and V rings). Warp 1:
+// tcgen05.mma issuer: S_t = Q_t K^T into TMEM, then O_t += P_t V with P read back from TMEM
+// (A-from-TMEM MMA) and O accumulated in TMEM. Warps 2-5 / 6-9: online softmax of tile A / B,
+// one thread per query row (TMEM lane), whole 128-column S row in registers, P written to TMEM
+// as packed bf16 over S. The running max is only moved when it grows by more than 2^8 (lazy
+// rescale), in which case the softmax warps rescale O in TMEM before releasing P.
 #include "../../include/sduss_b200.h"
 #include "host_util.h"
 #include "ptx.cuh"
 
 namespace b200 {
 
-constexpr int ATT_BM = 128;   // query rows per CTA
+constexpr int ATT_BM = 128;   // query rows per tile; a CTA owns TWO tiles (256 rows)
 constexpr int ATT_BN = 128;   // kv rows per tile
 constexpr int ATT_D = 64;     // head dim
 constexpr int ATT_KS = 3;     // K ring depth
 constexpr int ATT_VS = 3;     // V ring depth
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 softmax A, warps 6-9 softmax B
 constexpr int ATT_TILE_BYTES = 128 * ATT_D * 2;  // 16 KB
-constexpr int ATT_SMEM = (1 + ATT_KS + ATT_VS) * ATT_TILE_BYTES + 1024 + 256;
+constexpr int ATT_SMEM = (2 + ATT_KS + ATT_VS) * ATT_TILE_BYTES + 1024 + 256;
+constexpr float ATT_RESCALE_THRESHOLD = 8.f;  // lazy rescale: keep a stale max while p <= 2^8
 
 struct AttnArgs {
   const int* seq_table;   // [n_seq][8]: qa_row, qa_len, qb_row, qb_len, ka_row, ka_len, kb_row, kb_len
@@ -53,8 +56,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + ATT_TILE_BYTES;
+  uint8_t* sQ = smem;                                 // 2 tiles
+  uint8_t* sK = smem + 2 * ATT_TILE_BYTES;
   uint8_t* sV = sK + ATT_KS * ATT_TILE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_VS * ATT_TILE_BYTES);
   uint64_t* q_full = bars;             // 1
@@ -62,11 +65,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
   uint64_t* k_empty = k_full + ATT_KS; // KS
   uint64_t* v_full = k_empty + ATT_KS; // VS
   uint64_t* v_empty = v_full + ATT_VS; // VS
-  uint64_t* s_full = v_empty + ATT_VS; // 2
+  uint64_t* s_full = v_empty + ATT_VS; // 2 (per query tile)
   uint64_t* p_full = s_full + 2;       // 2
   uint64_t* o_full = p_full + 2;       // 2
-  uint64_t* o_empty = o_full + 2;      // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -76,7 +78,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
   const int* st = a.seq_table + item.x * 8;
   const int q_seg = item.y;
   const int q_row0 = st[q_seg * 2] + item.z;
-  const int q_valid = min(ATT_BM, st[q_seg * 2 + 1] - item.z);
+  const int q_rows = min(2 * ATT_BM, st[q_seg * 2 + 1] - item.z);  // valid query rows in this CTA
+  const int nq = q_rows > ATT_BM ? 2 : 1;                          // active query tiles
   const int ka_row = st[4], ka_len = st[5], kb_row = st[6], kb_len = st[7];
   const int nA = (ka_len + ATT_BN - 1) / ATT_BN;
   const int nB = (kb_len + ATT_BN - 1) / ATT_BN;
@@ -96,7 +99,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
-      mbar_init(&o_empty[i], 4);
     }
     fence_barrier_init();
   }
@@ -108,14 +110,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base;         // S0 / S1: 128 columns each (P overlays the front 64)
-  const uint32_t tO = tmem_base + 256;   // O0 / O1: 64 columns each
+  // TMEM columns: S_t at 128 t (P_t overlays its first 64 columns), O_t at 256 + 64 t
+  const uint32_t tS = tmem_base;
+  const uint32_t tO = tmem_base + 256;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_expect_tx(q_full, ATT_TILE_BYTES);
-      tma_load_2d(sQ, q_seg == 0 ? &tmQA : &tmQB, q_full, a.q_col[q_seg] + head * ATT_D, q_row0);
+      const CUtensorMap* qm = q_seg == 0 ? &tmQA : &tmQB;
+      mbar_expect_tx(q_full, nq * ATT_TILE_BYTES);
+      tma_load_2d(sQ, qm, q_full, a.q_col[q_seg] + head * ATT_D, q_row0);
+      if (nq == 2)
+        tma_load_2d(sQ + ATT_TILE_BYTES, qm, q_full, a.q_col[q_seg] + head * ATT_D, q_row0 + ATT_BM);
     }
     int ks = 0, vs = 0;
     uint32_t kph = 0, vph = 0;
@@ -145,132 +151,151 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
     int ks = 0, vs = 0;
     uint32_t kph = 0, vph = 0;
     mbar_wait(q_full, 0);
-    const uint64_t dq = make_sdesc_sw128(smem_u32(sQ));
-    auto issue_qk = [&](int j) {
-      mbar_wait(&k_full[ks], kph);
-      tc_fence_after();
+    tc_fence_after();
+    auto issue_qk = [&](int t, uint32_t k_addr) {  // S_t = Q_t K^T
       if (lane == 0) {
-        const uint64_t dk = make_sdesc_sw128(smem_u32(sK + ks * ATT_TILE_BYTES));
+        const uint64_t dq = make_sdesc_sw128(smem_u32(sQ + t * ATT_TILE_BYTES));
+        const uint64_t dk = make_sdesc_sw128(k_addr);
 #pragma unroll
         for (int k = 0; k < ATT_D / 16; ++k)
-          umma_ss(tS + (j & 1) * ATT_BN, dq + uint64_t(2 * k), dk + uint64_t(2 * k), idesc_qk,
+          umma_ss(tS + t * ATT_BN, dq + uint64_t(2 * k), dk + uint64_t(2 * k), idesc_qk,
                   k != 0 ? 1u : 0u);
-        umma_commit(&k_empty[ks]);
-        umma_commit(&s_full[j & 1]);
+        umma_commit(&s_full[t]);
       }
       __syncwarp();
-      if (++ks == ATT_KS) { ks = 0; kph ^= 1; }
     };
-    issue_qk(0);
-    for (int j = 0; j < n_tiles; ++j) {
-      if (j + 1 < n_tiles) issue_qk(j + 1);
-      const int b = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
-      mbar_wait(&p_full[b], ph);
-      mbar_wait(&v_full[vs], vph);
-      mbar_wait(&o_empty[b], ph ^ 1);
-      tc_fence_after();
+    auto issue_pv = [&](int t, uint32_t v_addr, int j) {  // O_t (+)= P_t V
       if (lane == 0) {
-        const uint64_t dv = make_sdesc_sw128(smem_u32(sV + vs * ATT_TILE_BYTES));
+        const uint64_t dv = make_sdesc_sw128(v_addr);
 #pragma unroll
         for (int k = 0; k < ATT_BN / 16; ++k)
           // A: 16 bf16 of K = 8 TMEM columns; B: 16 kv rows = 2048 bytes (>>4 = 128)
-          umma_ts(tO + b * ATT_D, tS + b * ATT_BN + 8 * k, dv + uint64_t(128 * k), idesc_pv,
-                  k != 0 ? 1u : 0u);
+          umma_ts(tO + t * ATT_D, tS + t * ATT_BN + 8 * k, dv + uint64_t(128 * k), idesc_pv,
+                  (j | k) != 0 ? 1u : 0u);
+        umma_commit(&o_full[t]);
+      }
+      __syncwarp();
+    };
+    // prologue: S_A(0), S_B(0)
+    mbar_wait(&k_full[ks], kph);
+    tc_fence_after();
+    for (int t = 0; t < nq; ++t) issue_qk(t, smem_u32(sK + ks * ATT_TILE_BYTES));
+    if (lane == 0) umma_commit(&k_empty[ks]);
+    __syncwarp();
+    if (++ks == ATT_KS) { ks = 0; kph ^= 1; }
+    for (int j = 0; j < n_tiles; ++j) {
+      const uint32_t ph = j & 1;
+      const bool more = j + 1 < n_tiles;
+      mbar_wait(&v_full[vs], vph);
+      if (more) mbar_wait(&k_full[ks], kph);
+      const uint32_t v_addr = smem_u32(sV + vs * ATT_TILE_BYTES);
+      const uint32_t k_addr = smem_u32(sK + ks * ATT_TILE_BYTES);
+      for (int t = 0; t < nq; ++t) {
+        mbar_wait(&p_full[t], ph);
+        tc_fence_after();
+        issue_pv(t, v_addr, j);
+        if (more) issue_qk(t, k_addr);  // overwrites S_t/P_t: ordered after PV_t(j) in the pipe
+      }
+      if (lane == 0) {
         umma_commit(&v_empty[vs]);
-        umma_commit(&o_full[b]);
+        if (more) umma_commit(&k_empty[ks]);
       }
       __syncwarp();
       if (++vs == ATT_VS) { vs = 0; vph ^= 1; }
+      if (more && ++ks == ATT_KS) { ks = 0; kph ^= 1; }
     }
   } else {
     // ------------------------------------------------------------ softmax + output
-    const int qd = warp & 3;
-    const int r = qd * 32 + lane;  // query row inside the tile == TMEM lane
-    const uint32_t lane_off = uint32_t(qd * 32) << 16;
-    float o_acc[ATT_D];
-#pragma unroll
-    for (int i = 0; i < ATT_D; ++i) o_acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-    const float sc = a.scale_log2;
+    const int t = (warp - 2) >> 2;  // query tile of this warpgroup
+    if (t < nq) {
+      const int qd = warp & 3;
+      const int r = qd * 32 + lane;  // query row inside the tile == TMEM lane
+      const uint32_t lane_off = uint32_t(qd * 32) << 16;
+      const uint32_t t_s = tS + lane_off + t * ATT_BN;
+      const uint32_t t_o = tO + lane_off + t * ATT_D;
+      float m_run = -INFINITY, l_run = 0.f;
+      const float sc = a.scale_log2;
 
-    auto fold_o = [&](int j, float alpha) {
-      const int b = j & 1;
-      mbar_wait(&o_full[b], (j >> 1) & 1);
+      for (int j = 0; j < n_tiles; ++j) {
+        const bool inA = j < nA;
+        const int n_valid =
+            inA ? min(ATT_BN, ka_len - j * ATT_BN) : min(ATT_BN, kb_len - (j - nA) * ATT_BN);
+        mbar_wait(&s_full[t], j & 1);
+        tc_fence_after();
+        float s[ATT_BN];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32(t_s + c * 32, reinterpret_cast<uint32_t*>(s) + c * 32);
+        tmem_wait_ld();
+        if (n_valid < ATT_BN) {
+#pragma unroll
+          for (int i = 0; i < ATT_BN; ++i)
+            if (i >= n_valid) s[i] = -INFINITY;
+        }
+        float mx = s[0];
+#pragma unroll
+        for (int i = 1; i < ATT_BN; ++i) mx = fmaxf(mx, s[i]);
+        const float m_new = fmaxf(m_run, mx);
+        // lazy rescale: only move the reference max when it grew by more than 2^8
+        const bool resc = (m_new - m_run) * sc > ATT_RESCALE_THRESHOLD;
+        float alpha = 1.f;
+        if (resc) {
+          alpha = fast_exp2((m_run - m_new) * sc);
+          m_run = m_new;
+        }
+        const float m_sc = m_run * sc;
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = fast_exp2(fmaf(s[c * 32 + i], sc, -m_sc));
+            const float p1 = fast_exp2(fmaf(s[c * 32 + i + 1], sc, -m_sc));
+            sum += p0 + p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+          tmem_st16(t_s + c * 16, pk);
+        }
+        l_run = l_run * alpha + sum;
+        if (j > 0) {
+          // PV_t(j-1) must have landed in O_t before it is rescaled and before PV_t(j) starts
+          mbar_wait(&o_full[t], (j - 1) & 1);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, resc)) {
+            uint32_t o[ATT_D];
+            tmem_ld32(t_o, o);
+            tmem_ld32(t_o + 32, o + 32);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < ATT_D; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(t_o, o);
+            tmem_st32(t_o + 32, o + 32);
+          }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      }
+      mbar_wait(&o_full[t], (n_tiles - 1) & 1);
       tc_fence_after();
-      uint32_t v[ATT_D];
-      tmem_ld32(tO + lane_off + b * ATT_D, v);
-      tmem_ld32(tO + lane_off + b * ATT_D + 32, v + 32);
+      uint32_t o[ATT_D];
+      tmem_ld32(t_o, o);
+      tmem_ld32(t_o + 32, o + 32);
       tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&o_empty[b]);
+      if (t * ATT_BM + r < q_rows) {
+        const float inv = 1.f / l_run;
+        __nv_bfloat16* op = a.out[q_seg] + size_t(q_row0 + t * ATT_BM + r) * a.ldo[q_seg] +
+                            a.o_col[q_seg] + head * ATT_D;
 #pragma unroll
-      for (int i = 0; i < ATT_D; ++i) o_acc[i] = fmaf(o_acc[i], alpha, __uint_as_float(v[i]));
-    };
-
-    for (int j = 0; j < n_tiles; ++j) {
-      const int b = j & 1;
-      const bool inA = j < nA;
-      const int n_valid = inA ? min(ATT_BN, ka_len - j * ATT_BN) : min(ATT_BN, kb_len - (j - nA) * ATT_BN);
-      mbar_wait(&s_full[b], (j >> 1) & 1);
-      tc_fence_after();
-      const uint32_t t_s = tS + lane_off + b * ATT_BN;
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_s + c * 32, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = (c * 32 + i < n_valid) ? __uint_as_float(v[i]) : -INFINITY;
-          mx = fmaxf(mx, s);
+        for (int i = 0; i < ATT_D; i += 8) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+          v.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+          v.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+          v.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + i) = v;
         }
-      }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = fast_exp2((m_run - m_new) * sc);
-      const float m_sc = m_new * sc;
-      // pass 2: p = exp2(s * scale - m * scale), row sum, bf16 P into TMEM (over S)
-      float sum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_s + c * 32, v);
-        tmem_wait_ld();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = (c * 32 + i < n_valid) ? fast_exp2(fmaf(__uint_as_float(v[i]), sc, -m_sc)) : 0.f;
-          float p1 = (c * 32 + i + 1 < n_valid) ? fast_exp2(fmaf(__uint_as_float(v[i + 1]), sc, -m_sc)) : 0.f;
-          sum += p0 + p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-        tmem_st16(t_s + c * 16, pk);
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[b]);
-      l_run = l_run * alpha + sum;
-      m_run = m_new;
-      if (j > 0) fold_o(j - 1, alpha_prev);
-      alpha_prev = alpha;
-    }
-    fold_o(n_tiles - 1, alpha_prev);
-
-    if (r < q_valid) {
-      const float inv = 1.f / l_run;
-      __nv_bfloat16* op = a.out[q_seg] + size_t(q_row0 + r) * a.ldo[q_seg] + a.o_col[q_seg] + head * ATT_D;
-#pragma unroll
-      for (int i = 0; i < ATT_D; i += 8) {
-        uint4 v;
-        v.x = pack_bf16x2(o_acc[i] * inv, o_acc[i + 1] * inv);
-        v.y = pack_bf16x2(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
-        v.z = pack_bf16x2(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
-        v.w = pack_bf16x2(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
-        *reinterpret_cast<uint4*>(op + i) = v;
       }
     }
   }
