@@ -299,6 +299,116 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- SDXL leg
+SDXL_SPEC = {"512": 1, "1024": 1}  # BASELINE configs[0] shape: 512^2 + 1024^2, CFG -> 4 latents
+
+
+def sdxl_cpu_oracle_steps_per_s(sd32):
+    """Oracle SDXL UNet, fp32, host cores: the 512^2 request with CFG (2 latents) + scale input +
+    CFG + Euler update; scaled to the whole 512^2+1024^2 step by FLOPs."""
+    from oracle import schedulers as osch
+    from oracle import sdxl_unet as ox
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = ox.sdxl_base_config()
+    g = torch.Generator().manual_seed(0)
+    sig, ts, init = osch.euler_sigmas(50)
+    lat = torch.randn(1, 4, 64, 64, generator=g) * init
+    ehs, te = torch.randn(2, 77, 2048, generator=g), torch.randn(2, 1280, generator=g)
+    ids = torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * 2)
+    t0 = time.perf_counter()
+    xin = osch.batch_scale_model_input(torch.cat([lat, lat]), [sig[0]])
+    out = ox.unet_forward(sd32, cfg, {"512": xin}, ts[:1].repeat(2), ehs, te, ids)
+    osch.euler_batch_step(osch.cfg_combine(out["512"], 5.0), lat, [sig[0]], [sig[1]])
+    dt = time.perf_counter() - t0
+    per = {r: ox.unet_flops_per_latent(cfg, int(r)) for r in SDXL_SPEC}
+    step_fl = sum(2 * n * per[r] for r, n in SDXL_SPEC.items())
+    return {"value": (1.0 / dt) * (2 * per["512"] / step_fl), "unit": "denoise steps/s", "cores": cores,
+            "kind": "port", "sample_seconds": dt,
+            "sample": f"1x512^2 request with CFG (2 latents) through the full SDXL-base oracle, fp32, {dt:.2f} s; "
+                      f"scaled by FLOPs {2 * per['512'] / 1e12:.2f}/{step_fl / 1e12:.2f} T"}, step_fl
+
+
+def run_b200_sdxl(args, rank, world, local_rank):
+    from sduss_b200 import ops
+    from sduss_b200.pipelines import B200StableDiffusionXLPipeline
+    from sduss_b200.schedulers import B200EulerDiscreteScheduler
+    from sduss_b200.synthetic import make_sdxl_requests, random_unet_state_dict
+    from sduss_b200.unet import B200UNet, UNetConfig
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = UNetConfig()
+    cfg.context_len = 77
+    sd = random_unet_state_dict(cfg, dev, seed=0)
+    model = B200UNet(sd, cfg, device=dev)
+    sched = B200EulerDiscreteScheduler()
+    pipe = B200StableDiffusionXLPipeline(model, sched)
+    reqs = make_sdxl_requests(cfg, SDXL_SPEC, 4 * (args.steps + args.warmup) + 32, sched, dev, seed=rank)
+    step = lambda: pipe.denoising_step(reqs, True, 0.0, 5.0, None, {}, None, None, None, True, 256)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            step()
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms / steps
+
+    for _ in range(args.warmup):
+        step()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ops.profile = {}
+    n0 = ops.launch_count
+    ms_prof = timed(args.steps)
+    launches = ops.launch_count - n0
+    prof, ops.profile = ops.profile, None
+    clk = clocks.stop()
+    torch.cuda.synchronize()
+    per_kernel = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in prof.items()}
+    step()  # first un-profiled call captures the CUDA graph of the forward
+    ms_step = min(ms_prof, timed(args.steps))
+    if rank != 0:
+        return
+    pk, pk_src = peaks()
+    line = {"metric": "mixed-res denoise steps/s (SDXL-base, 512^2+1024^2, CFG)",
+            "value": world * 1000.0 / ms_step, "unit": "denoise steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "BASELINE configs[0] shape on B200: SDXL-base UNet denoise step, 512^2 + 1024^2 "
+                                   "(1 request each), CFG on -> 4 latents, bf16, random-init",
+                       "parallelism": f"dp{world} replicas, no collective"},
+            "req_steps_per_s": world * sum(SDXL_SPEC.values()) * 1000.0 / ms_step,
+            "gpu_launches": launches, "clocks": clk,
+            "kernel_ms_per_step": {k: round(v, 3) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])}}
+    if world == 1 and not args.no_cpu:
+        sd32 = {k: v.float().cpu() for k, v in sd.items()}
+        line["cpu_baseline"], step_fl = sdxl_cpu_oracle_steps_per_s(sd32)
+        line["config"]["step_tflop"] = step_fl / 1e12
+        line["config"]["model_tflops_per_gpu"] = step_fl / 1e12 / (ms_step / 1e3)
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -306,6 +416,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--model", default="sd3", choices=["sd3", "sdxl"],
+                    help="sd3 = BASELINE configs[1] (default, the headline); sdxl = configs[0] shape on B200")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", 0))
@@ -316,7 +428,10 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
-    run_b200(args, rank, world, local_rank)
+    if args.model == "sdxl":
+        run_b200_sdxl(args, rank, world, local_rank)
+    else:
+        run_b200(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

@@ -41,7 +41,8 @@ def _compile(src):
     obj = os.path.join(OBJ, src[:-3] + ".o")
     if not _stale(os.path.join(CSRC, src), obj):
         return src, 0, "(up to date)"
-    cmd = ["nvcc", *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    extra = os.environ.get("SDUSS_B200_NVCC_EXTRA", "").split()
+    cmd = ["nvcc", *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
     p = subprocess.run(cmd, capture_output=True, text=True)
     return src, p.returncode, p.stdout + p.stderr
 

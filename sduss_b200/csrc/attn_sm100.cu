@@ -18,6 +18,8 @@
 // rescale), in which case the softmax warps rescale O in TMEM before releasing P.
 #include "../../include/sduss_b200.h"
 #include "host_util.h"
+#include <cstdio>
+
 #include "ptx.cuh"
 
 namespace b200 {
@@ -40,13 +42,65 @@ struct AttnArgs {
   int ldo[2];
   int o_col[2];
   float scale_log2;                  // softmax scale * log2(e)
+  long long* dbg;                    // optional [gridDim.x * gridDim.y][8] phase cycle counters (ATT_TIMING builds)
 };
+
+#ifdef ATT_TIMING
+#define ATT_T(var) const long long var = clock64()
+#define ATT_ACC(slot, a, b) tacc[slot] += (b) - (a)
+#else
+#define ATT_T(var)
+#define ATT_ACC(slot, a, b)
+#endif
+
+// Named barriers (ids 1, 2) ping-pong the MUFU-heavy exp phase between the two softmax
+// warpgroups: while one group exponentiates (MUFU at full rate), the other loads its next S
+// row, reduces the max, stores P and talks to the MMA warp. Without it both groups drift into
+// lock-step, share the MUFU pipe for ~2200 cycles and leave it idle for ~1200 (measured).
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// volatile variant: keeps its source position relative to the tcgen05.st of the previous chunk,
+// which pins the software pipelining of the exp loop (ptxas otherwise sinks all packs to the end)
+__device__ __forceinline__ float fast_exp2_pinned(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max rel. error
+// 7.5e-5, far below the bf16 rounding of P). A quarter of the exponentials go through it so the
+// MUFU pipe (16 ex2/clk/SM, the co-bottleneck of head_dim-64 attention) is relieved.
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -126.f);
+  const float magic = 12582912.f;          // 1.5 * 2^23: x + magic rounds x to an integer
+  const float xf = x + magic;
+  const float f = x - (xf - magic);        // fractional part in [-0.5, 0.5]
+  const float p = fmaf(fmaf(fmaf(0.0551708528f, f, 0.242609396f), f, 0.693260959f), f, 0.999928182f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(xf) << 23));  // p * 2^round(x)
+}
+
+// fp32 -> bf16 pairs on the ALU pipe (IADD + PRMT) instead of F2FP: the conversion instruction
+// shares the 16/clk/SM XU pipe with MUFU.EX2, where it would add 50% to the exp phase.
+// Round-half-up on the magnitude (p >= 0); differs from RN only on exact ties.
+__device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
+  const uint32_t a = __float_as_uint(lo) + 0x8000u, b = __float_as_uint(hi) + 0x8000u;
+  return __byte_perm(a, b, 0x7632);
+}
+
+constexpr int ATT_PINGPONG = 0;  // measured: 574 -> 519 TFLOP/s (a lone warp's exp phase is not MUFU-bound)
+constexpr int ATT_ALU_PACK = 0;  // measured: F2FP 574 vs IADD+PRMT 562 TFLOP/s
+constexpr int ATT_POLY_MASK = 0;  // 1: every 4th exponential by polynomial. Measured on B200: 574 -> 520
+                                  // TFLOP/s (issue slots, not MUFU alone, bound the softmax warps), so off.
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant__ CUtensorMap tmQB,
@@ -68,7 +122,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
   uint64_t* s_full = v_empty + ATT_VS; // 2 (per query tile)
   uint64_t* p_full = s_full + 2;       // 2
   uint64_t* o_full = p_full + 2;       // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* s_free = o_full + 2;       // 2: softmax has copied S_t to registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -99,6 +154,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
+      mbar_init(&s_free[i], 4);
     }
     fence_barrier_init();
   }
@@ -110,9 +166,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S_t at 128 t (P_t overlays its first 64 columns), O_t at 256 + 64 t
+  // TMEM columns: S_t at 128 t, P_t (packed bf16) at 256 + 64 t, O_t at 384 + 64 t. S and P are
+  // separate so that S_t(j+1) = Q_t K(j+1)^T can be issued while softmax still works on tile j.
   const uint32_t tS = tmem_base;
-  const uint32_t tO = tmem_base + 256;
+  const uint32_t tP = tmem_base + 256;
+  const uint32_t tO = tmem_base + 384;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -170,7 +228,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
 #pragma unroll
         for (int k = 0; k < ATT_BN / 16; ++k)
           // A: 16 bf16 of K = 8 TMEM columns; B: 16 kv rows = 2048 bytes (>>4 = 128)
-          umma_ts(tO + t * ATT_D, tS + t * ATT_BN + 8 * k, dv + uint64_t(128 * k), idesc_pv,
+          umma_ts(tO + t * ATT_D, tP + t * ATT_D + 8 * k, dv + uint64_t(128 * k), idesc_pv,
                   (j | k) != 0 ? 1u : 0u);
         umma_commit(&o_full[t]);
       }
@@ -186,23 +244,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t ph = j & 1;
       const bool more = j + 1 < n_tiles;
+      if (more) {
+        // S_t(j+1) as soon as softmax has pulled S_t(j) into registers
+        mbar_wait(&k_full[ks], kph);
+        const uint32_t k_addr = smem_u32(sK + ks * ATT_TILE_BYTES);
+        for (int t = 0; t < nq; ++t) {
+          mbar_wait(&s_free[t], ph);
+          tc_fence_after();
+          issue_qk(t, k_addr);
+        }
+        if (lane == 0) umma_commit(&k_empty[ks]);
+        __syncwarp();
+        if (++ks == ATT_KS) { ks = 0; kph ^= 1; }
+      }
       mbar_wait(&v_full[vs], vph);
-      if (more) mbar_wait(&k_full[ks], kph);
       const uint32_t v_addr = smem_u32(sV + vs * ATT_TILE_BYTES);
-      const uint32_t k_addr = smem_u32(sK + ks * ATT_TILE_BYTES);
       for (int t = 0; t < nq; ++t) {
         mbar_wait(&p_full[t], ph);
         tc_fence_after();
         issue_pv(t, v_addr, j);
-        if (more) issue_qk(t, k_addr);  // overwrites S_t/P_t: ordered after PV_t(j) in the pipe
       }
-      if (lane == 0) {
-        umma_commit(&v_empty[vs]);
-        if (more) umma_commit(&k_empty[ks]);
-      }
+      if (lane == 0) umma_commit(&v_empty[vs]);
       __syncwarp();
       if (++vs == ATT_VS) { vs = 0; vph ^= 1; }
-      if (more && ++ks == ATT_KS) { ks = 0; kph ^= 1; }
     }
   } else {
     // ------------------------------------------------------------ softmax + output
@@ -213,27 +277,46 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
       const uint32_t lane_off = uint32_t(qd * 32) << 16;
       const uint32_t t_s = tS + lane_off + t * ATT_BN;
       const uint32_t t_o = tO + lane_off + t * ATT_D;
+      const uint32_t t_p = tP + lane_off + t * ATT_D;
       float m_run = -INFINITY, l_run = 0.f;
       const float sc = a.scale_log2;
+#ifdef ATT_TIMING
+      long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const long long t_begin = clock64();
+#endif
+      // Ping-pong of the XU-heavy exp phase between the two warpgroups (named barriers 1, 2).
+      const bool pingpong = ATT_PINGPONG && nq == 2;
+      if (pingpong && t == 1) named_bar_arrive(1, 256);  // group A exponentiates first
 
       for (int j = 0; j < n_tiles; ++j) {
         const bool inA = j < nA;
         const int n_valid =
             inA ? min(ATT_BN, ka_len - j * ATT_BN) : min(ATT_BN, kb_len - (j - nA) * ATT_BN);
+        ATT_T(c0);
         mbar_wait(&s_full[t], j & 1);
         tc_fence_after();
+        ATT_T(c1);
         float s[ATT_BN];
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld32(t_s + c * 32, reinterpret_cast<uint32_t*>(s) + c * 32);
         tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);  // S_t may be overwritten by the next Q K^T
+        ATT_T(c2);
         if (n_valid < ATT_BN) {
 #pragma unroll
           for (int i = 0; i < ATT_BN; ++i)
             if (i >= n_valid) s[i] = -INFINITY;
         }
-        float mx = s[0];
+        // 8 independent chains (a single 127-deep fmax chain would expose ~500 cycles of latency)
+        float mx8[8];
 #pragma unroll
-        for (int i = 1; i < ATT_BN; ++i) mx = fmaxf(mx, s[i]);
+        for (int i = 0; i < 8; ++i) mx8[i] = s[i];
+#pragma unroll
+        for (int i = 8; i < ATT_BN; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], s[i]);
+        const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                               fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
         const float m_new = fmaxf(m_run, mx);
         // lazy rescale: only move the reference max when it grew by more than 2^8
         const bool resc = (m_new - m_run) * sc > ATT_RESCALE_THRESHOLD;
@@ -243,22 +326,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
           m_run = m_new;
         }
         const float m_sc = m_run * sc;
-        float sum = 0.f;
+        if (pingpong) named_bar_sync(1 + t, 256);  // my turn on the XU pipe
+        ATT_T(c3);
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk[ATT_BN / 2];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = fast_exp2(fmaf(s[c * 32 + i], sc, -m_sc));
-            const float p1 = fast_exp2(fmaf(s[c * 32 + i + 1], sc, -m_sc));
-            sum += p0 + p1;
-            pk[i >> 1] = pack_bf16x2(p0, p1);
-          }
-          tmem_st16(t_s + c * 16, pk);
+        for (int i = 0; i < ATT_BN; i += 2) {
+          const float p0 = fast_exp2(fmaf(s[i], sc, -m_sc));
+          const float x1 = fmaf(s[i + 1], sc, -m_sc);
+          const float p1 = (ATT_POLY_MASK && ((i >> 1) & 1)) ? poly_exp2(x1) : fast_exp2(x1);
+          sum4[(i >> 1) & 3] += p0 + p1;
+          pk[i >> 1] = ATT_ALU_PACK ? pack_bf16x2_alu(p0, p1) : pack_bf16x2(p0, p1);
         }
+        const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
         l_run = l_run * alpha + sum;
+        if (pingpong && !(t == 1 && j == n_tiles - 1)) named_bar_arrive(2 - t, 256);  // hand over
+        ATT_T(c4);
         if (j > 0) {
-          // PV_t(j-1) must have landed in O_t before it is rescaled and before PV_t(j) starts
+          // PV_t(j-1) must be complete before P_t is overwritten and before O_t is rescaled
           mbar_wait(&o_full[t], (j - 1) & 1);
           tc_fence_after();
           if (__any_sync(0xffffffffu, resc)) {
@@ -272,11 +357,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
             tmem_st32(t_o + 32, o + 32);
           }
         }
+        ATT_T(c5);
+        tmem_st32(t_p, pk);
+        tmem_st32(t_p + 32, pk + 32);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
+        ATT_T(c6);
+        ATT_ACC(0, c0, c1); ATT_ACC(1, c1, c2); ATT_ACC(2, c2, c3); ATT_ACC(3, c3, c4);
+        ATT_ACC(4, c4, c5); ATT_ACC(5, c5, c6);
       }
+#ifdef ATT_TIMING
+      if (a.dbg != nullptr && lane == 0 && (warp == 2 || warp == 6)) {
+        long long* d = a.dbg + (size_t(blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (warp == 6 ? 8 : 0);
+        for (int i = 0; i < 6; ++i) d[i] = tacc[i];
+        d[6] = clock64() - t_begin;
+        d[7] = n_tiles;
+      }
+#endif
       mbar_wait(&o_full[t], (n_tiles - 1) & 1);
       tc_fence_after();
       uint32_t o[ATT_D];
@@ -319,6 +418,11 @@ static int make_rows_map(CUtensorMap* m, const void* base, int rows, int cols, i
 
 using namespace b200;
 
+#ifdef ATT_TIMING
+long long* g_att_dbg = nullptr;
+extern "C" long long* b200_attn_debug_buffer(void) { return g_att_dbg; }
+#endif
+
 extern "C" int b200_attn_varlen_bf16(const B200AttnSource* src_a, const B200AttnSource* src_b,
                                      const int32_t* seq_table, const int32_t* work_items,
                                      int n_items, int n_heads, float softmax_scale, void* stream_) {
@@ -356,12 +460,36 @@ extern "C" int b200_attn_varlen_bf16(const B200AttnSource* src_a, const B200Attn
   a.seq_table = seq_table;
   a.work_items = work_items;
   a.scale_log2 = softmax_scale * 1.4426950408889634f;
+  a.dbg = nullptr;
+#ifdef ATT_TIMING
+  {
+    static long long* dbg_buf = nullptr;
+    if (!dbg_buf) cudaMalloc(&dbg_buf, size_t(1) << 26);
+    a.dbg = dbg_buf;
+    cudaMemsetAsync(dbg_buf, 0, size_t(n_items) * n_heads * 16 * 8, reinterpret_cast<cudaStream_t>(stream_));
+    extern long long* g_att_dbg;
+    g_att_dbg = dbg_buf;
+  }
+#endif
   static bool configured = false;
   if (!configured) {
     cudaError_t err = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
     if (err != cudaSuccess) return static_cast<int>(err);
     configured = true;
   }
+#ifdef ATT_TIMING
+  {
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, attn_fwd_kernel);
+    static bool once = false;
+    if (!once) {
+      once = true;
+      printf("attn attrs: maxThreadsPerBlock=%d numRegs=%d sharedStatic=%zu maxDyn=%d local=%zu\n",
+             fa.maxThreadsPerBlock, fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes,
+             fa.localSizeBytes);
+    }
+  }
+#endif
   dim3 grid(n_items, n_heads);
   attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, reinterpret_cast<cudaStream_t>(stream_)>>>(
       tm[0][0], tm[1][0], tm[0][1], tm[1][1], tm[0][2], tm[1][2], a);

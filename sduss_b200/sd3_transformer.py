@@ -141,6 +141,8 @@ class _Plan:
                                        v_col=2 * D, out=self.att)
         self.src_ctx = ops.attn_source(q=self.qkv_c, q_col=0, k=self.qkv_c, k_col=D, v=self.qkv_c,
                                        v_col=2 * D, out=self.att_c)
+        self.graph = None
+        self.graph_launches = 0
 
 
 class B200SD3Transformer2DModel(torch.nn.Module):
@@ -214,6 +216,7 @@ class B200SD3Transformer2DModel(torch.nn.Module):
         self.mod_b = torch.cat(mod_b, 0).to(self.device, torch.bfloat16).contiguous()
         self.proj_w, self.proj_b = w("proj_out.weight"), w("proj_out.bias")
         self._plans: Dict[tuple, _Plan] = {}
+        self.use_graphs = ops.graphs_enabled()
 
     @classmethod
     def from_diffusers(cls, model, device="cuda"):
@@ -245,7 +248,7 @@ class B200SD3Transformer2DModel(torch.nn.Module):
         plan.ehs.copy_(encoder_hidden_states.reshape(plan.Tc, -1))
         plan.pooled.copy_(pooled_projections)
         plan.t32.copy_(timestep.reshape(-1))
-        self._run(plan)
+        ops.run_plan(self, plan)
         out = plan.stage_out if _borrow else {k: v.clone() for k, v in plan.stage_out.items()}
         return (out,)
 

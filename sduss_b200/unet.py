@@ -108,7 +108,10 @@ class _Plan:
         self.t32 = torch.empty((L,), device=dev, dtype=torch.float32)
         self.ids32 = torch.empty((L * 6,), device=dev, dtype=torch.float32)
         self.ehs = torch.empty((L * ctx_len, cfg.cross_attention_dim), **bf)
+        self.text_embeds = torch.empty((L, cfg.pooled_dim), **bf)
         self.device = dev
+        self.graph = None
+        self.graph_launches = 0
 
     def buf(self, name, rows, cols):
         t = self.bufs.get(name)
@@ -246,6 +249,7 @@ class B200UNet(torch.nn.Module):
         put("kv_all.weight", torch.cat(kv_w, 0))
         self.kv_cols = kcol
         self._plans: Dict[tuple, _Plan] = {}
+        self.use_graphs = ops.graphs_enabled()
 
     @classmethod
     def from_diffusers(cls, model, device="cuda"):
@@ -354,11 +358,12 @@ class B200UNet(torch.nn.Module):
         pl.ehs.copy_(encoder_hidden_states.reshape(pl.ehs.shape))
         pl.t32.copy_(timestep.reshape(-1))
         pl.ids32.copy_(added_cond_kwargs["time_ids"].reshape(-1))
-        self._run(pl, added_cond_kwargs["text_embeds"])
+        pl.text_embeds.copy_(added_cond_kwargs["text_embeds"])
+        ops.run_plan(self, pl)
         out = pl.stage_out if _borrow else {k: v.clone() for k, v in pl.stage_out.items()}
         return (out,)
 
-    def _run(self, pl: _Plan, text_embeds):
+    def _run(self, pl: _Plan):
         cfg, w, G = self.cfg, self.w, ops.gemm
         ch = cfg.block_out_channels
         L = pl.L
@@ -371,9 +376,7 @@ class B200UNet(torch.nn.Module):
         add_in = pl.buf("add_in", L, cfg.pooled_dim + 6 * cfg.addition_time_embed_dim)
         ids = ops.timestep_embedding(pl.ids32, cfg.addition_time_embed_dim,
                                      out=pl.buf("ids_sin", 6 * L, cfg.addition_time_embed_dim))
-        te = pl.buf("text_embeds", L, cfg.pooled_dim)
-        te.copy_(text_embeds)
-        ops.copy_cols(te, add_in, cfg.pooled_dim)
+        ops.copy_cols(pl.text_embeds, add_in, cfg.pooled_dim)
         ops.copy_cols(ids.view(L, -1), add_in[:, cfg.pooled_dim:], 6 * cfg.addition_time_embed_dim)
         a1 = G(add_in, w["add_embedding.linear_1.weight"], pl.buf("a1", L, Tdim), bias=w["add_embedding.linear_1.bias"])
         ops.silu(a1, a1)

@@ -103,3 +103,24 @@ def test_sdxl_denoising_step_matches_oracle(cuda):
         cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
         assert cos > 0.999, cos
         assert r.scheduler_states._step_index == 1 and r.scheduler_states.timestep_idx == 1
+
+
+def test_full_width_unet_matches_oracle(cuda):
+    """SDXL-base channel widths (320/640/1280, heads 5/10/20, 2048-d text, 77 tokens, 2816-d
+    add-embedding) with the transformer depth cut to (1,1,2) so the CPU oracle stays fast."""
+    from oracle import sdxl_unet as ox
+    from sduss_b200.unet import B200UNet, UNetConfig
+    oc = ox.sdxl_base_config()
+    oc.transformer_layers_per_block = (1, 1, 2)
+    d = asdict(oc)
+    d.pop("context_len")
+    pc = UNetConfig(**d)
+    sd = {k: v.to(torch.bfloat16).float() for k, v in ox.init_unet_weights(oc, 0).items()}
+    model = B200UNet(sd, pc, device="cuda")
+    s, ehs, te, ids, t = _inputs(oc, {"256": 1, "512": 1})
+    q = lambda x: x.to(torch.bfloat16).float()
+    ref = ox.unet_forward(sd, oc, {k: q(v) for k, v in s.items()}, t, q(ehs), q(te), ids)
+    dv = lambda x: x.cuda().bfloat16()
+    out = model({k: dv(v) for k, v in s.items()}, t.cuda(), encoder_hidden_states=dv(ehs),
+                added_cond_kwargs={"text_embeds": dv(te), "time_ids": dv(ids)})[0]
+    _compare(out, ref)

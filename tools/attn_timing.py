@@ -1,0 +1,37 @@
+"""Phase-level cycle breakdown of the attention softmax warps (needs an ATT_TIMING build:
+SDUSS_B200_NVCC_EXTRA=-DATT_TIMING python -m sduss_b200.build)."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from sduss_b200 import ops
+from sduss_b200._lib import lib
+dev = torch.device("cuda"); H = 24; C = H * 64; ctx = 333
+img = [1024, 1024, 2304, 2304, 4096, 4096]
+Ta, Tb = sum(img), len(img) * ctx
+qa = torch.randn(Ta, 3 * C, device=dev).bfloat16(); qb = torch.randn(Tb, 3 * C, device=dev).bfloat16()
+oa = torch.empty(Ta, C, device=dev, dtype=torch.bfloat16); ob = torch.empty(Tb, C, device=dev, dtype=torch.bfloat16)
+seqs, ra = [], 0
+for i, s in enumerate(img):
+    seqs.append((ra, s, i * ctx, ctx, ra, s, i * ctx, ctx)); ra += s
+table, work, n = ops.build_attn_plan(seqs, dev)
+sa = ops.attn_source(q=qa, k=qa, k_col=C, v=qa, v_col=2 * C, out=oa)
+sb = ops.attn_source(q=qb, k=qb, k_col=C, v=qb, v_col=2 * C, out=ob)
+for _ in range(3): ops.attn_varlen(sa, sb, table, work, n, H, 0.125)
+torch.cuda.synchronize()
+lib.b200_attn_debug_buffer.restype = ctypes.c_void_p
+ptr = lib.b200_attn_debug_buffer()
+host = torch.empty(n * H * 16, dtype=torch.int64)
+import ctypes as C_
+cudart = C_.CDLL("/usr/local/cuda/lib64/libcudart.so.12")
+cudart.cudaMemcpy(C_.c_void_p(host.data_ptr()), C_.c_void_p(ptr), C_.c_size_t(n * H * 16 * 8), 2)
+d = host.numpy().reshape(-1, 2, 8)
+names = ["wait_s", "ld_s+free", "max", "exp+pack+st", "wait_o+token", "wait_st+arrive"]
+for t in (0, 1):
+    x = d[:, t, :]
+    x = x[x[:, 7] > 0]
+    tiles = x[:, 7].sum()
+    print(f"tile {'AB'[t]}: CTAs {len(x)}, tiles {tiles}, cycles/tile total {x[:, 6].sum() / tiles:.0f}")
+    for i, nme in enumerate(names):
+        print(f"   {nme:16s} {x[:, i].sum() / tiles:8.0f} clk/tile")
+    big = x[x[:, 7] == 35]
+    print("   35-tile CTAs: total/tile", big[:, 6].sum() / big[:, 7].sum(), " wait_s/tile", big[:, 0].sum() / big[:, 7].sum())
