@@ -175,7 +175,8 @@ int b200_conv3x3_encode_maps(const void* x, int ldx, int Cin, const int32_t* in_
  * Wt: [Cout, 9*Cin] bf16 with K index = (ky*3 + kx)*Cin + c; M_total = rows of the output
  * buffer. Epilogue modes: B200_EPI_BIAS, B200_EPI_ROWVEC (+ time-embedding vector of the
  * request), B200_EPI_GATE_RESID (+ residual). Cin % 64 == 0, Cout % 8 == 0. */
-int b200_conv3x3_bf16(const void* in_maps_dev, const int32_t* tiles_dev, int n_mtiles,
+int b200_conv3x3_bf16(const void* in_maps_dev, const void* out_maps_dev,
+                      const void* resid_maps_dev, const int32_t* tiles_dev, int n_mtiles,
                       const int32_t* out_lat_dev, int Cin, int Cout, int stride, const void* Wt,
                       int M_total, int epi_mode, const B200EpilogueDesc* ep, void* stream);
 

@@ -81,8 +81,8 @@ SIGNATURES = {
     "b200_euler_scale_input": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, ctypes.c_longlong,
                                c_void_p],
     "b200_conv3x3_encode_maps": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p],
-    "b200_conv3x3_bf16": [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
-                          c_int, c_int, ctypes.POINTER(EpilogueDesc), c_void_p],
+    "b200_conv3x3_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
+                          c_int, c_void_p, c_int, c_int, ctypes.POINTER(EpilogueDesc), c_void_p],
     "b200_groupnorm_nhwc_bf16": [c_void_p, c_int, ctypes.c_longlong, c_int, c_int, c_float,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                  c_int, c_void_p, c_void_p],

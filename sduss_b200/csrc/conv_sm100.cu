@@ -19,18 +19,22 @@ namespace b200 {
 
 constexpr int CV_BM = 128, CV_BK = 64, CV_TW = 8, CV_TH = 16, CV_THREADS = 256;
 
-template <int BN>
+template <int BN, int EPI>
 struct ConvCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr bool kResid = EPI == EPI_GATE_RESID;
+  static constexpr int kStages = (BN == 256) ? (kResid ? 3 : 4) : (kResid ? 4 : 5);
   static constexpr int kABytes = CV_BM * CV_BK * 2;
   static constexpr int kBBytes = BN * CV_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + (kResid ? 4 : 2) * EPI_STAGE_BYTES + 1024 + 256;
   static constexpr int kTmemCols = 2 * BN;
 };
 
 struct ConvArgs {
   const CUtensorMap* in_maps;  // [n_latents] device array, 64-byte aligned entries
+  const CUtensorMap* out_maps; // [n_latents] output maps {Cout, Wout, Hout}, box {64, 8, 16}
+  const CUtensorMap* res_maps; // [n_latents] residual maps (same geometry) or null
   const int4* tiles;           // [n_mtiles] {latent, y0, x0, 0} in OUTPUT pixel coordinates
   const int4* lat;             // [n_latents] {output row offset, Hout, Wout, 0}
   int n_mtiles, Cin, Cout, stride;
@@ -39,18 +43,21 @@ struct ConvArgs {
 template <int BN, int EPI>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, int M_total) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + Cfg::kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* stageC = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint8_t* stageR = stageC + 2 * EPI_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stageR + (Cfg::kResid ? 2 : 0) * EPI_STAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::kStages;
   uint64_t* tfull = bars + 2 * Cfg::kStages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* rfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -68,6 +75,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 4);
+      mbar_init(&rfull[i], 1);
     }
     fence_barrier_init();
   }
@@ -138,32 +146,66 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------ epilogue (TMA-staged)
     const int q = warp & 3;
+    const int r = q * 32 + lane;              // row in tile: pixel (r / 8, r % 8) of the block
+    const bool leader = threadIdx.x == 128;
+    const bool has_resid = (EPI == EPI_GATE_RESID) && a.res_maps != nullptr;
+    constexpr int NCH = BN / 64;
+    uint32_t ruse0 = 0, ruse1 = 0;
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
       const int4 tl = a.tiles[t / tiles_n];
       const int4 ld = a.lat[tl.x];
       const int n0 = (t % tiles_n) * BN;
+      if (has_resid && leader) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (c < NCH && n0 + c * 64 < a.Cout) {
+            mbar_expect_tx(&rfull[c], EPI_STAGE_BYTES);
+            tma_load_3d(stageR + c * EPI_STAGE_BYTES, a.res_maps + tl.x, &rfull[c], n0 + c * 64, tl.z, tl.y);
+          }
+        }
+      }
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
-      const int r = q * 32 + lane;              // row in tile: (r / 8, r % 8) pixel in the block
       const int y = tl.y + r / CV_TW, x = tl.z + r % CV_TW;
-      const int row = (y < ld.y && x < ld.z) ? ld.x + y * ld.z + x : M_total;
+      const bool row_ok = y < ld.y && x < ld.z;
+      const int row = row_ok ? ld.x + y * ld.z + x : M_total;
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
+      for (int c = 0; c < NCH; ++c) {
+        const int nc = n0 + c * 64;
+        if (nc >= a.Cout) break;
+        const int b = c & 1;
         float v[64];
         tmem_ld32(t_row + c * 64, reinterpret_cast<uint32_t*>(v));
         tmem_ld32(t_row + c * 64 + 32, reinterpret_cast<uint32_t*>(v) + 32);
         tmem_wait_ld();
-        epilogue_chunk64<EPI>(e, v, row, n0 + c * 64, M_total, a.Cout);
+        if (has_resid) {
+          mbar_wait(&rfull[b], (b ? ruse1 : ruse0) & 1);
+          if (b) ++ruse1; else ++ruse0;
+        }
+        epilogue_math64<EPI>(e, v, row, row_ok, nc, a.Cout, has_resid ? stageR + b * EPI_STAGE_BYTES : nullptr, r);
+        epilogue_stage64<EPI>(stageC + b * EPI_STAGE_BYTES, v, r);
+        fence_proxy_async();
+        if (leader) tma_store_wait_read<0>();
+        named_barrier<1, 128>();
+        if (leader) {
+          tma_store_3d(a.out_maps + tl.x, stageC + b * EPI_STAGE_BYTES, nc, tl.z, tl.y);
+          tma_store_commit();
+          if (has_resid && c + 2 < NCH && nc + 128 < a.Cout) {
+            mbar_expect_tx(&rfull[b], EPI_STAGE_BYTES);
+            tma_load_3d(stageR + b * EPI_STAGE_BYTES, a.res_maps + tl.x, &rfull[b], nc + 128, tl.z, tl.y);
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
+    if (leader) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -177,7 +219,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
 template <int BN, int EPI>
 static int launch_conv(const CUtensorMap& tmW, const ConvArgs& a, const EpiArgs& e, int M_total,
                        int num_sms, cudaStream_t stream) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, EPI>;
   auto kern = conv3x3_kernel<BN, EPI>;
   static bool configured = false;
   if (!configured) {
@@ -212,7 +254,7 @@ using namespace b200;
 // composition. in_desc: int32 [n][4] = {input row offset, Hin, Win, 0}.
 extern "C" int b200_conv3x3_encode_maps(const void* x, int ldx, int Cin, const int32_t* in_desc_host,
                                         int n_latents, int stride, void* maps_host) {
-  if (!x || !in_desc_host || !maps_host || n_latents <= 0 || (Cin % CV_BK) || (ldx & 7) ||
+  if (!x || !in_desc_host || !maps_host || n_latents <= 0 || (Cin & 7) || (ldx & 7) ||
       (stride != 1 && stride != 2))
     return B200_ERR_INVALID;
   CUtensorMap* out = static_cast<CUtensorMap*>(maps_host);
@@ -238,13 +280,16 @@ extern "C" int b200_conv3x3_encode_maps(const void* x, int ldx, int Cin, const i
   return B200_OK;
 }
 
-extern "C" int b200_conv3x3_bf16(const void* in_maps_dev, const int32_t* tiles_dev, int n_mtiles,
+extern "C" int b200_conv3x3_bf16(const void* in_maps_dev, const void* out_maps_dev,
+                                 const void* resid_maps_dev, const int32_t* tiles_dev, int n_mtiles,
                                  const int32_t* out_lat_dev, int Cin, int Cout, int stride,
                                  const void* Wt, int M_total, int epi_mode,
                                  const B200EpilogueDesc* ep, void* stream_) {
-  if (!in_maps_dev || !tiles_dev || !out_lat_dev || !Wt || !ep || !ep->C || n_mtiles <= 0)
+  if (!in_maps_dev || !out_maps_dev || !tiles_dev || !out_lat_dev || !Wt || !ep || n_mtiles <= 0)
     return B200_ERR_INVALID;
-  if ((Cin % CV_BK) || (Cout & 7) || (ep->ldc & 7) || (stride != 1 && stride != 2))
+  if ((reinterpret_cast<uintptr_t>(out_maps_dev) & 63) || (reinterpret_cast<uintptr_t>(resid_maps_dev) & 63))
+    return B200_ERR_INVALID;
+  if ((Cin % CV_BK) || (Cout & 7) || (stride != 1 && stride != 2))
     return B200_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(in_maps_dev) & 63) != 0) return B200_ERR_INVALID;
   if (epi_mode == EPI_ROWVEC && (!ep->rowvec || !ep->row_group)) return B200_ERR_INVALID;
@@ -258,7 +303,9 @@ extern "C" int b200_conv3x3_bf16(const void* in_maps_dev, const int32_t* tiles_d
   uint32_t b[2] = {CV_BK, uint32_t(BN)};
   int rc = get_tmap_bf16_sw128(&tmW, Wt, 2, d, s, b);
   if (rc) return rc;
-  ConvArgs a{static_cast<const CUtensorMap*>(in_maps_dev), reinterpret_cast<const int4*>(tiles_dev),
+  ConvArgs a{static_cast<const CUtensorMap*>(in_maps_dev),
+             static_cast<const CUtensorMap*>(out_maps_dev),
+             static_cast<const CUtensorMap*>(resid_maps_dev), reinterpret_cast<const int4*>(tiles_dev),
              reinterpret_cast<const int4*>(out_lat_dev), n_mtiles, Cin, Cout, stride};
   EpiArgs e;
   e.C = ep->C; e.ldc = ep->ldc; e.out_fp32 = ep->out_fp32;

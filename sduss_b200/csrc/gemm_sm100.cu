@@ -15,13 +15,17 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int GEMM_THREADS = 256;
 
-template <int BN>
+template <int BN, int EPI>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  // residual epilogues need two extra 16 KB staging tiles -> one pipeline stage less
+  static constexpr bool kResid = EPI == EPI_GATE_RESID;
+  static constexpr int kStages = (BN == 256) ? (kResid ? 3 : 4) : (kResid ? 4 : 5);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // + 2 output staging tiles + 2 residual staging tiles (16 KB each) for the TMA epilogue
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + (kResid ? 4 : 2) * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (256 or 512)
 };
 
@@ -32,19 +36,23 @@ struct GemmShape {
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                  GemmShape s, EpiArgs e) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + Cfg::kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* stageC = smem + Cfg::kStages * Cfg::kStageBytes;  // [2][16 KB] output chunks
+  uint8_t* stageR = stageC + 2 * EPI_STAGE_BYTES;            // [2][16 KB] residual chunks (kResid)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stageR + (Cfg::kResid ? 2 : 0) * EPI_STAGE_BYTES);
   uint64_t* full = bars;                       // [kStages]
   uint64_t* empty = bars + Cfg::kStages;       // [kStages]
   uint64_t* tfull = bars + 2 * Cfg::kStages;   // [2]
   uint64_t* tempty = tfull + 2;                // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* rfull = tempty + 2;                // [2] residual chunk landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -66,6 +74,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 4);
+      mbar_init(&rfull[i], 1);
     }
     fence_barrier_init();
   }
@@ -135,27 +144,69 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
     const int q = warp & 3;
+    const int r = q * 32 + lane;          // row inside the tile == TMEM lane
+    const bool leader = threadIdx.x == 128;
+    const bool has_resid = (EPI == EPI_GATE_RESID) && e.resid != nullptr;
+    constexpr int NCH = BN / 64;
+    uint32_t ruse0 = 0, ruse1 = 0;
     int it = 0;
+    if (leader) {
+      tma_prefetch_desc(&tmC);
+      if (has_resid) tma_prefetch_desc(&tmR);
+    }
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
       const int m0 = (t / tiles_n) * BM;
       const int n0 = (t % tiles_n) * BN;
+      if (has_resid && leader) {  // residual chunks 0 and 1 fly while the main loop finishes
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (c < NCH && n0 + c * 64 < s.N) {
+            mbar_expect_tx(&rfull[c], EPI_STAGE_BYTES);
+            tma_load_2d(stageR + c * EPI_STAGE_BYTES, &tmR, &rfull[c], n0 + c * 64, m0);
+          }
+        }
+      }
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
+      const int row = m0 + r;
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
+      for (int c = 0; c < NCH; ++c) {
+        const int nc = n0 + c * 64;
+        if (nc >= s.N) break;
+        const int b = c & 1;
         float v[64];
         tmem_ld32(t_row + c * 64, reinterpret_cast<uint32_t*>(v));
         tmem_ld32(t_row + c * 64 + 32, reinterpret_cast<uint32_t*>(v) + 32);
         tmem_wait_ld();
-        epilogue_chunk64<EPI>(e, v, row, n0 + c * 64, s.M, s.N);
+        if (e.out_fp32) {  // fp32 outputs keep the direct store path
+          epilogue_chunk64<EPI>(e, v, row, nc, s.M, s.N);
+          continue;
+        }
+        if (has_resid) {
+          mbar_wait(&rfull[b], (b ? ruse1 : ruse0) & 1);
+          if (b) ++ruse1; else ++ruse0;
+        }
+        epilogue_math64<EPI>(e, v, row, row < s.M, nc, s.N, has_resid ? stageR + b * EPI_STAGE_BYTES : nullptr, r);
+        epilogue_stage64<EPI>(stageC + b * EPI_STAGE_BYTES, v, r);
+        fence_proxy_async();                       // smem writes -> visible to the TMA engine
+        if (leader) tma_store_wait_read<0>();      // chunk c-1 has left its staging tile
+        named_barrier<1, 128>();
+        if (leader) {
+          tma_store_2d(&tmC, stageC + b * EPI_STAGE_BYTES, EPI == EPI_GEGLU ? (nc >> 1) : nc, m0);
+          tma_store_commit();
+          if (has_resid && c + 2 < NCH && nc + 128 < s.N) {  // stageR[b] was fully read before the barrier
+            mbar_expect_tx(&rfull[b], EPI_STAGE_BYTES);
+            tma_load_2d(stageR + b * EPI_STAGE_BYTES, &tmR, &rfull[b], nc + 128, m0);
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
+    if (leader) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -167,9 +218,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int BN, int EPI>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmShape s,
-                       const EpiArgs& e, int num_sms, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                       const CUtensorMap& tmR, GemmShape s, const EpiArgs& e, int num_sms,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, EPI>;
   auto kern = gemm_bf16_kernel<BN, EPI>;
   static bool configured = false;
   if (!configured) {
@@ -180,20 +232,21 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmShape
   }
   const int tiles = ((s.M + BM - 1) / BM) * ((s.N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(tmA, tmB, s, e);
+  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmR, s, e);
   return launch_status();
 }
 
 template <int BN>
-static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmShape s,
+static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                        const CUtensorMap& tmC, const CUtensorMap& tmR, GemmShape s,
                         const EpiArgs& e, int num_sms, cudaStream_t stream) {
   switch (epi) {
-    case EPI_BIAS: return launch_gemm<BN, EPI_BIAS>(tmA, tmB, s, e, num_sms, stream);
-    case EPI_GELU_TANH: return launch_gemm<BN, EPI_GELU_TANH>(tmA, tmB, s, e, num_sms, stream);
-    case EPI_GATE_RESID: return launch_gemm<BN, EPI_GATE_RESID>(tmA, tmB, s, e, num_sms, stream);
-    case EPI_QK_RMSNORM: return launch_gemm<BN, EPI_QK_RMSNORM>(tmA, tmB, s, e, num_sms, stream);
-    case EPI_GEGLU: return launch_gemm<BN, EPI_GEGLU>(tmA, tmB, s, e, num_sms, stream);
-    case EPI_ROWVEC: return launch_gemm<BN, EPI_ROWVEC>(tmA, tmB, s, e, num_sms, stream);
+    case EPI_BIAS: return launch_gemm<BN, EPI_BIAS>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
+    case EPI_GELU_TANH: return launch_gemm<BN, EPI_GELU_TANH>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
+    case EPI_GATE_RESID: return launch_gemm<BN, EPI_GATE_RESID>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
+    case EPI_QK_RMSNORM: return launch_gemm<BN, EPI_QK_RMSNORM>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
+    case EPI_GEGLU: return launch_gemm<BN, EPI_GEGLU>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
+    case EPI_ROWVEC: return launch_gemm<BN, EPI_ROWVEC>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
     default: return B200_ERR_INVALID;
   }
 }
@@ -260,6 +313,23 @@ extern "C" int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
   e.rms_eps = ep->rms_eps;
   e.q_scale = ep->q_scale;
   GemmShape s{M, N, K};
-  return bn256 ? dispatch_epi<256>(epi_mode, tmA, tmB, s, e, sms, stream)
-               : dispatch_epi<128>(epi_mode, tmA, tmB, s, e, sms, stream);
+  // output / residual tensor maps of the staged epilogue (bf16 outputs only)
+  CUtensorMap tmC = tmA, tmR = tmA;
+  if (!ep->out_fp32) {
+    if (reinterpret_cast<uintptr_t>(ep->C) & 15) return B200_ERR_INVALID;
+    const bool geglu = epi_mode == EPI_GEGLU;
+    uint64_t dC[2] = {uint64_t(geglu ? N / 2 : N), uint64_t(M)}, sC[1] = {uint64_t(ep->ldc) * 2};
+    uint32_t bC[2] = {geglu ? 32u : 64u, BM};
+    rc = get_tmap_bf16(&tmC, ep->C, 2, dC, sC, bC, geglu ? 0 : 128);
+    if (rc) return rc;
+    if (epi_mode == EPI_GATE_RESID && ep->resid) {
+      if ((reinterpret_cast<uintptr_t>(ep->resid) & 15) || (ep->ldr & 7)) return B200_ERR_INVALID;
+      uint64_t dR[2] = {uint64_t(N), uint64_t(M)}, sR[1] = {uint64_t(ep->ldr) * 2};
+      uint32_t bR[2] = {64u, BM};
+      rc = get_tmap_bf16(&tmR, ep->resid, 2, dR, sR, bR, 128);
+      if (rc) return rc;
+    }
+  }
+  return bn256 ? dispatch_epi<256>(epi_mode, tmA, tmB, tmC, tmR, s, e, sms, stream)
+               : dispatch_epi<128>(epi_mode, tmA, tmB, tmC, tmR, s, e, sms, stream);
 }

@@ -28,7 +28,7 @@ static EncodeTiledFn resolve_encode() {
 }
 
 struct Key {
-  uint64_t v[1 + 1 + 5 + 4 + 5];
+  uint64_t v[1 + 1 + 5 + 4 + 5 + 1];
   bool operator==(const Key& o) const { return std::memcmp(v, o.v, sizeof(v)) == 0; }
 };
 struct KeyHash {
@@ -44,6 +44,11 @@ struct KeyHash {
 
 int get_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                         const uint64_t* strides_bytes, const uint32_t* box) {
+  return get_tmap_bf16(out, base, rank, dims, strides_bytes, box, 128);
+}
+
+int get_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box, int swizzle) {
   if (rank < 2 || rank > 5 || base == nullptr) return B200_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return B200_ERR_INVALID;
   Key key;
@@ -53,6 +58,7 @@ int get_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uint
   for (int i = 0; i < rank; ++i) key.v[2 + i] = dims[i];
   for (int i = 0; i < rank - 1; ++i) key.v[7 + i] = strides_bytes[i];
   for (int i = 0; i < rank; ++i) key.v[11 + i] = box[i];
+  key.v[16] = static_cast<uint64_t>(swizzle);
 
   static std::mutex mu;
   static std::unordered_map<Key, CUtensorMap, KeyHash> cache;
@@ -82,7 +88,9 @@ int get_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uint
   CUtensorMap m;
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
                    const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                   : swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return B200_ERR_DRIVER;
   {

@@ -15,6 +15,9 @@ namespace b200 {
 // Returns B200_OK or an error code. Results are cached by value of all arguments.
 int get_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                         const uint64_t* strides_bytes, const uint32_t* box);
+// Same with an explicit swizzle: 0 = none, 64 = SWIZZLE_64B, 128 = SWIZZLE_128B.
+int get_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box, int swizzle);
 
 inline int launch_status() {
   cudaError_t e = cudaGetLastError();

@@ -19,12 +19,14 @@ launch_count = 0
 profile = None
 
 
-def _count(name):
+def _count(name, tag=None):
     global launch_count
     launch_count += 1
     if profile is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         profile.setdefault(name, []).append(ev)
+        if tag is not None:
+            profile.setdefault("tags", []).append((name, tag, ev))
         ev[0].record()
         return ev[1]
     return None
@@ -95,7 +97,7 @@ def gemm(a, w, out=None, *, epi=EPI_BIAS, bias=None, resid=None, gate=None, row_
     d.rms_wq, d.rms_wk = _ptr(rms_wq), _ptr(rms_wk)
     d.rms_q_cols, d.rms_k_cols = rms_q_cols, rms_k_cols
     d.rms_eps, d.q_scale = rms_eps, q_scale
-    _ev = _count("b200_gemm_bf16")
+    _ev = _count("b200_gemm_bf16", (M, N, K, epi))
     check(lib.b200_gemm_bf16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), M, N, K, epi,
                              ctypes.byref(d), _stream()), "b200_gemm_bf16")
     if _ev is not None:
@@ -257,13 +259,15 @@ def conv3x3_encode_maps(x, cin, in_desc_host, stride):
     return dev
 
 
-def conv3x3(maps_dev, tiles, n_mtiles, out_lat, cin, cout, stride, weight, out, *, epi=EPI_BIAS,
-            bias=None, resid=None, rowvec=None, row_group=None):
-    """out[M_total, cout] = conv3x3(x) through the implicit-GEMM kernel (see conv_sm100.cu)."""
+def conv3x3(maps_dev, tiles, n_mtiles, out_lat, cin, cout, stride, weight, out, *, out_maps,
+            resid_maps=None, epi=EPI_BIAS, bias=None, rowvec=None, row_group=None):
+    """out[M_total, cout] = conv3x3(x) through the implicit-GEMM kernel (see conv_sm100.cu).
+    out_maps / resid_maps: conv3x3_encode_maps(out or resid buffer, cout, out_desc_host, 1)."""
     _req(weight), _req(out)
-    d = _epi_desc(out, bias=bias, resid=resid, rowvec=rowvec, row_group=row_group)
-    _ev = _count("b200_conv3x3_bf16")
-    check(lib.b200_conv3x3_bf16(_ptr(maps_dev), _ptr(tiles), n_mtiles, _ptr(out_lat), cin, cout,
+    d = _epi_desc(out, bias=bias, rowvec=rowvec, row_group=row_group)
+    _ev = _count("b200_conv3x3_bf16", (out.shape[0], cout, 9 * cin, stride))
+    check(lib.b200_conv3x3_bf16(_ptr(maps_dev), _ptr(out_maps), _ptr(resid_maps), _ptr(tiles),
+                                n_mtiles, _ptr(out_lat), cin, cout,
                                 stride, _ptr(weight), out.shape[0], epi, ctypes.byref(d),
                                 _stream()), "b200_conv3x3_bf16")
     if _ev is not None:

@@ -269,13 +269,16 @@ class B200UNet(torch.nn.Module):
                            eps=self.cfg.norm_eps if eps is None else eps, silu=silu)
         return out
 
-    def _conv(self, pl, x, cin, name, in_level, stride, out, **epi):
+    def _conv(self, pl, x, cin, name, in_level, stride, out, resid=None, **epi):
         out_level = in_level + (1 if stride == 2 else 0)
         lay = pl.levels[out_level]
         w = self.w[name + ".weight"]
+        cout = w.shape[0]
         maps = pl.conv_maps(x, cin, in_level, stride)
-        return ops.conv3x3(maps, lay.tiles, lay.n_tiles, lay.desc, cin, w.shape[0], stride, w, out,
-                           bias=self.w[name + ".bias"], **epi)
+        out_maps = pl.conv_maps(out, cout, out_level, 1)
+        resid_maps = pl.conv_maps(resid, cout, out_level, 1) if resid is not None else None
+        return ops.conv3x3(maps, lay.tiles, lay.n_tiles, lay.desc, cin, cout, stride, w, out,
+                           out_maps=out_maps, resid_maps=resid_maps, bias=self.w[name + ".bias"], **epi)
 
     def _resnet(self, pl, x, name, level, temb_all):
         lay = pl.levels[level]

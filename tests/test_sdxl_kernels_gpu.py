@@ -50,15 +50,17 @@ def test_conv3x3(cuda, sizes, cin, cout, stride):
     maps = ops.conv3x3_encode_maps(x, cin, lin.desc_host, stride)
     out = torch.zeros(lout.T, cout, device=cuda, dtype=torch.bfloat16)
     resid = _rand((lout.T, cout), 3).cuda().bfloat16()
-    ops.conv3x3(maps, lout.tiles, lout.n_tiles, lout.desc, cin, cout, stride, wt, out,
-                epi=ops.EPI_GATE_RESID, bias=bias.cuda().bfloat16(), resid=resid)
+    omaps = ops.conv3x3_encode_maps(out, cout, lout.desc_host, 1)
+    rmaps = ops.conv3x3_encode_maps(resid, cout, lout.desc_host, 1)
+    ops.conv3x3(maps, lout.tiles, lout.n_tiles, lout.desc, cin, cout, stride, wt, out, out_maps=omaps,
+                resid_maps=rmaps, epi=ops.EPI_GATE_RESID, bias=bias.cuda().bfloat16())
     ref = [F.conv2d(t[None], wgt, bias, stride=stride, padding=1)[0] for t in lats]
     ref = _pack(ref) + resid.float().cpu()
     err = (out.float().cpu() - ref).abs().max().item()
     assert err <= 2e-2 * ref.abs().max().item(), err
     # per-request row vector epilogue (time embedding add)
     rv = _rand((len(sizes), cout), 4).cuda().bfloat16()
-    ops.conv3x3(maps, lout.tiles, lout.n_tiles, lout.desc, cin, cout, stride, wt, out,
+    ops.conv3x3(maps, lout.tiles, lout.n_tiles, lout.desc, cin, cout, stride, wt, out, out_maps=omaps,
                 epi=ops.EPI_ROWVEC, bias=bias.cuda().bfloat16(), rowvec=rv, row_group=lout.row_group)
     ref2 = _pack([F.conv2d(t[None], wgt, bias, stride=stride, padding=1)[0] + rv[i].float().cpu()[:, None, None]
                   for i, t in enumerate(lats)])
