@@ -227,6 +227,7 @@ def run_b200(args, rank, world, local_rank):
     ms_step = timed(step, args.steps, 0)
     launches = ops.launch_count - n0
     prof, ops.profile = ops.profile, None
+    prof.pop("tags", None)
     clk = clocks.stop()
     torch.cuda.synchronize()
     attn_ms = sum(a.elapsed_time(b) for a, b in prof.get("b200_attn_varlen_bf16", []))
@@ -380,6 +381,7 @@ def run_b200_sdxl(args, rank, world, local_rank):
     ms_prof = timed(args.steps)
     launches = ops.launch_count - n0
     prof, ops.profile = ops.profile, None
+    prof.pop("tags", None)
     clk = clocks.stop()
     torch.cuda.synchronize()
     per_kernel = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in prof.items()}

@@ -129,6 +129,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const int head = blockIdx.y;
 
+  // work tables are written once per plan (not by the preceding kernel): safe before pdl_wait()
   const int4 item = reinterpret_cast<const int4*>(a.work_items)[blockIdx.x];
   const int* st = a.seq_table + item.x * 8;
   const int q_seg = item.y;
@@ -166,6 +167,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
   // TMEM columns: S_t at 128 t, P_t (packed bf16) at 256 + 64 t, O_t at 384 + 64 t. S and P are
   // separate so that S_t(j+1) = Q_t K(j+1)^T can be issued while softmax still works on tile j.
   const uint32_t tS = tmem_base;
@@ -491,7 +494,7 @@ extern "C" int b200_attn_varlen_bf16(const B200AttnSource* src_a, const B200Attn
   }
 #endif
   dim3 grid(n_items, n_heads);
-  attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      tm[0][0], tm[1][0], tm[0][1], tm[1][1], tm[0][2], tm[1][2], a);
-  return launch_status();
+  return launch_pdl(attn_fwd_kernel, grid, dim3(ATT_THREADS), ATT_SMEM,
+                    reinterpret_cast<cudaStream_t>(stream_), tm[0][0], tm[1][0], tm[0][1], tm[1][1],
+                    tm[0][2], tm[1][2], a);
 }

@@ -87,6 +87,8 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -230,8 +232,7 @@ static int launch_conv(const CUtensorMap& tmW, const ConvArgs& a, const EpiArgs&
   }
   const int tiles = a.n_mtiles * ((a.Cout + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, CV_THREADS, Cfg::kSmemBytes, stream>>>(tmW, a, e, M_total);
-  return launch_status();
+  return launch_pdl(kern, dim3(grid), dim3(CV_THREADS), Cfg::kSmemBytes, stream, tmW, a, e, M_total);
 }
 
 template <int BN>

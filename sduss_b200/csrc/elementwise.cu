@@ -52,6 +52,8 @@ struct LnArgs {
 constexpr int LN_MAXIT = 8;  // 8 iterations * 32 lanes * 8 elements = 2048 columns
 
 __global__ void __launch_bounds__(256) ln_mod_kernel(LnArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= a.T) return;
@@ -280,9 +282,8 @@ extern "C" int b200_layernorm_mod_bf16(const void* x, int ldx, int T, int D, flo
            shift_col, scale_col, static_cast<bf16*>(y), ldy, shift2_col, scale2_col,
            static_cast<bf16*>(y2), ldy2};
   const int rows_per_block = 8;
-  ln_mod_kernel<<<(T + rows_per_block - 1) / rows_per_block, 256, 0,
-                  reinterpret_cast<cudaStream_t>(stream)>>>(a);
-  return launch_status();
+  return launch_pdl(ln_mod_kernel, dim3((T + rows_per_block - 1) / rows_per_block), dim3(256), 0,
+                    reinterpret_cast<cudaStream_t>(stream), a);
 }
 
 extern "C" int b200_silu_bf16(const void* x, void* y, long long n, void* stream) {

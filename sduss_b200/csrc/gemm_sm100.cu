@@ -7,6 +7,8 @@
 // diffusers FeedForward / AdaLayerNorm linears they wrap).
 #include "../../include/sduss_b200.h"
 #include "epilogue.cuh"
+#include <cstdlib>
+
 #include "host_util.h"
 
 namespace b200 {
@@ -33,7 +35,10 @@ struct GemmShape {
   int M, N, K;
 };
 
-template <int BN, int EPI>
+// MC = 2: CTA pairs (cluster of 2 along M) share every W tile: each CTA fetches half of it and
+// multicasts it into both CTAs' shared memory, cutting L2 -> SM operand traffic by a third
+// (the 128x256x64 main loop is L2-bandwidth bound: 96 B/clk/SM of operand loads on 148 SMs).
+template <int BN, int EPI, int MC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -57,10 +62,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int tiles_m = (s.M + BM - 1) / BM;
   const int tiles_n = (s.N + BN - 1) / BN;
+  // MC == 2: tiles are enumerated per CTA pair; rank r of the pair owns M tile 2 * pair + r
+  // (a pair's second tile may lie beyond M: TMA zero-fills its loads and clips its stores).
+  const int tiles_m = (s.M + BM * MC - 1) / (BM * MC);
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (s.K + BK - 1) / BK;
+  const uint32_t rank = MC == 2 ? cluster_ctarank() : 0;
+  const int first_tile = MC == 2 ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int tile_step = MC == 2 ? int(gridDim.x >> 1) : int(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -69,7 +79,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], MC);  // released by the MMA warp of every CTA the stage is multicast to
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -85,21 +95,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if constexpr (MC == 2) cluster_sync_all();  // peer barriers are initialised before any multicast
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();  // the prologue above overlapped the previous kernel; its outputs are visible now
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t / tiles_n) * BM;
+    for (int t = first_tile; t < num_tiles; t += tile_step) {
+      const int m0 = ((t / tiles_n) * MC + int(rank)) * BM;
       const int n0 = (t % tiles_n) * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (lane == 0) {
           mbar_expect_tx(&full[stage], Cfg::kStageBytes);
           tma_load_2d(smemA + stage * Cfg::kABytes, &tmA, &full[stage], kb * BK, m0);
-          tma_load_2d(smemB + stage * Cfg::kBBytes, &tmB, &full[stage], kb * BK, n0);
+          if constexpr (MC == 2) {
+            // my half of the W tile (BN/2 rows), delivered to both CTAs of the pair
+            tma_load_2d_mc(smemB + stage * Cfg::kBBytes + rank * (Cfg::kBBytes / 2), &tmB, &full[stage],
+                           kb * BK, n0 + int(rank) * (BN / 2), uint16_t(3));
+          } else {
+            tma_load_2d(smemB + stage * Cfg::kBBytes, &tmB, &full[stage], kb * BK, n0);
+          }
         }
         __syncwarp();
         if (++stage == Cfg::kStages) {
@@ -114,7 +133,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = first_tile; t < num_tiles; t += tile_step, ++it) {
       const int acc = it & 1;
       mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -131,7 +150,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             umma_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc,
                     (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);
+          if constexpr (MC == 2) umma_commit_mc(&empty[stage], uint16_t(3));
+          else umma_commit(&empty[stage]);
           if (kb == num_kb - 1) umma_commit(&tfull[acc]);
         }
         __syncwarp();
@@ -154,9 +174,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tma_prefetch_desc(&tmC);
       if (has_resid) tma_prefetch_desc(&tmR);
     }
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = first_tile; t < num_tiles; t += tile_step, ++it) {
       const int acc = it & 1;
-      const int m0 = (t / tiles_n) * BM;
+      const int m0 = ((t / tiles_n) * MC + int(rank)) * BM;
       const int n0 = (t % tiles_n) * BN;
       if (has_resid && leader) {  // residual chunks 0 and 1 fly while the main loop finishes
 #pragma unroll
@@ -211,18 +231,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC == 2) cluster_sync_all();  // the peer may still arrive on my barriers until here
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BN, int EPI>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-                       const CUtensorMap& tmR, GemmShape s, const EpiArgs& e, int num_sms,
-                       cudaStream_t stream) {
+template <int BN, int EPI, int MC>
+static int launch_gemm_mc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                          const CUtensorMap& tmR, GemmShape s, const EpiArgs& e, int num_sms,
+                          cudaStream_t stream) {
   using Cfg = GemmCfg<BN, EPI>;
-  auto kern = gemm_bf16_kernel<BN, EPI>;
+  auto kern = gemm_bf16_kernel<BN, EPI, MC>;
   static bool configured = false;
   if (!configured) {
     cudaError_t err =
@@ -230,23 +251,32 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     if (err != cudaSuccess) return static_cast<int>(err);
     configured = true;
   }
-  const int tiles = ((s.M + BM - 1) / BM) * ((s.N + BN - 1) / BN);
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmR, s, e);
-  return launch_status();
+  const int tiles = ((s.M + BM * MC - 1) / (BM * MC)) * ((s.N + BN - 1) / BN);
+  const int slots = num_sms / MC;
+  const int grid = (tiles < slots ? tiles : slots) * MC;
+  return launch_pdl_cluster(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::kSmemBytes, stream, MC, tmA, tmB,
+                            tmC, tmR, s, e);
+}
+
+template <int BN, int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                       const CUtensorMap& tmR, GemmShape s, const EpiArgs& e, int num_sms,
+                       cudaStream_t stream, bool multicast) {
+  return multicast ? launch_gemm_mc<BN, EPI, 2>(tmA, tmB, tmC, tmR, s, e, num_sms, stream)
+                   : launch_gemm_mc<BN, EPI, 1>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
 }
 
 template <int BN>
 static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
                         const CUtensorMap& tmC, const CUtensorMap& tmR, GemmShape s,
-                        const EpiArgs& e, int num_sms, cudaStream_t stream) {
+                        const EpiArgs& e, int num_sms, cudaStream_t stream, bool multicast) {
   switch (epi) {
-    case EPI_BIAS: return launch_gemm<BN, EPI_BIAS>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
-    case EPI_GELU_TANH: return launch_gemm<BN, EPI_GELU_TANH>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
-    case EPI_GATE_RESID: return launch_gemm<BN, EPI_GATE_RESID>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
-    case EPI_QK_RMSNORM: return launch_gemm<BN, EPI_QK_RMSNORM>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
-    case EPI_GEGLU: return launch_gemm<BN, EPI_GEGLU>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
-    case EPI_ROWVEC: return launch_gemm<BN, EPI_ROWVEC>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
+    case EPI_BIAS: return launch_gemm<BN, EPI_BIAS>(tmA, tmB, tmC, tmR, s, e, num_sms, stream, multicast);
+    case EPI_GELU_TANH: return launch_gemm<BN, EPI_GELU_TANH>(tmA, tmB, tmC, tmR, s, e, num_sms, stream, multicast);
+    case EPI_GATE_RESID: return launch_gemm<BN, EPI_GATE_RESID>(tmA, tmB, tmC, tmR, s, e, num_sms, stream, multicast);
+    case EPI_QK_RMSNORM: return launch_gemm<BN, EPI_QK_RMSNORM>(tmA, tmB, tmC, tmR, s, e, num_sms, stream, multicast);
+    case EPI_GEGLU: return launch_gemm<BN, EPI_GEGLU>(tmA, tmB, tmC, tmR, s, e, num_sms, stream, multicast);
+    case EPI_ROWVEC: return launch_gemm<BN, EPI_ROWVEC>(tmA, tmB, tmC, tmR, s, e, num_sms, stream, multicast);
     default: return B200_ERR_INVALID;
   }
 }
@@ -284,13 +314,18 @@ extern "C" int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
   const bool bn256 = (N >= 256) && (tiles256 >= sms);
   const int BN = bn256 ? 256 : 128;
 
+  // pair CTAs (W-tile multicast) whenever there are at least two M tiles and enough pairs of
+  // tiles to occupy the 74 SM pairs
+  static const bool mc_allowed = []() { const char* v = getenv("SDUSS_B200_NO_MULTICAST"); return !(v && v[0] == '1'); }();
+  const long pair_tiles = long((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+  const bool multicast = mc_allowed && M > BM && pair_tiles >= (sms / 2) / 2;
   CUtensorMap tmA, tmB;
   uint64_t dA[2] = {uint64_t(K), uint64_t(M)}, sA[1] = {uint64_t(lda) * 2};
   uint32_t bA[2] = {BK, BM};
   int rc = get_tmap_bf16_sw128(&tmA, A, 2, dA, sA, bA);
   if (rc) return rc;
   uint64_t dB[2] = {uint64_t(K), uint64_t(N)}, sB[1] = {uint64_t(ldw) * 2};
-  uint32_t bB[2] = {BK, uint32_t(BN)};
+  uint32_t bB[2] = {BK, uint32_t(multicast ? BN / 2 : BN)};
   rc = get_tmap_bf16_sw128(&tmB, W, 2, dB, sB, bB);
   if (rc) return rc;
 
@@ -330,6 +365,6 @@ extern "C" int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
       if (rc) return rc;
     }
   }
-  return bn256 ? dispatch_epi<256>(epi_mode, tmA, tmB, tmC, tmR, s, e, sms, stream)
-               : dispatch_epi<128>(epi_mode, tmA, tmB, tmC, tmR, s, e, sms, stream);
+  return bn256 ? dispatch_epi<256>(epi_mode, tmA, tmB, tmC, tmR, s, e, sms, stream, multicast)
+               : dispatch_epi<128>(epi_mode, tmA, tmB, tmC, tmR, s, e, sms, stream, multicast);
 }

@@ -26,4 +26,52 @@ inline int launch_status() {
 
 int device_sm_count();
 
+// SDUSS_B200_NO_PDL=1 disables programmatic dependent launch (plain stream order).
+bool pdl_enabled();
+
+// Launches `kern` with the programmatic-stream-serialization attribute (PDL). The kernel must
+// execute pdl_wait() before its first dependent global-memory access.
+template <typename... KArgs, typename... Args>
+inline int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                      Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t err = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  return err == cudaSuccess ? launch_status() : static_cast<int>(err);
+}
+
+// Same with a thread-block cluster of `cluster_x` CTAs along x (grid.x must be a multiple).
+template <typename... KArgs, typename... Args>
+inline int launch_pdl_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t st, int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  int n = 1;
+  if (cluster_x > 1) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = cluster_x;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    n = 2;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  cudaError_t err = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  return err == cudaSuccess ? launch_status() : static_cast<int>(err);
+}
+
 }  // namespace b200

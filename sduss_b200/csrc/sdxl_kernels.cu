@@ -43,6 +43,8 @@ constexpr int GN_MAXC = 2560;
 __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* x, int ldx, int C,
                                                        int cpg, int G, float* partial) {
   __shared__ float ch_sum[GN_MAXC], ch_sq[GN_MAXC];
+  pdl_launch_dependents();
+  pdl_wait();
   const int chunk = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = C >> 3;
@@ -82,24 +84,35 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* x, i
   }
 }
 
-// lat: [L][4] = {first chunk, number of chunks, 0, 0}
+// lat: [L][4] = {first chunk, number of chunks, 0, 0}. One warp per (latent, group): lanes stride
+// the chunk list, then a fixed-order fp64 shuffle tree (deterministic).
 __global__ void gn_finalize_kernel(const float* partial, const int4* lat, int L, int G, int cpg,
                                    float eps, float* stats) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (idx >= L * G) return;
   const int l = idx / G, g = idx % G;
   const int4 d = lat[l];
   double s = 0.0, q = 0.0;
-  for (int c = 0; c < d.y; ++c) {
+  for (int c = lane; c < d.y; c += 32) {
     s += double(partial[(size_t(d.x + c) * GN_MAXG + g) * 2]);
     q += double(partial[(size_t(d.x + c) * GN_MAXG + g) * 2 + 1]);
   }
-  const double n = double(d.y) * GN_CHUNK * cpg;
-  const double mean = s / n;
-  double var = q / n - mean * mean;
-  if (var < 0.0) var = 0.0;
-  stats[idx * 2] = float(mean);
-  stats[idx * 2 + 1] = float(1.0 / sqrt(var + double(eps)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    const double n = double(d.y) * GN_CHUNK * cpg;
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[idx * 2] = float(mean);
+    stats[idx * 2 + 1] = float(1.0 / sqrt(var + double(eps)));
+  }
 }
 
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* x, int ldx, long T,
@@ -108,6 +121,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* x, i
                                                        const __nv_bfloat16* gamma,
                                                        const __nv_bfloat16* beta, int silu,
                                                        __nv_bfloat16* y, int ldy) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nvec = C >> 3;
   const long i = blockIdx.x * long(blockDim.x) + threadIdx.x;
   if (i >= T * nvec) return;
@@ -185,6 +200,8 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* x, int ldx, const int4* i
 // dst[:, dst_col : dst_col + cols] = src[:, src_col : src_col + cols]  (skip-connection concat)
 __global__ void copy_cols_kernel(const __nv_bfloat16* src, int lds, __nv_bfloat16* dst, int ldd,
                                  long T, int cols) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nvec = cols >> 3;
   const long idx = blockIdx.x * long(blockDim.x) + threadIdx.x;
   if (idx >= T * nvec) return;
@@ -252,15 +269,18 @@ extern "C" int b200_groupnorm_nhwc_bf16(const void* x, int ldx, long long T, int
   const int chunks = int(T / GN_CHUNK);
   float* partial = static_cast<float*>(workspace);
   float* stats = partial + size_t(chunks) * GN_MAXG * 2;
-  gn_stats_kernel<<<chunks, 256, 0, ST(stream)>>>(static_cast<const bf16*>(x), ldx, C, cpg, groups, partial);
-  gn_finalize_kernel<<<(n_latents * groups + 127) / 128, 128, 0, ST(stream)>>>(
-      partial, reinterpret_cast<const int4*>(lat_chunks), n_latents, groups, cpg, eps, stats);
+  int rc = launch_pdl(gn_stats_kernel, dim3(chunks), dim3(256), 0, ST(stream),
+                      static_cast<const bf16*>(x), ldx, C, cpg, groups, partial);
+  if (rc) return rc;
+  rc = launch_pdl(gn_finalize_kernel, dim3((n_latents * groups + 3) / 4), dim3(128), 0, ST(stream),
+                  static_cast<const float*>(partial), reinterpret_cast<const int4*>(lat_chunks),
+                  n_latents, groups, cpg, eps, stats);
+  if (rc) return rc;
   const long total = T * (C >> 3);
-  gn_apply_kernel<<<unsigned((total + 255) / 256), 256, 0, ST(stream)>>>(
-      static_cast<const bf16*>(x), ldx, T, C, cpg, groups, stats, row_group,
-      static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta), silu, static_cast<bf16*>(y),
-      ldy);
-  return launch_status();
+  return launch_pdl(gn_apply_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, ST(stream),
+                    static_cast<const bf16*>(x), ldx, long(T), C, cpg, groups,
+                    static_cast<const float*>(stats), row_group, static_cast<const bf16*>(gamma),
+                    static_cast<const bf16*>(beta), silu, static_cast<bf16*>(y), ldy);
 }
 
 extern "C" int b200_pack_im2col3x3(const uint64_t* lat_ptr, const int32_t* desc, int n_latents,
@@ -301,9 +321,8 @@ extern "C" int b200_copy_cols_bf16(const void* src, int lds, void* dst, int ldd,
   if (!src || !dst || T <= 0 || cols <= 0 || (cols & 7) || (lds & 7) || (ldd & 7))
     return B200_ERR_INVALID;
   const long total = T * (cols >> 3);
-  copy_cols_kernel<<<unsigned((total + 255) / 256), 256, 0, ST(stream)>>>(
-      static_cast<const bf16*>(src), lds, static_cast<bf16*>(dst), ldd, T, cols);
-  return launch_status();
+  return launch_pdl(copy_cols_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, ST(stream),
+                    static_cast<const bf16*>(src), lds, static_cast<bf16*>(dst), ldd, long(T), cols);
 }
 
 extern "C" int b200_split_patches(const uint64_t* lat_ptr, const int32_t* ldesc,

@@ -225,6 +225,12 @@ class B200SD3Transformer2DModel(torch.nn.Module):
         return cls(model.state_dict(), model.config, device=device)
 
     # ------------------------------------------------------------------
+    def _side_stream(self):
+        st = getattr(self, "_side", None)
+        if st is None:
+            st = self._side = torch.cuda.Stream(device=self.device)
+        return st
+
     def _plan(self, hidden_states, ctx_len) -> _Plan:
         comp = tuple((res, t.shape[0], t.shape[-2], t.shape[-1])
                      for res, t in hidden_states.items() if t is not None and t.shape[0] > 0)
@@ -274,23 +280,45 @@ class B200SD3Transformer2DModel(torch.nn.Module):
         ops.sd3_patchify(pl.in_ptr, pl.desc, pl.L, pl.max_tokens, cfg.in_channels, p, pl.tokens)
         G(pl.tokens, self.pe_w, pl.x, bias=self.pe_b, epi=ops.EPI_GATE_RESID, resid=pl.pos_rows)
         mod = pl.mod
+        # Two-stream schedule: the context stream (1998 rows: its GEMMs fill only part of a wave)
+        # runs on a side CUDA stream next to the image stream and the two meet at the joint
+        # attention of every block. Inside a captured CUDA graph these become parallel branches.
+        main = torch.cuda.current_stream()
+        side = self._side_stream()
+        ev_main, ev_side = torch.cuda.Event(), torch.cuda.Event()
+        ev_main.record(main)
+        side.wait_event(ev_main)
         for blk in self.blocks:
             m, cm = blk["mod"], blk["cmod"]
             dual, last = blk["dual"], blk["last"]
+            with torch.cuda.stream(side):
+                if last:  # AdaLayerNormContinuous: (scale, shift)
+                    ops.layernorm_mod(pl.c, pl.cn, eps=1e-6, mod=mod, row_group=pl.row_group_ctx,
+                                      shift_col=cm + D, scale_col=cm)
+                else:
+                    ops.layernorm_mod(pl.c, pl.cn, eps=1e-6, mod=mod, row_group=pl.row_group_ctx,
+                                      shift_col=cm, scale_col=cm + D)
+                G(pl.cn, blk["aqkv_w"], pl.qkv_c, bias=blk["aqkv_b"], epi=ops.EPI_QK_RMSNORM,
+                  rms_wq=blk["norm_added_q"], rms_wk=blk["norm_added_k"], rms_q_cols=D, rms_k_cols=D)
+                ev_side.record(side)
             ops.layernorm_mod(pl.x, pl.xn, eps=1e-6, mod=mod, row_group=pl.row_group,
                               shift_col=m, scale_col=m + D,
                               y2=pl.xn2 if dual else None, shift2_col=m + 6 * D, scale2_col=m + 7 * D)
-            if last:  # AdaLayerNormContinuous: (scale, shift)
-                ops.layernorm_mod(pl.c, pl.cn, eps=1e-6, mod=mod, row_group=pl.row_group_ctx,
-                                  shift_col=cm + D, scale_col=cm)
-            else:
-                ops.layernorm_mod(pl.c, pl.cn, eps=1e-6, mod=mod, row_group=pl.row_group_ctx,
-                                  shift_col=cm, scale_col=cm + D)
             G(pl.xn, blk["qkv_w"], pl.qkv, bias=blk["qkv_b"], epi=ops.EPI_QK_RMSNORM,
               rms_wq=blk["norm_q"], rms_wk=blk["norm_k"], rms_q_cols=D, rms_k_cols=D)
-            G(pl.cn, blk["aqkv_w"], pl.qkv_c, bias=blk["aqkv_b"], epi=ops.EPI_QK_RMSNORM,
-              rms_wq=blk["norm_added_q"], rms_wk=blk["norm_added_k"], rms_q_cols=D, rms_k_cols=D)
+            main.wait_event(ev_side)
             ops.attn_varlen(pl.src_img, pl.src_ctx, *pl.joint_plan, H, scale)
+            ev_main.record(main)
+            if not last:
+                with torch.cuda.stream(side):
+                    side.wait_event(ev_main)
+                    G(pl.att_c, blk["aout_w"], pl.c, bias=blk["aout_b"], epi=ops.EPI_GATE_RESID,
+                      resid=pl.c, gate=mod[:, cm + 2 * D:cm + 3 * D], row_group=pl.row_group_ctx)
+                    ops.layernorm_mod(pl.c, pl.cn, eps=1e-6, mod=mod, row_group=pl.row_group_ctx,
+                                      shift_col=cm + 3 * D, scale_col=cm + 4 * D)
+                    G(pl.cn, blk["ffc1_w"], pl.ff_c, bias=blk["ffc1_b"], epi=ops.EPI_GELU_TANH)
+                    G(pl.ff_c, blk["ffc2_w"], pl.c, bias=blk["ffc2_b"], epi=ops.EPI_GATE_RESID,
+                      resid=pl.c, gate=mod[:, cm + 5 * D:cm + 6 * D], row_group=pl.row_group_ctx)
             G(pl.att, blk["out_w"], pl.x, bias=blk["out_b"], epi=ops.EPI_GATE_RESID, resid=pl.x,
               gate=mod[:, m + 2 * D:m + 3 * D], row_group=pl.row_group)
             if dual:
@@ -304,14 +332,8 @@ class B200SD3Transformer2DModel(torch.nn.Module):
             G(pl.xn, blk["ff1_w"], pl.ff, bias=blk["ff1_b"], epi=ops.EPI_GELU_TANH)
             G(pl.ff, blk["ff2_w"], pl.x, bias=blk["ff2_b"], epi=ops.EPI_GATE_RESID, resid=pl.x,
               gate=mod[:, m + 5 * D:m + 6 * D], row_group=pl.row_group)
-            if not last:
-                G(pl.att_c, blk["aout_w"], pl.c, bias=blk["aout_b"], epi=ops.EPI_GATE_RESID,
-                  resid=pl.c, gate=mod[:, cm + 2 * D:cm + 3 * D], row_group=pl.row_group_ctx)
-                ops.layernorm_mod(pl.c, pl.cn, eps=1e-6, mod=mod, row_group=pl.row_group_ctx,
-                                  shift_col=cm + 3 * D, scale_col=cm + 4 * D)
-                G(pl.cn, blk["ffc1_w"], pl.ff_c, bias=blk["ffc1_b"], epi=ops.EPI_GELU_TANH)
-                G(pl.ff_c, blk["ffc2_w"], pl.c, bias=blk["ffc2_b"], epi=ops.EPI_GATE_RESID,
-                  resid=pl.c, gate=mod[:, cm + 5 * D:cm + 6 * D], row_group=pl.row_group_ctx)
+        ev_side.record(side)
+        main.wait_event(ev_side)  # rejoin (the last block has no context output, but keep the graph closed)
         om = self.out_mod
         ops.layernorm_mod(pl.x, pl.xn, eps=1e-6, mod=mod, row_group=pl.row_group,
                           shift_col=om + D, scale_col=om)
