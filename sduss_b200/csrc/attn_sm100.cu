@@ -331,15 +331,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
         const float m_sc = m_run * sc;
         if (pingpong) named_bar_sync(1 + t, 256);  // my turn on the XU pipe
         ATT_T(c3);
+        // exp in chunks of 16 columns, in place, software-pipelined by one chunk: the MUFU.EX2 of
+        // chunk c are issued (pinned order) before chunk c-1 is summed and packed to bf16, so the
+        // FADD / F2FP work sits in the shadow of the 8-cycle MUFU issue interval.
         float sum4[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t pk[ATT_BN / 2];
 #pragma unroll
-        for (int i = 0; i < ATT_BN; i += 2) {
-          const float p0 = fast_exp2(fmaf(s[i], sc, -m_sc));
-          const float x1 = fmaf(s[i + 1], sc, -m_sc);
-          const float p1 = (ATT_POLY_MASK && ((i >> 1) & 1)) ? poly_exp2(x1) : fast_exp2(x1);
-          sum4[(i >> 1) & 3] += p0 + p1;
-          pk[i >> 1] = ATT_ALU_PACK ? pack_bf16x2_alu(p0, p1) : pack_bf16x2(p0, p1);
+        for (int c = 0; c <= ATT_BN / 16; ++c) {
+          if (c < ATT_BN / 16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s[c * 16 + i] = fast_exp2_pinned(fmaf(s[c * 16 + i], sc, -m_sc));
+          }
+          if (c > 0) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              const int k = (c - 1) * 16 + i;
+              sum4[(i >> 1) & 3] += s[k] + s[k + 1];
+              pk[k >> 1] = pack_bf16x2(s[k], s[k + 1]);
+            }
+          }
         }
         const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
         l_run = l_run * alpha + sum;

@@ -25,7 +25,7 @@ import ctypes as C_
 cudart = C_.CDLL("/usr/local/cuda/lib64/libcudart.so.12")
 cudart.cudaMemcpy(C_.c_void_p(host.data_ptr()), C_.c_void_p(ptr), C_.c_size_t(n * H * 16 * 8), 2)
 d = host.numpy().reshape(-1, 2, 8)
-names = ["wait_s", "ld_s+free", "max", "exp+pack+st", "wait_o+token", "wait_st+arrive"]
+names = ["wait_s", "ld_s+free", "max(+token)", "exp", "wait_o(+resc)", "st_p+arrive"]
 for t in (0, 1):
     x = d[:, t, :]
     x = x[x[:, 7] > 0]
