@@ -95,10 +95,12 @@ typedef struct B200AttnSource {
 
 /* seq_table: int32 [n_seq][8] = {qa_row, qa_len, qb_row, qb_len, ka_row, ka_len, kb_row, kb_len}
  *            (row offsets into the A / B source buffers; a length of 0 disables the segment).
- * work_items: int32 [n_items][4] = {seq, q_segment (0 = A, 1 = B), row offset of the 256-row
- *            query block inside that segment, 0}; one CTA per (item, head).
+ * work_items: int32 [n_items][4] = {seq, q_segment (0 = A, 1 = B), row offset of the query
+ *            block inside that segment, 0}; one CTA per (item, head). A query block covers
+ *            b200_attn_rows_per_item() consecutive rows (a build constant: 128 or 256).
  * Every row of the K / V source buffers must hold finite values. src_b may be NULL.
  * NULL q / k / v pointers inside a source mean that side contributes no such segment. */
+int b200_attn_rows_per_item(void);
 int b200_attn_varlen_bf16(const B200AttnSource* src_a, const B200AttnSource* src_b,
                           const int32_t* seq_table, const int32_t* work_items, int n_items,
                           int n_heads, float softmax_scale, void* stream);

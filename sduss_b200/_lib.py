@@ -6,7 +6,9 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsduss_b200.so")
+# SDUSS_B200_LIB: kernel-development hook (tools/build_variant.py) to A/B a differently compiled
+# build of the same library; it is never a fallback, the named file must exist.
+LIB_PATH = os.environ.get("SDUSS_B200_LIB") or os.path.join(_HERE, "libsduss_b200.so")
 
 OK = 0
 ERR_INVALID = 10001
@@ -63,6 +65,7 @@ lib = _load()
 SIGNATURES = {
     "b200_version": [],
     "b200_sm_count": [],
+    "b200_attn_rows_per_item": [],
     "b200_gemm_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                        ctypes.POINTER(EpilogueDesc), c_void_p],
     "b200_attn_varlen_bf16": [ctypes.POINTER(AttnSource), ctypes.POINTER(AttnSource), c_void_p,

@@ -124,7 +124,7 @@ def attn_source(q=None, q_col=0, k=None, k_col=0, v=None, v_col=0, out=None, o_c
     return s
 
 
-ATTN_Q_TILE = 256  # query rows per CTA of attn_fwd_kernel (two 128-row tiles)
+ATTN_Q_TILE = lib.b200_attn_rows_per_item()  # query rows per CTA of attn_fwd_kernel
 
 
 def build_attn_plan(seqs, device):

@@ -48,8 +48,7 @@ class _StepState:
         self.R, self.total = R, x_off
         self.max_elems = max(d[1] for d in desc)
         self.desc = torch.tensor(desc, dtype=torch.int64).to(device)
-        self.sig_host = torch.empty((R, 2), dtype=torch.float32).pin_memory()
-        self.sig = torch.empty((R, 2), dtype=torch.float32, device=device)
+        self.device = device
         self.spans = [(d[0], d[1]) for d in desc]
 
 
@@ -82,14 +81,17 @@ class B200DenoisingPipelineBase:
         st = self._state(plan, cfg)
         flat = [r for _, rs in reqs_sorted for r in rs]
         x = torch.cat([r.sampling_params.latents.reshape(-1) for r in flat]).to(torch.bfloat16)
-        sig = st.sig_host.numpy()
+        # (sigma, sigma_next) per request. A fresh host tensor per call: the step is asynchronous
+        # (CUDA-graph replay), so a reused pinned staging buffer would be overwritten by the next
+        # call before this call's copy has run.
+        sig = np.empty((st.R, 2), dtype=np.float32)
         for i, r in enumerate(flat):
             ss = r.scheduler_states
             sig[i, 0] = float(ss.sigmas[ss._step_index])
             sig[i, 1] = float(ss.sigmas[ss._step_index + 1])
-        st.sig.copy_(st.sig_host, non_blocking=True)
+        sig_dev = torch.from_numpy(sig).to(st.device)
         out = torch.empty_like(x)
-        ops.cfg_scheduler_step(plan.flat_out, x, out, st.desc, st.sig, st.R, st.max_elems,
+        ops.cfg_scheduler_step(plan.flat_out, x, out, st.desc, sig_dev, st.R, st.max_elems,
                                guidance, cfg, self.step_mode)
         for (off, n), r in zip(st.spans, flat):
             ss = r.scheduler_states

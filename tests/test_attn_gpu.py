@@ -85,3 +85,40 @@ def test_cross(cuda):
         ref = _ref(q[ra:ra + s].view(s, H, 64), kk[:, 0], kk[:, 1], 0.125).reshape(s, C)
         _check(out[ra:ra + s], ref)
         ra += s
+
+
+def _joint(cuda, qkv_a, qkv_b, img_lens, ctx_len, rows_a=None):
+    """Runs the packed joint attention for sequences laid out back to back; returns (out_a, out_b)."""
+    from sduss_b200 import ops
+    C = H * 64
+    out_a = torch.zeros(qkv_a.shape[0], C, device=cuda, dtype=torch.bfloat16)
+    out_b = torch.zeros(qkv_b.shape[0], C, device=cuda, dtype=torch.bfloat16)
+    seqs, ra = [], 0
+    for i, s in enumerate(img_lens):
+        seqs.append((ra, s, i * ctx_len, ctx_len, ra, s, i * ctx_len, ctx_len))
+        ra += s
+    table, work, n = ops.build_attn_plan(seqs, cuda)
+    sa = ops.attn_source(q=qkv_a, q_col=0, k=qkv_a, k_col=C, v=qkv_a, v_col=2 * C, out=out_a)
+    sb = ops.attn_source(q=qkv_b, q_col=0, k=qkv_b, k_col=C, v=qkv_b, v_col=2 * C, out=out_b)
+    ops.attn_varlen(sa, sb, table, work, n, H, 0.125)
+    torch.cuda.synchronize()
+    return out_a, out_b
+
+
+def test_deterministic_and_batch_invariant(cuda):
+    """Same inputs -> same bits on every launch, and a sequence's output does not depend on the
+    sequences packed around it (the property Mixfusion's mixed batches rely on)."""
+    img_lens, ctx = (1024, 200, 2304, 256), 333
+    C = H * 64
+    qkv_a = _rand((sum(img_lens), 3 * C), cuda, 11)
+    qkv_b = _rand((len(img_lens) * ctx, 3 * C), cuda, 12)
+    oa, ob = _joint(cuda, qkv_a, qkv_b, img_lens, ctx)
+    for _ in range(5):
+        oa2, ob2 = _joint(cuda, qkv_a, qkv_b, img_lens, ctx)
+        assert torch.equal(oa, oa2) and torch.equal(ob, ob2)
+    ra = 0
+    for i, s in enumerate(img_lens):
+        a1, b1 = _joint(cuda, qkv_a[ra:ra + s].contiguous(), qkv_b[i * ctx:(i + 1) * ctx].contiguous(), (s,), ctx)
+        assert torch.equal(a1, oa[ra:ra + s]), i
+        assert torch.equal(b1, ob[i * ctx:(i + 1) * ctx]), i
+        ra += s

@@ -58,23 +58,28 @@ def test_sd3_three_step_rollout(cuda, cfg_on):
 
 def test_changing_batch_composition_reuses_plans(cuda):
     """Requests join and leave between steps (what sduss' scheduler does): every composition gets
-    its own plan / CUDA graph, and a request's trajectory does not depend on its batch mates."""
+    its own plan / CUDA graph, and a request's trajectory does not depend on its batch mates.
+    Repeated with fresh requests and a churned allocator: the steps are asynchronous graph
+    replays, so any host staging that is reused across calls shows up here as a mismatch."""
     from sduss_b200.synthetic import make_sd3_requests
     cfg, sd, model, sched, pipe = _sd3()
-    a = make_sd3_requests(cfg, {"256": 1, "512": 1}, 28, sched, cuda, ctx_len=cfg.context_len, seed=5)
-    b = make_sd3_requests(cfg, {"256": 1, "512": 1}, 28, sched, cuda, ctx_len=cfg.context_len, seed=5)
-    extra = make_sd3_requests(cfg, {"768": 1}, 28, sched, cuda, ctx_len=cfg.context_len, seed=6)
-    # a: alone for three steps; b: same requests, but a 768 request joins for step 2 only
-    for _ in range(3):
-        pipe.denoising_step(a, True, 7.0, True, 256)
-    pipe.denoising_step(b, True, 7.0, True, 256)
-    pipe.denoising_step({**b, **extra}, True, 7.0, True, 256)
-    pipe.denoising_step(b, True, 7.0, True, 256)
-    torch.cuda.synchronize()
-    assert len(model._plans) == 2
-    for res in a:
-        assert torch.equal(a[res][0].sampling_params.latents, b[res][0].sampling_params.latents)
-    assert extra["768"][0].scheduler_states._step_index == 1
+    for it in range(6):
+        junk = [torch.full((1 << 20,), float("nan"), device=cuda, dtype=torch.bfloat16) for _ in range(4)]
+        del junk
+        a = make_sd3_requests(cfg, {"256": 1, "512": 1}, 28, sched, cuda, ctx_len=cfg.context_len, seed=5 + it)
+        b = make_sd3_requests(cfg, {"256": 1, "512": 1}, 28, sched, cuda, ctx_len=cfg.context_len, seed=5 + it)
+        extra = make_sd3_requests(cfg, {"768": 1}, 28, sched, cuda, ctx_len=cfg.context_len, seed=60 + it)
+        # a: alone for three steps; b: same requests, but a 768 request joins for step 2 only
+        for _ in range(3):
+            pipe.denoising_step(a, True, 7.0, True, 256)
+        pipe.denoising_step(b, True, 7.0, True, 256)
+        pipe.denoising_step({**b, **extra}, True, 7.0, True, 256)
+        pipe.denoising_step(b, True, 7.0, True, 256)
+        torch.cuda.synchronize()
+        assert len(model._plans) == 2
+        for res in a:
+            assert torch.equal(a[res][0].sampling_params.latents, b[res][0].sampling_params.latents), (it, res)
+            assert a[res][0].scheduler_states._step_index == 3
 
 
 def test_sdxl_three_step_rollout_cfg_off(cuda):

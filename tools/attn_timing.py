@@ -33,5 +33,5 @@ for t in (0, 1):
     print(f"tile {'AB'[t]}: CTAs {len(x)}, tiles {tiles}, cycles/tile total {x[:, 6].sum() / tiles:.0f}")
     for i, nme in enumerate(names):
         print(f"   {nme:16s} {x[:, i].sum() / tiles:8.0f} clk/tile")
-    big = x[x[:, 7] == 35]
-    print("   35-tile CTAs: total/tile", big[:, 6].sum() / big[:, 7].sum(), " wait_s/tile", big[:, 0].sum() / big[:, 7].sum())
+
+
