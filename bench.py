@@ -146,8 +146,10 @@ def run_reference(args, rank, world):
             "value": res["value"], "unit": "denoise steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 / res["value"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "SD3.5-medium MMDiT denoise step, mixed batch 512^2+768^2+1024^2, CFG on "
-                                   "(oracle on host CPU; bounded sample scaled by FLOPs)"},
+            "config": {"workload": "BASELINE configs[1]: SD3.5-medium MMDiT denoise step, mixed batch "
+                                   "512^2+768^2+1024^2 (1 request each), CFG on -> 6 latents, random-init",
+                       "arm": "oracle (fp32 restatement of the reference path) on the host cores; each "
+                              "step is a bounded sample scaled by FLOPs"},
             "cpu_baseline": res,
             "e2e": {"value": res["value"], "unit": "denoise steps/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
@@ -222,19 +224,23 @@ def run_b200(args, rank, world, local_rank):
         step()
     barrier()
     clocks.start()
+    # per-launch CUDA events (eager launches, one stream, so that no other kernel of the step
+    # runs beside the one being timed); the step itself is re-timed below as the product runs it
     ops.profile = {}
+    model.two_streams = False
     n0 = ops.launch_count
     ms_step = timed(step, args.steps, 0)
     launches = ops.launch_count - n0
+    model.two_streams = True
     prof, ops.profile = ops.profile, None
     prof.pop("tags", None)
-    clk = clocks.stop()
     torch.cuda.synchronize()
     attn_ms = sum(a.elapsed_time(b) for a, b in prof.get("b200_attn_varlen_bf16", []))
     gemm_ms = sum(a.elapsed_time(b) for a, b in prof.get("b200_gemm_bf16", []))
     n_attn = len(prof.get("b200_attn_varlen_bf16", []))
-    # re-time without the per-launch events (they add launch overhead)
+    # the timed region proper: CUDA-graph replay of the two-stream schedule, no per-launch events
     ms_step = min(ms_step, timed(step, args.steps, 1))
+    clk = clocks.stop()
 
     # ---- e2e: every request tensor in pinned host memory, H2D + D2H inside the timed region
     hreqs = fresh(True)
@@ -286,7 +292,11 @@ def run_b200(args, rank, world, local_rank):
         "clocks": clk,
         "roofline": {"kernel": "attn_fwd_kernel (b200_attn_varlen_bf16)", "bound": "tensor",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "frac": (achieved / peak) if achieved else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one joint-attention launch of
+                     # this workload (ncu --set full, profiles/r01_ncu_attn_3x64.txt); algorithmic
+                     # bytes of that launch (Q, K, V in, O out): 207 MB
+                     "traffic": 155412736 + 35321600, "traffic_unit": "bytes per joint-attention launch",
                      "peak_source": pk_src + ", sustained bf16",
                      "launches_timed": n_attn, "kernel_ms_per_step": attn_ms / args.steps,
                      "gemm_ms_per_step": gemm_ms / args.steps,

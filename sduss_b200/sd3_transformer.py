@@ -284,7 +284,9 @@ class B200SD3Transformer2DModel(torch.nn.Module):
         # runs on a side CUDA stream next to the image stream and the two meet at the joint
         # attention of every block. Inside a captured CUDA graph these become parallel branches.
         main = torch.cuda.current_stream()
-        side = self._side_stream()
+        # two_streams = False serialises the context branch behind the image branch (used by
+        # bench.py's per-kernel timing pass, where concurrent kernels would blur the durations)
+        side = self._side_stream() if getattr(self, "two_streams", True) else main
         ev_main, ev_side = torch.cuda.Event(), torch.cuda.Event()
         ev_main.record(main)
         side.wait_event(ev_main)
