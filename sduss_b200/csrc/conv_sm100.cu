@@ -155,6 +155,11 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
     const bool has_resid = (EPI == EPI_GATE_RESID) && a.res_maps != nullptr;
     constexpr int NCH = BN / 64;
     uint32_t ruse0 = 0, ruse1 = 0;
+    // Staging buffers alternate over ALL chunks this CTA stores, not per tile: a tile with an odd
+    // number of chunks (N tail, N < BN) would otherwise be followed by a chunk that reuses the
+    // buffer whose TMA store is still in flight (the store is only waited for after the next
+    // chunk has been staged). Seen as corrupted tail columns on short-K GEMMs (conv_in: K = 64).
+    uint32_t chunk_ctr = 0;
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -165,8 +170,9 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           if (c < NCH && n0 + c * 64 < a.Cout) {
-            mbar_expect_tx(&rfull[c], EPI_STAGE_BYTES);
-            tma_load_3d(stageR + c * EPI_STAGE_BYTES, a.res_maps + tl.x, &rfull[c], n0 + c * 64, tl.z, tl.y);
+            const int rb = (chunk_ctr + c) & 1;
+            mbar_expect_tx(&rfull[rb], EPI_STAGE_BYTES);
+            tma_load_3d(stageR + rb * EPI_STAGE_BYTES, a.res_maps + tl.x, &rfull[rb], n0 + c * 64, tl.z, tl.y);
           }
         }
       }
@@ -180,7 +186,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
       for (int c = 0; c < NCH; ++c) {
         const int nc = n0 + c * 64;
         if (nc >= a.Cout) break;
-        const int b = c & 1;
+        const int b = (chunk_ctr + c) & 1;
         float v[64];
         tmem_ld32(t_row + c * 64, reinterpret_cast<uint32_t*>(v));
         tmem_ld32(t_row + c * 64 + 32, reinterpret_cast<uint32_t*>(v) + 32);
@@ -202,6 +208,10 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
             tma_load_3d(stageR + b * EPI_STAGE_BYTES, a.res_maps + tl.x, &rfull[b], nc + 128, tl.z, tl.y);
           }
         }
+      }
+      {
+        const int left = (a.Cout - n0 + 63) / 64;
+        chunk_ctr += uint32_t(left < NCH ? left : NCH);
       }
       tc_fence_before();
       __syncwarp();

@@ -169,6 +169,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool has_resid = (EPI == EPI_GATE_RESID) && e.resid != nullptr;
     constexpr int NCH = BN / 64;
     uint32_t ruse0 = 0, ruse1 = 0;
+    // Staging buffers alternate over ALL chunks this CTA stores, not per tile: a tile with an odd
+    // number of chunks (N tail, N < BN) would otherwise be followed by a chunk that reuses the
+    // buffer whose TMA store is still in flight (the store is only waited for after the next
+    // chunk has been staged). Seen as corrupted tail columns on short-K GEMMs (conv_in: K = 64).
+    uint32_t chunk_ctr = 0;
     int it = 0;
     if (leader) {
       tma_prefetch_desc(&tmC);
@@ -182,8 +187,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           if (c < NCH && n0 + c * 64 < s.N) {
-            mbar_expect_tx(&rfull[c], EPI_STAGE_BYTES);
-            tma_load_2d(stageR + c * EPI_STAGE_BYTES, &tmR, &rfull[c], n0 + c * 64, m0);
+            const int rb = (chunk_ctr + c) & 1;
+            mbar_expect_tx(&rfull[rb], EPI_STAGE_BYTES);
+            tma_load_2d(stageR + rb * EPI_STAGE_BYTES, &tmR, &rfull[rb], n0 + c * 64, m0);
           }
         }
       }
@@ -195,7 +201,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int c = 0; c < NCH; ++c) {
         const int nc = n0 + c * 64;
         if (nc >= s.N) break;
-        const int b = c & 1;
+        const int b = (chunk_ctr + c) & 1;
         float v[64];
         tmem_ld32(t_row + c * 64, reinterpret_cast<uint32_t*>(v));
         tmem_ld32(t_row + c * 64 + 32, reinterpret_cast<uint32_t*>(v) + 32);
@@ -221,6 +227,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_2d(stageR + b * EPI_STAGE_BYTES, &tmR, &rfull[b], nc + 128, m0);
           }
         }
+      }
+      {
+        const int left = (s.N - n0 + 63) / 64;
+        chunk_ctr += uint32_t(left < NCH ? left : NCH);
       }
       tc_fence_before();
       __syncwarp();

@@ -30,6 +30,26 @@ def test_gemm_bias(cuda, M, N, K):
     _close(out32, a.float() @ w.float().t(), tol=2e-3)
 
 
+@pytest.mark.parametrize("M,N,K", [(40960, 320, 64), (40960, 64, 64), (30000, 192, 128), (40960, 448, 64)])
+def test_gemm_many_short_tiles_with_n_tail(cuda, M, N, K):
+    """Dozens of output tiles per CTA, one or two K blocks each, and an odd number of 64-column
+    chunks per tile (N tail / N < BN). Regression: the TMA-store staging buffers alternated per
+    tile, so such a tile was followed by a chunk staged into the buffer whose store was still in
+    flight (SDXL conv_in, M = 40960, N = 320, K = 64, came out corrupted and non-deterministic)."""
+    from sduss_b200 import ops
+    a, w, b = _rand((M, K), cuda, seed=1), _rand((N, K), cuda, 0.2, seed=2), _rand((N,), cuda, seed=3)
+    ref = a.float() @ w.float().t() + b.float()
+    outs = [ops.gemm(a, w, bias=b) for _ in range(4)]
+    for o in outs:
+        _close(o, ref)
+        assert torch.equal(o, outs[0])
+    resid = _rand((M, N), cuda, seed=6)
+    outs = [ops.gemm(a, w, bias=b, epi=ops.EPI_GATE_RESID, resid=resid) for _ in range(3)]
+    for o in outs:
+        _close(o, ref + resid.float())
+        assert torch.equal(o, outs[0])
+
+
 def test_gemm_strided_a(cuda):
     from sduss_b200 import ops
     big = _rand((512, 1024), cuda, seed=4)

@@ -35,6 +35,10 @@ def _rand(shape, seed, scale=1.0):
     ([(32, 32), (64, 64), (96, 96)], 64, 64, 2),
     ([(16, 16), (48, 48)], 320, 320, 2),
     ([(32, 32)], 320, 8, 1),
+    # many output tiles per CTA with a short K loop and an odd number of 64-column chunks per
+    # tile (Cout = 320 = 256 + 64; Cout = 8): regression for the epilogue staging-buffer reuse
+    ([(128, 128), (128, 128), (64, 64)], 64, 320, 1),
+    ([(128, 128), (128, 128)], 64, 8, 1),
 ])
 def test_conv3x3(cuda, sizes, cin, cout, stride):
     from sduss_b200 import ops
