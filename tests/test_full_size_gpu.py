@@ -75,3 +75,64 @@ def test_sdxl_base_config1_invariance(cuda):
     _check(pipe, reqs, lambda r: pipe.denoising_step(r, True, 0.0, 5.0, None, {}, None, None, None, True, 256))
     del model, pipe
     torch.cuda.empty_cache()
+
+
+def _compare(out, ref):
+    """bf16 kernels vs fp32 oracle: cosine >= 0.999 per resolution and max-abs error
+    <= 6 % of the output range."""
+    for k in ref:
+        o, r = out[k].float().cpu(), ref[k].float()
+        cos = torch.nn.functional.cosine_similarity(o.flatten(), r.flatten(), dim=0).item()
+        err = (o - r).abs().max().item()
+        assert cos >= 0.999, (k, cos)
+        assert err <= 0.06 * (r.max() - r.min()).item(), (k, err)
+
+
+def test_sdxl_base_full_model_matches_oracle(cuda):
+    """The whole SDXL-base UNet (all 70 transformer blocks, 2.6 B parameters) on a 512^2 + 1024^2
+    batch against the fp32 CPU oracle with the same bf16-rounded weights and inputs."""
+    from dataclasses import asdict
+    from oracle import sdxl_unet as ox
+    from sduss_b200.unet import B200UNet, UNetConfig
+    oc = ox.sdxl_base_config()
+    d = asdict(oc)
+    d.pop("context_len")
+    sd = {k: v.to(torch.bfloat16).float() for k, v in ox.init_unet_weights(oc, 0).items()}
+    model = B200UNet(sd, UNetConfig(**d), device="cuda")
+    g = torch.Generator().manual_seed(1)
+    q = lambda x: x.to(torch.bfloat16).float()
+    s = {"512": q(torch.randn(1, 4, 64, 64, generator=g)), "1024": q(torch.randn(1, 4, 128, 128, generator=g))}
+    ehs = q(torch.randn(2, oc.context_len, oc.cross_attention_dim, generator=g))
+    te = q(torch.randn(2, oc.pooled_dim, generator=g))
+    ids = torch.tensor([[1024., 1024, 0, 0, 1024, 1024]] * 2)
+    t = torch.tensor([981.0, 500.0])
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    ref = ox.unet_forward(sd, oc, s, t, ehs, te, ids)
+    dv = lambda x: x.cuda().bfloat16()
+    out = model({k: dv(v) for k, v in s.items()}, t.cuda(), encoder_hidden_states=dv(ehs),
+                added_cond_kwargs={"text_embeds": dv(te), "time_ids": dv(ids)})[0]
+    _compare(out, ref)
+    del model
+    torch.cuda.empty_cache()
+
+
+def test_sd35_medium_full_model_matches_oracle(cuda):
+    """The whole SD3.5-medium MMDiT (24 blocks, dual attention in 0-12, 333 context tokens) on a
+    512^2 + 1024^2 batch against the fp32 CPU oracle."""
+    from oracle import sd3_mmdit as o3
+    from sduss_b200.sd3_transformer import B200SD3Transformer2DModel
+    cfg = o3.sd35_medium_config()
+    sd = {k: v.to(torch.bfloat16).float() for k, v in o3.init_sd3_weights(cfg, 0).items()}
+    model = B200SD3Transformer2DModel(sd, cfg, device="cuda")
+    g = torch.Generator().manual_seed(1)
+    q = lambda x: x.to(torch.bfloat16).float()
+    hs = {"512": q(torch.randn(1, 16, 64, 64, generator=g)), "1024": q(torch.randn(1, 16, 128, 128, generator=g))}
+    ehs = q(torch.randn(2, 333, cfg.joint_attention_dim, generator=g))
+    pooled = q(torch.randn(2, cfg.pooled_projection_dim, generator=g))
+    t = torch.tensor([981.0, 500.0])
+    ref = o3.sd3_forward(sd, cfg, hs, ehs, pooled, t)
+    out = model({k: v.cuda().bfloat16() for k, v in hs.items()}, ehs.cuda().bfloat16(),
+                pooled.cuda().bfloat16(), t.cuda())[0]
+    _compare(out, ref)
+    del model
+    torch.cuda.empty_cache()
