@@ -60,6 +60,97 @@ def run_plan(model, plan):
     launch_count += plan.graph_launches
 
 
+class PlanCache:
+    """Least-recently-used cache of per-composition plans (static workspaces, descriptor tables and
+    the captured CUDA graph). A serving run sees many batch compositions (up to 12 requests over
+    three resolutions in the reference's experiments) and a plan owns hundreds of MB to tens of GB
+    of workspace, so the cache is bounded by device memory, not by count: when the plans together
+    exceed `budget_bytes` the least recently used ones are dropped (their graph with them) and
+    re-created on demand. The reference allocates its activations from torch's caching allocator
+    every step instead; here pointers must be stable for graph replay."""
+
+    def __init__(self, device, budget_fraction=0.35):
+        import collections
+        self.plans = collections.OrderedDict()
+        total = torch.cuda.get_device_properties(device).total_memory if torch.cuda.is_available() else 1 << 40
+        self.budget_bytes = int(total * budget_fraction)
+        self.evictions = 0
+
+    def __len__(self):
+        return len(self.plans)
+
+    def values(self):
+        return self.plans.values()
+
+    def clear(self):
+        self.plans.clear()
+
+    @staticmethod
+    def plan_bytes(plan, seen=None):
+        """Bytes of device/host storage reachable from the plan; storages already in `seen` (e.g.
+        a workspace arena shared by several plans) are not counted again."""
+        seen, n = (set() if seen is None else seen), 0
+        stack = list(vars(plan).values())
+        while stack:
+            v = stack.pop()
+            if torch.is_tensor(v):
+                st = v.untyped_storage()
+                if st.data_ptr() not in seen:
+                    seen.add(st.data_ptr())
+                    n += st.nbytes()
+            elif isinstance(v, dict):
+                stack.extend(v.values())
+            elif isinstance(v, (list, tuple)):
+                stack.extend(v)
+        return n
+
+    def total_bytes(self):
+        seen = set()
+        return sum(self.plan_bytes(p, seen) for p in self.plans.values())
+
+    def get(self, key, factory):
+        plan = self.plans.get(key)
+        if plan is not None:
+            self.plans.move_to_end(key)
+            return plan
+        # make room before the new plan allocates (sizes of lazily filled plans are read now)
+        while self.plans and self.total_bytes() > self.budget_bytes:
+            self.plans.popitem(last=False)
+            self.evictions += 1
+        plan = self.plans[key] = factory()
+        return plan
+
+
+class Arena:
+    """One growing device allocation that every plan of a model carves its per-step workspaces
+    from. Only one plan runs at a time and each of these buffers is fully rewritten by every
+    forward before it is read, so plans can overlap in memory: a serving run with hundreds of
+    batch compositions then needs the workspace of the largest one, not their sum. When a
+    larger plan arrives a new block is allocated; older plans keep (a reference to) the block
+    their CUDA graph was captured on."""
+    ALIGN = 1024
+
+    def __init__(self, device):
+        self.device = device
+        self.block = None
+
+    def carve(self, specs):
+        """specs: [(name, shape, dtype)] -> {name: tensor view}, plus the block they live in."""
+        offs, total = [], 0
+        for _, shape, dtype in specs:
+            n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+            offs.append(total)
+            total += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        if self.block is None or self.block.numel() < total:
+            grow = 0 if self.block is None else int(self.block.numel() * 1.25)
+            self.block = torch.empty((max(total, grow),), dtype=torch.uint8, device=self.device)
+        out = {}
+        for (name, shape, dtype), off in zip(specs, offs):
+            n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+            out[name] = self.block[off:off + n].view(dtype).view(*shape)
+        return out, self.block
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 

@@ -61,7 +61,6 @@ class B200DenoisingPipelineBase:
     def __init__(self, model, scheduler):
         self.model = model
         self.scheduler = scheduler
-        self._states = {}
 
     # -- helpers -----------------------------------------------------------------------
     @staticmethod
@@ -69,11 +68,12 @@ class B200DenoisingPipelineBase:
         return sorted((r for r in reqs if len(reqs[r]) > 0), key=lambda s: int(s))
 
     def _state(self, plan, cfg: bool):
-        key = (id(plan), cfg)
-        st = self._states.get(key)
+        # lives on the plan, so it goes away with it when the plan cache evicts the plan
+        states = plan.__dict__.setdefault("_step_states", {})
+        st = states.get(cfg)
         if st is None:
             elems = {res: t[0].numel() for res, t in plan.stage_out.items()}
-            st = self._states[key] = _StepState(plan, plan.comp, elems, cfg, self.model.device)
+            st = states[cfg] = _StepState(plan, plan.comp, elems, cfg, self.model.device)
         return st
 
     def _finish(self, plan, reqs_sorted, cfg: bool, guidance: float):

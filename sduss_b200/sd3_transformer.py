@@ -78,8 +78,22 @@ class _Plan:
         # addresses predictions by element offset from flat_out)
         numel_in = [n * cfg.in_channels * h * w for _, n, h, w in comp]
         numel_out = [n * cfg.out_channels * h * w for _, n, h, w in comp]
-        self.flat_in = torch.empty((sum(numel_in),), **bf)
-        self.flat_out = torch.empty((sum(numel_out),), **bf)
+        # Per-step workspaces, carved from the model's shared arena (see ops.Arena): every one of
+        # them is fully rewritten by each forward before it is read.
+        T, Tc = self.T, self.Tc
+        b16, f32 = torch.bfloat16, torch.float32
+        specs = [("flat_in", (sum(numel_in),), b16), ("flat_out", (sum(numel_out),), b16),
+                 ("tokens", (T, cfg.in_channels * p * p), b16), ("x", (T, D), b16), ("xn", (T, D), b16),
+                 ("xn2", (T, D), b16), ("c", (Tc, D), b16), ("cn", (Tc, D), b16), ("qkv", (T, 3 * D), b16),
+                 ("qkv_c", (Tc, 3 * D), b16), ("att", (T, D), b16), ("att_c", (Tc, D), b16),
+                 ("ff", (T, 4 * D), b16), ("ff_c", (Tc, 4 * D), b16),
+                 ("out_tok", (T, p * p * cfg.out_channels), b16), ("mod", (L, model.mod_cols), b16),
+                 ("t32", (L,), f32), ("tsin", (L, 256), b16), ("e1", (L, D), b16), ("e2", (L, D), b16),
+                 ("e3", (L, D), b16), ("temb", (L, D), b16), ("pooled", (L, cfg.pooled_projection_dim), b16),
+                 ("ehs", (Tc, cfg.joint_attention_dim), b16)]
+        views, self.block = model.arena.carve(specs)
+        for name, t in views.items():
+            setattr(self, name, t)
         self.stage_in, self.stage_out, self.out_elem_off = {}, {}, {}
         oi = oo = 0
         for (res, n, h, w), ni, no in zip(comp, numel_in, numel_out):
@@ -112,30 +126,6 @@ class _Plan:
         self.joint_plan = ops.build_attn_plan(joint, dev)
         selfp = [(int(off[l]), S[l], 0, 0, int(off[l]), S[l], 0, 0) for l in range(L)]
         self.self_plan = ops.build_attn_plan(selfp, dev)
-        # workspaces
-        T, Tc = self.T, self.Tc
-        self.tokens = torch.empty((T, cfg.in_channels * p * p), **bf)
-        self.x = torch.empty((T, D), **bf)
-        self.xn = torch.empty((T, D), **bf)
-        self.xn2 = torch.empty((T, D), **bf)
-        self.c = torch.empty((Tc, D), **bf)
-        self.cn = torch.empty((Tc, D), **bf)
-        self.qkv = torch.empty((T, 3 * D), **bf)
-        self.qkv_c = torch.empty((Tc, 3 * D), **bf)
-        self.att = torch.empty((T, D), **bf)
-        self.att_c = torch.empty((Tc, D), **bf)
-        self.ff = torch.empty((T, 4 * D), **bf)
-        self.ff_c = torch.empty((Tc, 4 * D), **bf)
-        self.out_tok = torch.empty((T, p * p * cfg.out_channels), **bf)
-        self.mod = torch.empty((L, model.mod_cols), **bf)
-        self.t32 = torch.empty((L,), device=dev, dtype=torch.float32)
-        self.tsin = torch.empty((L, 256), **bf)
-        self.e1 = torch.empty((L, D), **bf)
-        self.e2 = torch.empty((L, D), **bf)
-        self.e3 = torch.empty((L, D), **bf)
-        self.temb = torch.empty((L, D), **bf)
-        self.pooled = torch.empty((L, cfg.pooled_projection_dim), **bf)
-        self.ehs = torch.empty((Tc, cfg.joint_attention_dim), **bf)
         # attention sources (pointers are static)
         self.src_img = ops.attn_source(q=self.qkv, q_col=0, k=self.qkv, k_col=D, v=self.qkv,
                                        v_col=2 * D, out=self.att)
@@ -215,7 +205,8 @@ class B200SD3Transformer2DModel(torch.nn.Module):
         self.mod_w = torch.cat(mod_w, 0).to(self.device, torch.bfloat16).contiguous()
         self.mod_b = torch.cat(mod_b, 0).to(self.device, torch.bfloat16).contiguous()
         self.proj_w, self.proj_b = w("proj_out.weight"), w("proj_out.bias")
-        self._plans: Dict[tuple, _Plan] = {}
+        self._plans = ops.PlanCache(self.device)
+        self.arena = ops.Arena(self.device)
         self.use_graphs = ops.graphs_enabled()
 
     @classmethod
@@ -235,10 +226,7 @@ class B200SD3Transformer2DModel(torch.nn.Module):
         comp = tuple((res, t.shape[0], t.shape[-2], t.shape[-1])
                      for res, t in hidden_states.items() if t is not None and t.shape[0] > 0)
         key = (comp, ctx_len)
-        plan = self._plans.get(key)
-        if plan is None:
-            plan = self._plans[key] = _Plan(self, comp, ctx_len)
-        return plan
+        return self._plans.get(key, lambda: _Plan(self, comp, ctx_len))
 
     @torch.no_grad()
     def forward(self, hidden_states: Dict[str, torch.Tensor], encoder_hidden_states=None,

@@ -248,7 +248,7 @@ class B200UNet(torch.nn.Module):
         self.temb_cols = tcol
         put("kv_all.weight", torch.cat(kv_w, 0))
         self.kv_cols = kcol
-        self._plans: Dict[tuple, _Plan] = {}
+        self._plans = ops.PlanCache(self.device)
         self.use_graphs = ops.graphs_enabled()
 
     @classmethod
@@ -337,10 +337,7 @@ class B200UNet(torch.nn.Module):
         comp = tuple((res, t.shape[0], t.shape[-2], t.shape[-1])
                      for res, t in sample.items() if t is not None and t.shape[0] > 0)
         key = (comp, ctx_len)
-        pl = self._plans.get(key)
-        if pl is None:
-            pl = self._plans[key] = _Plan(self, comp, ctx_len)
-        return pl
+        return self._plans.get(key, lambda: _Plan(self, comp, ctx_len))
 
     @torch.no_grad()
     def forward(self, sample: Dict[str, torch.Tensor], timestep, encoder_hidden_states,

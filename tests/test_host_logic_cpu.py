@@ -110,3 +110,53 @@ def test_two_rank_gloo_timing_aggregation(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0 and "ok" in out, out
+
+
+def test_plan_cache_is_lru_and_memory_bounded():
+    """ops.PlanCache: plans are evicted least-recently-used once their tensors exceed the budget;
+    shared storages are counted once; a hit refreshes recency."""
+    import torch
+    from types import SimpleNamespace
+    from sduss_b200 import ops
+    cache = ops.PlanCache("cpu")
+    cache.budget_bytes = 3000
+
+    def plan(nbytes):
+        base = torch.zeros(nbytes, dtype=torch.uint8)
+        return SimpleNamespace(a=base, views={"v": base[: nbytes // 2]}, lst=[base[1:]], graph=None)
+
+    assert ops.PlanCache.plan_bytes(plan(1000)) == 1000        # views share the storage
+    made = []
+    get = lambda k: cache.get(k, lambda: made.append(k) or plan(1000))
+    p1, p2, p3 = get("a"), get("b"), get("c")
+    assert len(cache) == 3 and cache.evictions == 0
+    assert get("a") is p1 and made == ["a", "b", "c"]           # hit: no rebuild, "a" is now most recent
+    get("d")                                                    # 3000 bytes cached: within budget, nothing dropped
+    assert len(cache) == 4 and cache.evictions == 0
+    get("e")                                                    # 4000 > 3000: the least recently used ("b") goes
+    assert cache.evictions == 1 and "b" not in cache.plans and "a" in cache.plans
+    get("b")
+    assert made == ["a", "b", "c", "d", "e", "b"]
+
+
+def test_arena_views_are_aligned_disjoint_and_shared_between_plans():
+    import torch
+    from types import SimpleNamespace
+    from sduss_b200 import ops
+    arena = ops.Arena("cpu")
+    specs = [("a", (3, 5), torch.bfloat16), ("b", (7,), torch.float32), ("c", (2, 2, 2), torch.bfloat16)]
+    v1, blk1 = arena.carve(specs)
+    assert v1["a"].shape == (3, 5) and v1["b"].dtype == torch.float32
+    ptrs = sorted((t.data_ptr(), t.numel() * t.element_size()) for t in v1.values())
+    for (p0, n0), (p1, _) in zip(ptrs, ptrs[1:]):
+        assert p0 + n0 <= p1 and (p1 - blk1.data_ptr()) % ops.Arena.ALIGN == 0
+    v1["a"].fill_(1.0); v1["b"].fill_(2.0)
+    assert float(v1["a"].float().sum()) == 15.0                 # writing one view does not touch another
+    v2, blk2 = arena.carve(specs[:1])                           # a smaller plan reuses the same block
+    assert blk2 is blk1 and v2["a"].data_ptr() == v1["a"].data_ptr()
+    v3, blk3 = arena.carve([("big", (100000,), torch.float32)])  # a larger one gets a new block,
+    assert blk3 is not blk1 and blk1.numel() > 0                 # the old block stays valid for old plans
+    cache = ops.PlanCache("cpu")
+    cache.get("p1", lambda: SimpleNamespace(block=blk1, x=v1["a"]))
+    cache.get("p2", lambda: SimpleNamespace(block=blk1, x=v2["a"]))
+    assert cache.total_bytes() == blk1.numel()                   # the shared block is counted once

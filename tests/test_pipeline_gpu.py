@@ -128,3 +128,29 @@ def test_unsupported_arguments_raise(cuda):
         model(x, e, p, t, skip_layers=[1])
     with pytest.raises(AssertionError):
         model(x, e, p, t, joint_attention_kwargs={"scale": 0.5})
+
+
+def test_plan_cache_eviction_keeps_results(cuda):
+    """A serving run sees more batch compositions than fit in memory: plans (and their CUDA graphs)
+    are dropped and rebuilt. The trajectory of a request must not depend on that."""
+    from sduss_b200.synthetic import make_sd3_requests
+    cfg, sd, model, sched, pipe = _sd3()
+    specs = [{"256": 1, "512": 1}, {"256": 2}, {"512": 1, "768": 1}, {"256": 1, "512": 1}, {"256": 2}]
+
+    def rollout():
+        reqs = [make_sd3_requests(cfg, s, 28, sched, cuda, ctx_len=cfg.context_len, seed=20 + i)
+                for i, s in enumerate(specs)]
+        for _ in range(2):
+            for r in reqs:
+                pipe.denoising_step(r, True, 7.0, True, 256)
+        torch.cuda.synchronize()
+        return [r[res][0].sampling_params.latents.clone() for r in reqs for res in r]
+
+    ref = rollout()
+    assert model._plans.evictions == 0 and len(model._plans) == 3
+    model._plans.clear()
+    model._plans.budget_bytes = 1          # every new composition evicts all cached plans
+    got = rollout()
+    assert model._plans.evictions > 0
+    for a, b in zip(ref, got):
+        assert torch.equal(a, b)

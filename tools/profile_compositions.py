@@ -64,7 +64,7 @@ for a, b, c in compositions(n_comp):
     sec50 = s.elapsed_time(e) / 4 / 1e3 * STEPS
     rows.append((a, b, c, sec50))
     print(f"{a},{b},{c},{sec50:.6f}", flush=True)
-    model._plans.clear(); pipe._states.clear(); del reqs
+    model._plans.clear(); del reqs
     torch.cuda.empty_cache()
 with open(out, "w") as f:
     f.write("512 num, 768 num, 1024 num, avg unet time\n")
