@@ -120,10 +120,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
+  // grid = (heads, work items): CTAs are dispatched in linear order, x fastest, and the work
+  // items are sorted longest first, so all heads of the longest sequences start first and the
+  // tail of the launch is made of the shortest ones (longest-processing-time-first).
+  const int head = blockIdx.x;
 
   // work tables are written once per plan (not by the preceding kernel): safe before pdl_wait()
-  const int4 item = reinterpret_cast<const int4*>(a.work_items)[blockIdx.x];
+  const int4 item = reinterpret_cast<const int4*>(a.work_items)[blockIdx.y];
   const int* st = a.seq_table + item.x * 8;
   const int q_seg = item.y;
   const int q_row0 = st[q_seg * 2] + item.z;
@@ -372,7 +375,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
       }
 #ifdef ATT_TIMING
       if (a.dbg != nullptr && lane == 0 && qd == 2 && t < 2) {
-        long long* d = a.dbg + (size_t(blockIdx.y) * gridDim.x + blockIdx.x) * 16 + t * 8;
+        long long* d = a.dbg + (size_t(blockIdx.x) * gridDim.y + blockIdx.y) * 16 + t * 8;
         for (int i = 0; i < 6; ++i) d[i] = tacc[i];
         d[6] = clock64() - t_begin;
         d[7] = n_tiles;
@@ -494,7 +497,8 @@ extern "C" int b200_attn_varlen_bf16(const B200AttnSource* src_a, const B200Attn
     }
   }
 #endif
-  dim3 grid(n_items, n_heads);
+  if (n_items > 65535) return B200_ERR_UNSUPPORTED;
+  dim3 grid(n_heads, n_items);
   return launch_pdl(attn_fwd_kernel, grid, dim3(ATT_THREADS), ATT_SMEM,
                     reinterpret_cast<cudaStream_t>(stream_), tm[0][0], tm[1][0], tm[0][1], tm[1][1],
                     tm[0][2], tm[1][2], a);
