@@ -160,3 +160,66 @@ def test_arena_views_are_aligned_disjoint_and_shared_between_plans():
     cache.get("p1", lambda: SimpleNamespace(block=blk1, x=v1["a"]))
     cache.get("p2", lambda: SimpleNamespace(block=blk1, x=v2["a"]))
     assert cache.total_bytes() == blk1.numel()                   # the shared block is counted once
+
+
+def test_registry_plugin_overrides_only_the_hot_path(monkeypatch):
+    """sduss_b200.plugin.make_b200_pipeline: the class sduss registers instead of its ESyMReD
+    pipeline. Fakes stand in for the reference class and for the GPU modules."""
+    import sys, types
+    from sduss_b200 import plugin
+
+    class FakeReference:                       # shape of ESyMReDStableDiffusion3Pipeline
+        SUPPORT_MIXED_PRECISION = True
+        SUPPORT_RESOLUTIONS = [512, 768, 1024]
+
+        def __init__(self, transformer=None, scheduler=None, vae=None):
+            self.transformer, self.scheduler, self.vae = transformer, scheduler, vae
+
+        @classmethod
+        def instantiate_pipeline(cls, **kwargs):
+            raise AssertionError("the reference wrapper must not run")
+
+        def prepare_inference(self, **kw):
+            return "reference prepare"
+
+        def post_inference(self, **kw):
+            return "reference post"
+
+        def denoising_step(self, *a, **k):
+            raise AssertionError("the reference step must not run")
+
+    calls = []
+    fake_model_mod = types.ModuleType("sduss_b200.sd3_transformer")
+
+    class FakeB200Model:
+        @classmethod
+        def from_diffusers(cls, module, device="cuda"):
+            calls.append(("from_diffusers", module, device))
+            return ("b200", module)
+    fake_model_mod.B200SD3Transformer2DModel = FakeB200Model
+    fake_pipe_mod = types.ModuleType("sduss_b200.pipelines")
+
+    class FakeStep:
+        def __init__(self, model, scheduler):
+            calls.append(("step_init", model, scheduler))
+
+        def denoising_step(self, *a, **k):
+            calls.append(("step", a, k))
+    fake_pipe_mod.B200StableDiffusion3Pipeline = FakeStep
+    monkeypatch.setitem(sys.modules, "sduss_b200.sd3_transformer", fake_model_mod)
+    monkeypatch.setitem(sys.modules, "sduss_b200.pipelines", fake_pipe_mod)
+
+    cls = plugin.make_b200_pipeline(FakeReference, "sd3", device="cuda:0")
+    assert issubclass(cls, FakeReference) and cls.__name__ == "B200FakeReference"
+    assert cls.SUPPORT_RESOLUTIONS == [512, 768, 1024]
+    pipe = cls.instantiate_pipeline(sub_modules={"transformer": "diffusers-transformer", "scheduler": "sched", "vae": "vae"})
+    assert calls[0] == ("from_diffusers", "diffusers-transformer", "cuda:0")
+    assert pipe.transformer == ("b200", "diffusers-transformer") and pipe.vae == "vae"
+    assert pipe.prepare_inference() == "reference prepare" and pipe.post_inference() == "reference post"
+    pipe.denoising_step({"512": []}, do_classifier_free_guidance=True)
+    pipe.denoising_step({"512": []})
+    assert [c[0] for c in calls] == ["from_diffusers", "step_init", "step", "step"]   # built once, reused
+    assert calls[1] == ("step_init", ("b200", "diffusers-transformer"), "sched")
+    import pytest
+    with pytest.raises(ValueError):
+        plugin.make_b200_pipeline(FakeReference, "sd15")
