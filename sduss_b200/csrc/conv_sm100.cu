@@ -306,9 +306,8 @@ extern "C" int b200_conv3x3_bf16(const void* in_maps_dev, const void* out_maps_d
   if (epi_mode == EPI_ROWVEC && (!ep->rowvec || !ep->row_group)) return B200_ERR_INVALID;
   const int sms = device_sm_count();
   if (sms <= 0) return B200_ERR_DRIVER;
-  const long tiles256 = long(n_mtiles) * ((Cout + 255) / 256);
-  const bool bn256 = (Cout >= 256) && (tiles256 >= sms);
-  const int BN = bn256 ? 256 : 128;
+  const int BN = choose_tile_n(n_mtiles, Cout, 9 * (Cin / CV_BK), sms, /*multicast=*/false);
+  const bool bn256 = BN == 256;
   CUtensorMap tmW;
   uint64_t d[2] = {uint64_t(9) * Cin, uint64_t(Cout)}, s[1] = {uint64_t(9) * Cin * 2};
   uint32_t b[2] = {CV_BK, uint32_t(BN)};

@@ -319,10 +319,10 @@ extern "C" int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
   if (sms <= 0) return B200_ERR_DRIVER;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
 
-  // Small-N problems (and ones whose 256-wide tiling leaves most SMs idle) use 128-wide tiles.
-  const long tiles256 = long((M + BM - 1) / BM) * ((N + 255) / 256);
-  const bool bn256 = (N >= 256) && (tiles256 >= sms);
-  const int BN = bn256 ? 256 : 128;
+  // 128 x 256 or 128 x 128 tiles: whichever the operand-traffic / occupancy model predicts faster
+  static const bool mc_allowed0 = []() { const char* v = getenv("SDUSS_B200_NO_MULTICAST"); return !(v && v[0] == '1'); }();
+  const int BN = choose_tile_n((M + BM - 1) / BM, N, (K + BK - 1) / BK, sms, mc_allowed0 && M > BM);
+  const bool bn256 = BN == 256;
 
   // pair CTAs (W-tile multicast) whenever there are at least two M tiles and enough pairs of
   // tiles to occupy the 74 SM pairs

@@ -26,6 +26,28 @@ inline int launch_status() {
 
 int device_sm_count();
 
+// Tile-width choice for the 128-row tcgen05 GEMM / implicit-GEMM kernels. A tile of 128 x BN does
+// 2 BN tensor-pipe cycles per 64-deep K block and pulls 16 KB of A plus BN x 128 B of W through
+// L2 -> SM (W halved when CTA pairs multicast it). Small-M, deep-K problems (SDXL's level-2 token
+// GEMMs: M = 2560) are bound by that operand traffic, not by SM occupancy: 100 tiles of 128 x 256
+// on 148 SMs beat 200 tiles of 128 x 128 (measured 58 us -> see profiles/). Returns 256 or 128.
+// L2 -> SM throughput used by the model: ~3600 B/clk chip-wide (fitted on M=2560 N=1280 K=5120).
+inline int choose_tile_n(long m_tiles, int N, int num_kb, int sms, bool multicast) {
+  if (N < 256) return 128;
+  double best = 0;
+  int pick = 128;
+  for (int bn : {256, 128}) {
+    const long tiles = m_tiles * ((N + bn - 1) / bn);
+    const long rounds = (tiles + sms - 1) / sms;
+    const double t_math = double(rounds) * num_kb * (2.0 * bn);
+    const double w_bytes = bn * 128.0 * ((multicast && m_tiles > 1) ? 0.5 : 1.0);
+    const double t_l2 = double(tiles) * num_kb * (16384.0 + w_bytes) / 3600.0;
+    const double t = (t_math > t_l2 ? t_math : t_l2) + 2048.0 * rounds;  // + per-tile epilogue / fill
+    if (best == 0 || t < best) { best = t; pick = bn; }
+  }
+  return pick;
+}
+
 // SDUSS_B200_NO_PDL=1 disables programmatic dependent launch (plain stream order).
 bool pdl_enabled();
 
