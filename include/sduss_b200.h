@@ -95,15 +95,25 @@ typedef struct B200AttnSource {
 
 /* seq_table: int32 [n_seq][8] = {qa_row, qa_len, qb_row, qb_len, ka_row, ka_len, kb_row, kb_len}
  *            (row offsets into the A / B source buffers; a length of 0 disables the segment).
- * work_items: int32 [n_items][4] = {seq, q_segment (0 = A, 1 = B), row offset of the query
- *            block inside that segment, 0}; one CTA per (item, head). A query block covers
- *            b200_attn_rows_per_item() consecutive rows (a build constant: 128 or 256).
+ * The kernel is persistent (one CTA per SM, or max_ctas of them if max_ctas > 0). Its work list
+ * comes from b200_attn_build_schedule, a pure host function (no GPU needed) run once per batch
+ * composition:
+ *   work_units:  int32 [n_units][4] = {seq, q_segment (0 = A, 1 = B), row offset of the query
+ *                block inside that segment, head}, longest first; a query block covers
+ *                b200_attn_rows_per_item() consecutive rows (a build constant).
+ * Call it with work_units == NULL to get n_units, allocate, call again (host memory; seq_table
+ * there is the HOST copy), then copy the table to the device.
+ * sched_state: int32 [2] in device memory, zeroed once by the caller; the CTAs draw units from
+ * it and the last one re-arms it, so the same buffer serves every later launch (CUDA-graph
+ * replays included). Launches that can run concurrently need separate buffers.
  * Every row of the K / V source buffers must hold finite values. src_b may be NULL.
  * NULL q / k / v pointers inside a source mean that side contributes no such segment. */
 int b200_attn_rows_per_item(void);
+int b200_attn_build_schedule(const int32_t* seq_table, int n_seq, int n_heads,
+                             int32_t* work_units, int* n_units_out);
 int b200_attn_varlen_bf16(const B200AttnSource* src_a, const B200AttnSource* src_b,
-                          const int32_t* seq_table, const int32_t* work_items, int n_items,
-                          int n_heads, float softmax_scale, void* stream);
+                          const int32_t* seq_table, const int32_t* work_units, int n_units,
+                          int32_t* sched_state, int max_ctas, float softmax_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * HBM-bound kernels (coalesced 16-byte vectors, warp-shuffle reductions).

@@ -68,8 +68,9 @@ SIGNATURES = {
     "b200_attn_rows_per_item": [],
     "b200_gemm_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                        ctypes.POINTER(EpilogueDesc), c_void_p],
+    "b200_attn_build_schedule": [c_void_p, c_int, c_int, c_void_p, ctypes.POINTER(c_int)],
     "b200_attn_varlen_bf16": [ctypes.POINTER(AttnSource), ctypes.POINTER(AttnSource), c_void_p,
-                              c_void_p, c_int, c_int, c_float, c_void_p],
+                              c_void_p, c_int, c_void_p, c_int, c_float, c_void_p],
     "b200_layernorm_mod_bf16": [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                 c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
                                 c_int, c_void_p, c_int, c_void_p],

@@ -9,7 +9,8 @@
 // This replaces the per-resolution Python loops around xformers / SDPA in the reference
 // (sduss/model_executor/modules/attention.py:155-203 self, :59-110 cross, :297-368 joint).
 //
-// CTA = ATT_NQ 128-row query tiles of one (sequence, head), walking the keys in steps of ATT_BN
+// The kernel is persistent: one CTA per SM walks a host-built list of work units (schedule below).
+// A unit = ATT_NQ 128-row query tiles of one (sequence, head), walking the keys in steps of ATT_BN
 // rows. Warps [0, 4 NQ): online softmax, one warpgroup per query tile, one thread per query row
 // (TMEM lane), the whole ATT_BN-column S row in registers, P written back to TMEM as packed
 // bf16. Warp 4 NQ: TMA producer (Q once, K and V rings). Warps 4 NQ + 1 + t: one tcgen05.mma
@@ -29,7 +30,10 @@
 // softmax warps rescale O in TMEM before releasing P.
 #include "../../include/sduss_b200.h"
 #include "host_util.h"
+#include <algorithm>
 #include <cstdio>
+#include <queue>
+#include <vector>
 
 #include "ptx.cuh"
 
@@ -60,19 +64,27 @@ constexpr int ATT_Q_BYTES = ATT_BM * ATT_D * 2;   // 16 KB
 constexpr int ATT_KV_BYTES = ATT_BN * ATT_D * 2;  // 8 or 16 KB
 constexpr int ATT_BOX_ROWS = 64;                  // rows per TMA box (all maps)
 constexpr int ATT_BOX_BYTES = ATT_BOX_ROWS * ATT_D * 2;
-constexpr int ATT_SMEM = ATT_NQ * ATT_Q_BYTES + (ATT_KS + ATT_VS) * ATT_KV_BYTES + 1024 + 256;
+constexpr int ATT_QBUF = 2;  // Q tile sets: the next unit's queries load under the current unit
+constexpr int ATT_SD = 4;    // depth of the in-CTA unit-id ring (scheduler warp -> other roles)
+constexpr int ATT_SMEM =
+    ATT_QBUF * ATT_NQ * ATT_Q_BYTES + (ATT_KS + ATT_VS) * ATT_KV_BYTES + 1024 + 512;
 constexpr int ATT_TMEM_USED = ATT_NQ * (ATT_BN + ATT_BN / 2 + ATT_D);
 constexpr int ATT_TMEM_COLS = ATT_TMEM_USED <= 256 ? 256 : 512;
 static_assert(ATT_TMEM_USED <= 512, "TMEM budget");
 static_assert(ATT_BN == 64 || ATT_BN == 128, "kv step");
 constexpr float ATT_RESCALE_THRESHOLD = 8.f;  // lazy rescale: keep a stale max while p <= 2^8
+#ifndef ATT_F32X2
+#define ATT_F32X2 1  // packed fp32 pairs (FFMA2 / FADD2) in the softmax
+#endif
 #ifndef ATT_SKEW
-#define ATT_SKEW 400  // one-time start offset (cycles) between the softmax groups of a CTA
+#define ATT_SKEW 0  // one-time start offset (cycles) between the softmax groups of a CTA (A/B knob)
 #endif
 
 struct AttnArgs {
   const int* seq_table;   // [n_seq][8]: qa_row, qa_len, qb_row, qb_len, ka_row, ka_len, kb_row, kb_len
-  const int* work_items;  // [n_items][4]: seq, q_seg (0 = A, 1 = B), row offset in segment, unused
+  const int* work_units;  // [n_units][4]: seq, q_seg (0 = A, 1 = B), row offset in segment, head
+  int* sched;             // [2]: next unit to hand out (minus gridDim.x), CTAs finished; self-resetting
+  int n_units;
   int q_col[2], k_col[2], v_col[2];  // column of head 0 inside each source buffer
   __nv_bfloat16* out[2];             // output buffers for Q segment A / B
   int ldo[2];
@@ -95,6 +107,30 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// One work unit, decoded from the tables (written once per plan, not by the preceding kernel:
+// safe to read before pdl_wait()).
+struct AttnUnit {
+  int q_seg, q_row0, q_rows, nq, head;
+  int ka_row, ka_len, kb_row, kb_len, nA, n_tiles;
+};
+
+__device__ __forceinline__ AttnUnit load_unit(const AttnArgs& a, int u) {
+  const int4 item = __ldg(reinterpret_cast<const int4*>(a.work_units) + u);
+  const int4* st = reinterpret_cast<const int4*>(a.seq_table + item.x * 8);
+  const int4 q = __ldg(st), k = __ldg(st + 1);
+  AttnUnit w;
+  w.q_seg = item.y;
+  w.head = item.w;
+  const int seg_row = w.q_seg == 0 ? q.x : q.z, seg_len = w.q_seg == 0 ? q.y : q.w;
+  w.q_row0 = seg_row + item.z;
+  w.q_rows = min(ATT_NQ * ATT_BM, seg_len - item.z);  // valid query rows of this unit
+  w.nq = (w.q_rows + ATT_BM - 1) / ATT_BM;            // active query tiles
+  w.ka_row = k.x; w.ka_len = k.y; w.kb_row = k.z; w.kb_len = k.w;
+  w.nA = (w.ka_len + ATT_BN - 1) / ATT_BN;
+  w.n_tiles = w.nA + (w.kb_len + ATT_BN - 1) / ATT_BN;
+  return w;
+}
+
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant__ CUtensorMap tmQB,
                 const __grid_constant__ CUtensorMap tmKA, const __grid_constant__ CUtensorMap tmKB,
@@ -103,12 +139,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                 // NQ tiles
-  uint8_t* sK = smem + ATT_NQ * ATT_Q_BYTES;
+  uint8_t* sQ = smem;                                 // QBUF sets of NQ tiles
+  uint8_t* sK = smem + ATT_QBUF * ATT_NQ * ATT_Q_BYTES;
   uint8_t* sV = sK + ATT_KS * ATT_KV_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_VS * ATT_KV_BYTES);
-  uint64_t* q_full = bars;                  // 1
-  uint64_t* k_full = bars + 1;              // KS
+  uint64_t* q_full = bars;                  // QBUF
+  uint64_t* q_empty = q_full + ATT_QBUF;    // QBUF: every issuer has issued its last Q K^T of the unit
+  uint64_t* k_full = q_empty + ATT_QBUF;    // KS
   uint64_t* k_empty = k_full + ATT_KS;      // KS
   uint64_t* v_full = k_empty + ATT_KS;      // VS
   uint64_t* v_empty = v_full + ATT_VS;      // VS
@@ -116,42 +153,47 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
   uint64_t* p_full = s_full + ATT_NQ;       // NQ
   uint64_t* o_full = p_full + ATT_NQ;       // NQ
   uint64_t* s_free = o_full + ATT_NQ;       // NQ: softmax has copied S_t to registers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + ATT_NQ);
+  uint64_t* u_full = s_free + ATT_NQ;       // SD: unit id published
+  uint64_t* u_empty = u_full + ATT_SD;      // SD: read by every other warp
+  volatile int* u_ids = reinterpret_cast<volatile int*>(u_empty + ATT_SD);  // SD
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(const_cast<int*>(u_ids) + ATT_SD);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // grid = (heads, work items): CTAs are dispatched in linear order, x fastest, and the work
-  // items are sorted longest first, so all heads of the longest sequences start first and the
-  // tail of the launch is made of the shortest ones (longest-processing-time-first).
-  const int head = blockIdx.x;
-
-  // work tables are written once per plan (not by the preceding kernel): safe before pdl_wait()
-  const int4 item = reinterpret_cast<const int4*>(a.work_items)[blockIdx.y];
-  const int* st = a.seq_table + item.x * 8;
-  const int q_seg = item.y;
-  const int q_row0 = st[q_seg * 2] + item.z;
-  const int q_rows = min(ATT_NQ * ATT_BM, st[q_seg * 2 + 1] - item.z);  // valid query rows in this CTA
-  const int nq = (q_rows + ATT_BM - 1) / ATT_BM;                        // active query tiles
-  const int ka_row = st[4], ka_len = st[5], kb_row = st[6], kb_len = st[7];
-  const int nA = (ka_len + ATT_BN - 1) / ATT_BN;
-  const int nB = (kb_len + ATT_BN - 1) / ATT_BN;
-  const int n_tiles = nA + nB;
+  // Persistent CTA, one per SM. Units are sorted longest first (b200_attn_build_schedule); CTA b
+  // starts with unit b and then takes the next unit from a global counter, which balances the SMs
+  // like the hardware CTA dispatcher would, without paying launch + TMEM allocation + load latency
+  // per unit (~2 us, 7-20 % of a short sequence): the roles below walk the unit sequence
+  // independently and meet only through mbarriers, so the Q / K / V loads and the first Q K^T of
+  // the next unit run under the last softmax steps and the output write of the current one, and
+  // the query tiles of a CTA drift apart freely (Q is double-buffered, the K / V rings bound the
+  // drift). The producer warp draws the unit ids and hands them to the other warps through a
+  // small smem ring (u_ids).
 
   if (warp == ATT_TMA_WARP && lane == 0) {
-    mbar_init(q_full, 1);
+    for (int i = 0; i < ATT_QBUF; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], ATT_NQ);
+    }
+    // Every ring stage is released by all ATT_NQ issuer warps (idle tiles release it unread), so
+    // the arrival counts do not depend on the unit.
     for (int i = 0; i < ATT_KS; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], nq);
+      mbar_init(&k_empty[i], ATT_NQ);
     }
     for (int i = 0; i < ATT_VS; ++i) {
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], nq);
+      mbar_init(&v_empty[i], ATT_NQ);
     }
     for (int i = 0; i < ATT_NQ; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
       mbar_init(&s_free[i], 4);
+    }
+    for (int i = 0; i < ATT_SD; ++i) {
+      mbar_init(&u_full[i], 1);
+      mbar_init(&u_empty[i], ATT_SM_WARPS + ATT_NQ);
     }
     fence_barrier_init();
   }
@@ -170,92 +212,147 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
   const uint32_t tS = tmem_base;
   const uint32_t tP = tmem_base + ATT_NQ * ATT_BN;
   const uint32_t tO = tP + ATT_NQ * (ATT_BN / 2);
+  // next unit id of this warp (consumer side of the u_ids ring); -1 = no more work
+  auto take_unit = [&](uint32_t it) -> int {
+    const uint32_t slot = it % ATT_SD;
+    mbar_wait(&u_full[slot], (it / ATT_SD) & 1);
+    const int u = u_ids[slot];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&u_empty[slot]);
+    return u;
+  };
 
   if (warp == ATT_TMA_WARP) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      const CUtensorMap* qm = q_seg == 0 ? &tmQA : &tmQB;
-      const int boxes = (q_rows + ATT_BOX_ROWS - 1) / ATT_BOX_ROWS;
-      mbar_expect_tx(q_full, boxes * ATT_BOX_BYTES);
-      for (int b = 0; b < boxes; ++b)
-        tma_load_2d(sQ + b * ATT_BOX_BYTES, qm, q_full, a.q_col[q_seg] + head * ATT_D,
-                    q_row0 + b * ATT_BOX_ROWS);
-    }
     int ks = 0, vs = 0;
     uint32_t kph = 0, vph = 0;
-    for (int j = 0; j < n_tiles; ++j) {
-      const bool inA = j < nA;
-      const int row = inA ? ka_row + j * ATT_BN : kb_row + (j - nA) * ATT_BN;
-      mbar_wait(&k_empty[ks], kph ^ 1);
+    int u = blockIdx.x;  // grid <= n_units
+    for (uint32_t it = 0;; ++it) {
+      // draw the unit after this one now; the result is only needed at the end of the iteration
+      int drawn = 0;
+      if (u >= 0 && lane == 0) drawn = atomicAdd(a.sched, 1);
+      const uint32_t slot = it % ATT_SD;
+      mbar_wait(&u_empty[slot], ((it / ATT_SD) & 1) ^ 1);
       if (lane == 0) {
-        mbar_expect_tx(&k_full[ks], ATT_KV_BYTES);
-#pragma unroll
-        for (int b = 0; b < ATT_BN / ATT_BOX_ROWS; ++b)
-          tma_load_2d(sK + ks * ATT_KV_BYTES + b * ATT_BOX_BYTES, inA ? &tmKA : &tmKB, &k_full[ks],
-                      a.k_col[inA ? 0 : 1] + head * ATT_D, row + b * ATT_BOX_ROWS);
+        u_ids[slot] = u;
+        mbar_arrive(&u_full[slot]);
       }
-      mbar_wait(&v_empty[vs], vph ^ 1);
+      if (u < 0) break;
+      const AttnUnit w = load_unit(a, u);
+      const uint32_t qb = it % ATT_QBUF;
+      mbar_wait(&q_empty[qb], ((it / ATT_QBUF) & 1) ^ 1);  // unit it - QBUF no longer reads this set
       if (lane == 0) {
-        mbar_expect_tx(&v_full[vs], ATT_KV_BYTES);
-#pragma unroll
-        for (int b = 0; b < ATT_BN / ATT_BOX_ROWS; ++b)
-          tma_load_2d(sV + vs * ATT_KV_BYTES + b * ATT_BOX_BYTES, inA ? &tmVA : &tmVB, &v_full[vs],
-                      a.v_col[inA ? 0 : 1] + head * ATT_D, row + b * ATT_BOX_ROWS);
+        const CUtensorMap* qm = w.q_seg == 0 ? &tmQA : &tmQB;
+        const int boxes = (w.q_rows + ATT_BOX_ROWS - 1) / ATT_BOX_ROWS;
+        mbar_expect_tx(&q_full[qb], boxes * ATT_BOX_BYTES);
+        for (int b = 0; b < boxes; ++b)
+          tma_load_2d(sQ + qb * (ATT_NQ * ATT_Q_BYTES) + b * ATT_BOX_BYTES, qm, &q_full[qb],
+                      a.q_col[w.q_seg] + w.head * ATT_D, w.q_row0 + b * ATT_BOX_ROWS);
       }
-      __syncwarp();
-      if (++ks == ATT_KS) { ks = 0; kph ^= 1; }
-      if (++vs == ATT_VS) { vs = 0; vph ^= 1; }
+      for (int j = 0; j < w.n_tiles; ++j) {
+        const bool inA = j < w.nA;
+        const int row = inA ? w.ka_row + j * ATT_BN : w.kb_row + (j - w.nA) * ATT_BN;
+        mbar_wait(&k_empty[ks], kph ^ 1);
+        if (lane == 0) {
+          mbar_expect_tx(&k_full[ks], ATT_KV_BYTES);
+#pragma unroll
+          for (int b = 0; b < ATT_BN / ATT_BOX_ROWS; ++b)
+            tma_load_2d(sK + ks * ATT_KV_BYTES + b * ATT_BOX_BYTES, inA ? &tmKA : &tmKB,
+                        &k_full[ks], a.k_col[inA ? 0 : 1] + w.head * ATT_D, row + b * ATT_BOX_ROWS);
+        }
+        mbar_wait(&v_empty[vs], vph ^ 1);
+        if (lane == 0) {
+          mbar_expect_tx(&v_full[vs], ATT_KV_BYTES);
+#pragma unroll
+          for (int b = 0; b < ATT_BN / ATT_BOX_ROWS; ++b)
+            tma_load_2d(sV + vs * ATT_KV_BYTES + b * ATT_BOX_BYTES, inA ? &tmVA : &tmVB,
+                        &v_full[vs], a.v_col[inA ? 0 : 1] + w.head * ATT_D, row + b * ATT_BOX_ROWS);
+        }
+        __syncwarp();
+        if (++ks == ATT_KS) { ks = 0; kph ^= 1; }
+        if (++vs == ATT_VS) { vs = 0; vph ^= 1; }
+      }
+      drawn = __shfl_sync(0xffffffffu, drawn, 0) + int(gridDim.x);
+      u = drawn < a.n_units ? drawn : -1;
     }
   } else if (warp > ATT_TMA_WARP) {
     // ------------------------------------------------------------ MMA issuer of query tile t
     const int t = warp - ATT_MMA_WARP0;
-    if (t < nq) {
-      constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, ATT_D, 0, 1);  // V is MN-major
-      const uint64_t dq = make_sdesc_sw128(smem_u32(sQ + t * ATT_Q_BYTES));
-      int ks = 0, vs = 0;
-      uint32_t kph = 0, vph = 0;
-      mbar_wait(q_full, 0);
+    constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, ATT_D, 0, 1);  // V is MN-major
+    int ks = 0, vs = 0;
+    uint32_t kph = 0, vph = 0;
+    uint32_t g = 0;  // key steps tile t has run in earlier units (phase of its s/p/o barriers)
+    uint64_t dq = 0;
+    auto issue_qk = [&](uint32_t k_addr) {  // S_t = Q_t K^T
+      if (lane == 0) {
+        const uint64_t dk = make_sdesc_sw128(k_addr);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_ss(tS + t * ATT_BN, dq + uint64_t(2 * k), dk + uint64_t(2 * k), idesc_qk,
+                  k != 0 ? 1u : 0u);
+        umma_commit(&s_full[t]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](uint32_t v_addr, int j) {  // O_t (+)= P_t V
+      if (lane == 0) {
+        const uint64_t dv = make_sdesc_sw128(v_addr);
+#pragma unroll
+        for (int k = 0; k < ATT_BN / 16; ++k)
+          // A: 16 bf16 of K = 8 TMEM columns; B: 16 kv rows = 2048 bytes (>>4 = 128)
+          umma_ts(tO + t * ATT_D, tP + t * (ATT_BN / 2) + 8 * k, dv + uint64_t(128 * k), idesc_pv,
+                  (j | k) != 0 ? 1u : 0u);
+        umma_commit(&o_full[t]);
+      }
+      __syncwarp();
+    };
+    for (uint32_t it = 0;; ++it) {
+      const int u = take_unit(it);
+      if (u < 0) break;
+      const AttnUnit w = load_unit(a, u);
+      const uint32_t qb = it % ATT_QBUF;
+      uint64_t* q_empty_u = &q_empty[qb];
+      dq = make_sdesc_sw128(smem_u32(sQ + (qb * ATT_NQ + t) * ATT_Q_BYTES));
+      mbar_wait(&q_full[qb], (it / ATT_QBUF) & 1);
       tc_fence_after();
-      auto issue_qk = [&](uint32_t k_addr) {  // S_t = Q_t K^T
-        if (lane == 0) {
-          const uint64_t dk = make_sdesc_sw128(k_addr);
-#pragma unroll
-          for (int k = 0; k < ATT_D / 16; ++k)
-            umma_ss(tS + t * ATT_BN, dq + uint64_t(2 * k), dk + uint64_t(2 * k), idesc_qk,
-                    k != 0 ? 1u : 0u);
-          umma_commit(&s_full[t]);
+      if (t >= w.nq) {
+        // idle tile of a short unit: release Q and every ring stage unread
+        if (lane == 0) mbar_arrive(q_empty_u);
+        for (int j = 0; j < w.n_tiles; ++j) {
+          mbar_wait(&k_full[ks], kph);
+          if (lane == 0) mbar_arrive(&k_empty[ks]);
+          if (++ks == ATT_KS) { ks = 0; kph ^= 1; }
+          mbar_wait(&v_full[vs], vph);
+          if (lane == 0) mbar_arrive(&v_empty[vs]);
+          if (++vs == ATT_VS) { vs = 0; vph ^= 1; }
         }
         __syncwarp();
-      };
-      auto issue_pv = [&](uint32_t v_addr, int j) {  // O_t (+)= P_t V
-        if (lane == 0) {
-          const uint64_t dv = make_sdesc_sw128(v_addr);
-#pragma unroll
-          for (int k = 0; k < ATT_BN / 16; ++k)
-            // A: 16 bf16 of K = 8 TMEM columns; B: 16 kv rows = 2048 bytes (>>4 = 128)
-            umma_ts(tO + t * ATT_D, tP + t * (ATT_BN / 2) + 8 * k, dv + uint64_t(128 * k), idesc_pv,
-                    (j | k) != 0 ? 1u : 0u);
-          umma_commit(&o_full[t]);
-        }
-        __syncwarp();
-      };
-      // prologue: S_t(0)
+        continue;
+      }
+      // prologue: S_t(0); the softmax warps must have pulled the last S_t of the previous unit
       mbar_wait(&k_full[ks], kph);
+      if (g > 0) mbar_wait(&s_free[t], (g - 1) & 1);
       tc_fence_after();
       issue_qk(smem_u32(sK + ks * ATT_KV_BYTES));
-      if (lane == 0) umma_commit(&k_empty[ks]);
+      if (lane == 0) {
+        umma_commit(&k_empty[ks]);
+        if (w.n_tiles == 1) umma_commit(q_empty_u);
+      }
       __syncwarp();
       if (++ks == ATT_KS) { ks = 0; kph ^= 1; }
-      for (int j = 0; j < n_tiles; ++j) {
-        const uint32_t ph = j & 1;
-        if (j + 1 < n_tiles) {
+      for (int j = 0; j < w.n_tiles; ++j) {
+        const uint32_t ph = (g + j) & 1;
+        if (j + 1 < w.n_tiles) {
           // S_t(j+1) as soon as softmax has pulled S_t(j) into registers
           mbar_wait(&k_full[ks], kph);
           mbar_wait(&s_free[t], ph);
           tc_fence_after();
           issue_qk(smem_u32(sK + ks * ATT_KV_BYTES));
-          if (lane == 0) umma_commit(&k_empty[ks]);
+          if (lane == 0) {
+            umma_commit(&k_empty[ks]);
+            if (j + 2 == w.n_tiles) umma_commit(q_empty_u);  // last read of Q_t in this unit
+          }
           __syncwarp();
           if (++ks == ATT_KS) { ks = 0; kph ^= 1; }
         }
@@ -267,34 +364,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
         __syncwarp();
         if (++vs == ATT_VS) { vs = 0; vph ^= 1; }
       }
+      g += uint32_t(w.n_tiles);
     }
   } else {
     // ------------------------------------------------------------ softmax + output
     const int t = warp >> 2;  // query tile of this warpgroup
-    if (t < nq) {
-      const int qd = warp & 3;
-      const int r = qd * 32 + lane;  // query row inside the tile == TMEM lane
-      const uint32_t lane_off = uint32_t(qd * 32) << 16;
-      const uint32_t t_s = tS + lane_off + t * ATT_BN;
-      const uint32_t t_o = tO + lane_off + t * ATT_D;
-      const uint32_t t_p = tP + lane_off + t * (ATT_BN / 2);
-      float m_run = -INFINITY, l_run = 0.f;
-      const float sc = a.scale_log2;
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;  // query row inside the tile == TMEM lane
+    const uint32_t lane_off = uint32_t(qd * 32) << 16;
+    const uint32_t t_s = tS + lane_off + t * ATT_BN;
+    const uint32_t t_o = tO + lane_off + t * ATT_D;
+    const uint32_t t_p = tP + lane_off + t * (ATT_BN / 2);
+    const float sc = a.scale_log2;
+    uint32_t g = 0;  // key steps this tile has run in earlier units
 #ifdef ATT_TIMING
-      long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      const long long t_begin = clock64();
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_begin = clock64();
+    long long n_steps = 0;
 #endif
+    for (uint32_t it = 0;; ++it) {
+      const int u = take_unit(it);
+      if (u < 0) break;
+      const AttnUnit w = load_unit(a, u);
+      if (t >= w.nq) continue;
+      float m_run = -INFINITY, l_run = 0.f;
 
-      for (int j = 0; j < n_tiles; ++j) {
-        const bool inA = j < nA;
-        const int n_valid =
-            inA ? min(ATT_BN, ka_len - j * ATT_BN) : min(ATT_BN, kb_len - (j - nA) * ATT_BN);
+      for (int j = 0; j < w.n_tiles; ++j) {
+        const bool inA = j < w.nA;
+        const int n_valid = inA ? min(ATT_BN, w.ka_len - j * ATT_BN)
+                                : min(ATT_BN, w.kb_len - (j - w.nA) * ATT_BN);
+        const uint32_t ph = (g + j) & 1;
         ATT_T(c0);
-        mbar_wait(&s_full[t], j & 1);
-        // The groups start one after the other: S_0(0), S_1(0), ... complete back to back, and
-        // groups that exponentiate at the same time also leave the MUFU pipe idle at the same
-        // time. Measured: +2 % (692 -> 706 TFLOP/s) for 400 cycles between group starts.
-        if (ATT_SKEW > 0 && j == 0 && t > 0) {
+        mbar_wait(&s_full[t], ph);
+        // Optional start offset between the groups (groups that exponentiate at the same time also
+        // leave the MUFU pipe idle at the same time). It gave +2 % with one unit per CTA; in the
+        // persistent kernel the tiles drift on their own and it measures as noise (0 / 400 / 800
+        // cycles: 731 / 733 / 731 TFLOP/s), so it is off.
+        if (ATT_SKEW > 0 && g == 0 && j == 0 && t > 0) {
           const long long until = clock64() + t * ATT_SKEW;
           while (clock64() < until) {
           }
@@ -333,8 +439,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
         }
         const float m_sc = m_run * sc;
         ATT_T(c3);
-        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t pk[ATT_BN / 2];
+#if ATT_F32X2
+        // Packed fp32 pairs (FFMA2 / FADD2, sm_100): the scale-and-shift and the row sum take one
+        // issue slot per two elements; the warps are issue-bound next to the MUFU pipe.
+        float2* s2 = reinterpret_cast<float2*>(s);
+        const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-m_sc, -m_sc);
+#pragma unroll
+        for (int i = 0; i < ATT_BN / 2; ++i) {
+          const float2 x = __ffma2_rn(s2[i], sc2, nm2);
+          s2[i] = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+        }
+        float2 acc2[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc2[i] = s2[i];
+#pragma unroll
+        for (int i = 4; i < ATT_BN / 2; ++i) acc2[i & 3] = __fadd2_rn(acc2[i & 3], s2[i]);
+#pragma unroll
+        for (int i = 0; i < ATT_BN / 2; ++i) pk[i] = pack_bf16x2(s2[i].x, s2[i].y);
+        const float2 acc = __fadd2_rn(__fadd2_rn(acc2[0], acc2[1]), __fadd2_rn(acc2[2], acc2[3]));
+        const float sum = acc.x + acc.y;
+#else
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < ATT_BN; ++i) {
           s[i] = fast_exp2(fmaf(s[i], sc, -m_sc));
@@ -345,11 +471,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
           pk[i >> 1] = pack_bf16x2(s[i], s[i + 1]);
         }
         const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+#endif
         l_run = l_run * alpha + sum;
         ATT_T(c4);
         if (j > 0) {
           // PV_t(j-1) must be complete before P_t is overwritten and before O_t is rescaled
-          mbar_wait(&o_full[t], (j - 1) & 1);
+          mbar_wait(&o_full[t], ph ^ 1);
           tc_fence_after();
           if (__any_sync(0xffffffffu, resc)) {
             uint32_t o[ATT_D];
@@ -373,24 +500,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
         ATT_ACC(0, c0, c1); ATT_ACC(1, c1, c2); ATT_ACC(2, c2, c3); ATT_ACC(3, c3, c4);
         ATT_ACC(4, c4, c5); ATT_ACC(5, c5, c6);
       }
+      g += uint32_t(w.n_tiles);
 #ifdef ATT_TIMING
-      if (a.dbg != nullptr && lane == 0 && qd == 2 && t < 2) {
-        long long* d = a.dbg + (size_t(blockIdx.x) * gridDim.y + blockIdx.y) * 16 + t * 8;
-        for (int i = 0; i < 6; ++i) d[i] = tacc[i];
-        d[6] = clock64() - t_begin;
-        d[7] = n_tiles;
-      }
+      n_steps += w.n_tiles;
 #endif
-      mbar_wait(&o_full[t], (n_tiles - 1) & 1);
+      // Output of the unit. The first P V of the next unit overwrites O_t, but it needs p_full of
+      // that unit, which these warps only give after this read has completed.
+      ATT_T(e0);
+      mbar_wait(&o_full[t], (g - 1) & 1);
       tc_fence_after();
       uint32_t o[ATT_D];
       tmem_ld32(t_o, o);
       tmem_ld32(t_o + 32, o + 32);
       tmem_wait_ld();
-      if (t * ATT_BM + r < q_rows) {
+      tc_fence_before();
+      if (t * ATT_BM + r < w.q_rows) {
         const float inv = 1.f / l_run;
-        __nv_bfloat16* op = a.out[q_seg] + size_t(q_row0 + t * ATT_BM + r) * a.ldo[q_seg] +
-                            a.o_col[q_seg] + head * ATT_D;
+        __nv_bfloat16* op = a.out[w.q_seg] +
+                            size_t(w.q_row0 + t * ATT_BM + r) * a.ldo[w.q_seg] +
+                            a.o_col[w.q_seg] + w.head * ATT_D;
 #pragma unroll
         for (int i = 0; i < ATT_D; i += 8) {
           uint4 v;
@@ -401,7 +529,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
           *reinterpret_cast<uint4*>(op + i) = v;
         }
       }
+      ATT_T(e1);
+      ATT_ACC(6, e0, e1);
     }
+#ifdef ATT_TIMING
+    if (a.dbg != nullptr && lane == 0 && qd == 2 && t < 2) {
+      long long* d = a.dbg + size_t(blockIdx.x) * 32 + t * 16;
+      for (int i = 0; i < 7; ++i) d[i] = tacc[i];
+      d[7] = n_steps;
+      d[8] = clock64() - t_begin;
+    }
+#endif
   }
 
   tc_fence_before();
@@ -409,6 +547,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+  }
+  if (threadIdx.x == 0) {
+    // the last CTA to finish re-arms the unit counter for the next launch (graph replays included)
+    __threadfence();
+    if (atomicInc(reinterpret_cast<unsigned*>(a.sched) + 1, gridDim.x - 1) == gridDim.x - 1) a.sched[0] = 0;
   }
 }
 
@@ -430,10 +573,46 @@ extern "C" long long* b200_attn_debug_buffer(void) { return g_att_dbg; }
 
 extern "C" int b200_attn_rows_per_item(void) { return ATT_NQ * ATT_BM; }
 
+// Host-side work list of the persistent kernel. Units = (query block of ATT_NQ tiles, head),
+// sorted longest first by the softmax time the kernel is bound by: key steps x max(active tiles x
+// MUFU time per tile-step, length of one warp's dependent chain). The kernel hands them out in
+// this order (longest-processing-time-first list scheduling).
+extern "C" int b200_attn_build_schedule(const int32_t* seq_table, int n_seq, int n_heads,
+                                        int32_t* work_units, int* n_units_out) {
+  if (!seq_table || n_seq <= 0 || n_heads <= 0 || !n_units_out) return B200_ERR_INVALID;
+  struct Block { long cost; int seq, seg, off; };
+  std::vector<Block> blocks;
+  for (int i = 0; i < n_seq; ++i) {
+    const int32_t* s = seq_table + i * 8;
+    const long steps = (s[5] + ATT_BN - 1) / ATT_BN + (s[7] + ATT_BN - 1) / ATT_BN;
+    for (int seg = 0; seg < 2; ++seg)
+      for (int off = 0; off < s[2 * seg + 1]; off += ATT_NQ * ATT_BM) {
+        const int rows = std::min(ATT_NQ * ATT_BM, s[2 * seg + 1] - off);
+        const long nq = (rows + ATT_BM - 1) / ATT_BM;
+        blocks.push_back({steps * std::max(nq * 560L, 900L), i, seg, off});
+      }
+  }
+  std::stable_sort(blocks.begin(), blocks.end(),
+                   [](const Block& x, const Block& y) { return x.cost > y.cost; });
+  const long n_units = long(blocks.size()) * n_heads;
+  if (n_units <= 0 || n_units > (1L << 28)) return B200_ERR_INVALID;
+  *n_units_out = int(n_units);
+  if (!work_units) return B200_OK;  // size query
+  int32_t* w = work_units;
+  for (const Block& bl : blocks)
+    for (int h = 0; h < n_heads; ++h, w += 4) {
+      w[0] = bl.seq; w[1] = bl.seg; w[2] = bl.off; w[3] = h;
+    }
+  return B200_OK;
+}
+
 extern "C" int b200_attn_varlen_bf16(const B200AttnSource* src_a, const B200AttnSource* src_b,
-                                     const int32_t* seq_table, const int32_t* work_items,
-                                     int n_items, int n_heads, float softmax_scale, void* stream_) {
-  if (!src_a || !seq_table || !work_items || n_items <= 0 || n_heads <= 0) return B200_ERR_INVALID;
+                                     const int32_t* seq_table, const int32_t* work_units,
+                                     int n_units, int32_t* sched_state, int max_ctas,
+                                     float softmax_scale, void* stream_) {
+  if (!src_a || !seq_table || !work_units || !sched_state || n_units <= 0 || max_ctas < 0)
+    return B200_ERR_INVALID;
+  const int n_ctas = std::min(n_units, max_ctas > 0 ? max_ctas : device_sm_count());
   const B200AttnSource* srcs[2] = {src_a, src_b ? src_b : src_a};
   CUtensorMap tm[2][3];
   bool have[2][3] = {{false, false, false}, {false, false, false}};
@@ -465,7 +644,9 @@ extern "C" int b200_attn_varlen_bf16(const B200AttnSource* src_a, const B200Attn
     for (int t = 0; t < 3; ++t)
       if (!have[s][t]) tm[s][t] = *any;
   a.seq_table = seq_table;
-  a.work_items = work_items;
+  a.work_units = work_units;
+  a.sched = sched_state;
+  a.n_units = n_units;
   a.scale_log2 = softmax_scale * 1.4426950408889634f;
   a.dbg = nullptr;
 #ifdef ATT_TIMING
@@ -473,7 +654,7 @@ extern "C" int b200_attn_varlen_bf16(const B200AttnSource* src_a, const B200Attn
     static long long* dbg_buf = nullptr;
     if (!dbg_buf) cudaMalloc(&dbg_buf, size_t(1) << 26);
     a.dbg = dbg_buf;
-    cudaMemsetAsync(dbg_buf, 0, (size_t(n_items) * n_heads * 16 + 1024) * 8, reinterpret_cast<cudaStream_t>(stream_));
+    cudaMemsetAsync(dbg_buf, 0, (size_t(n_ctas) * 32 + 1024) * 8, reinterpret_cast<cudaStream_t>(stream_));
     extern long long* g_att_dbg;
     g_att_dbg = dbg_buf;
   }
@@ -497,8 +678,7 @@ extern "C" int b200_attn_varlen_bf16(const B200AttnSource* src_a, const B200Attn
     }
   }
 #endif
-  if (n_items > 65535) return B200_ERR_UNSUPPORTED;
-  dim3 grid(n_heads, n_items);
+  dim3 grid(n_ctas);
   return launch_pdl(attn_fwd_kernel, grid, dim3(ATT_THREADS), ATT_SMEM,
                     reinterpret_cast<cudaStream_t>(stream_), tm[0][0], tm[1][0], tm[0][1], tm[1][1],
                     tm[0][2], tm[1][2], a);

@@ -2,6 +2,7 @@
 raise on a non-zero status. PyTorch is plumbing here (memory + streams); all arithmetic
 happens inside libsduss_b200.so."""
 import ctypes
+import os
 
 import torch
 
@@ -218,29 +219,38 @@ def attn_source(q=None, q_col=0, k=None, k_col=0, v=None, v_col=0, out=None, o_c
 ATTN_Q_TILE = lib.b200_attn_rows_per_item()  # query rows per CTA of attn_fwd_kernel
 
 
-def build_attn_plan(seqs, device):
+def attn_max_ctas():
+    """0 = one CTA per SM (the library default). SDUSS_B200_ATTN_MAX_CTAS overrides it for A/B
+    measurements (a huge value gives one unit per CTA, i.e. plain hardware dispatch)."""
+    return int(os.environ.get("SDUSS_B200_ATTN_MAX_CTAS", "0"))
+
+
+def build_attn_plan(seqs, device, n_heads, max_ctas=None):
     """seqs: list of 8-tuples (qa_row, qa_len, qb_row, qb_len, ka_row, ka_len, kb_row, kb_len).
-    Returns (seq_table, work_items, n_items) as int32 device tensors; query tiles of the
-    longest sequences come first so the tail of the grid is made of short ones."""
-    table = np.asarray(seqs, dtype=np.int32).reshape(-1, 8)
-    items = []
-    for i, s in enumerate(table):
-        kv = int(s[5]) + int(s[7])
-        for seg in (0, 1):
-            qlen = int(s[2 * seg + 1])
-            for off in range(0, qlen, ATTN_Q_TILE):
-                items.append((kv, i, seg, off))
-    items.sort(key=lambda t: -t[0])
-    work = np.asarray([(i, seg, off, 0) for _, i, seg, off in items], dtype=np.int32).reshape(-1, 4)
-    return (torch.from_numpy(table).to(device), torch.from_numpy(work).to(device), len(items))
+    Returns (seq_table, work_units, n_units, sched_state, max_ctas) for attn_varlen: int32 tensors
+    on `device`; the unit list (longest first) is built by the library's host function
+    b200_attn_build_schedule; sched_state is the zeroed, self-resetting unit counter of the
+    persistent kernel (one per plan: launches of one plan never overlap)."""
+    table = np.ascontiguousarray(np.asarray(seqs, dtype=np.int32).reshape(-1, 8))
+    n_units = ctypes.c_int(0)
+    check(lib.b200_attn_build_schedule(table.ctypes.data, table.shape[0], n_heads, None,
+                                       ctypes.byref(n_units)), "b200_attn_build_schedule")
+    units = np.zeros((n_units.value, 4), dtype=np.int32)
+    check(lib.b200_attn_build_schedule(table.ctypes.data, table.shape[0], n_heads,
+                                       units.ctypes.data, ctypes.byref(n_units)),
+          "b200_attn_build_schedule")
+    return (torch.from_numpy(table).to(device), torch.from_numpy(units).to(device), n_units.value,
+            torch.zeros(2, dtype=torch.int32, device=device),
+            attn_max_ctas() if max_ctas is None else max_ctas)
 
 
-def attn_varlen(src_a, src_b, seq_table, work_items, n_items, n_heads, scale):
+def attn_varlen(src_a, src_b, seq_table, work_units, n_units, sched_state, max_ctas, scale):
     _ev = _count("b200_attn_varlen_bf16")
     check(lib.b200_attn_varlen_bf16(ctypes.byref(src_a),
                                     ctypes.byref(src_b) if src_b is not None else None,
-                                    _ptr(seq_table), _ptr(work_items), n_items, n_heads,
-                                    ctypes.c_float(scale), _stream()), "b200_attn_varlen_bf16")
+                                    _ptr(seq_table), _ptr(work_units), n_units, _ptr(sched_state),
+                                    max_ctas, ctypes.c_float(scale), _stream()),
+          "b200_attn_varlen_bf16")
     if _ev is not None:
         _ev.record()
 

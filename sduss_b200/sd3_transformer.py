@@ -123,9 +123,9 @@ class _Plan:
         # attention work lists
         joint = [(int(off[l]), S[l], l * ctx_len, ctx_len, int(off[l]), S[l], l * ctx_len, ctx_len)
                  for l in range(L)]
-        self.joint_plan = ops.build_attn_plan(joint, dev)
+        self.joint_plan = ops.build_attn_plan(joint, dev, model.cfg.num_attention_heads)
         selfp = [(int(off[l]), S[l], 0, 0, int(off[l]), S[l], 0, 0) for l in range(L)]
-        self.self_plan = ops.build_attn_plan(selfp, dev)
+        self.self_plan = ops.build_attn_plan(selfp, dev, model.cfg.num_attention_heads)
         # attention sources (pointers are static)
         self.src_img = ops.attn_source(q=self.qkv, q_col=0, k=self.qkv, k_col=D, v=self.qkv,
                                        v_col=2 * D, out=self.att)
@@ -297,7 +297,7 @@ class B200SD3Transformer2DModel(torch.nn.Module):
             G(pl.xn, blk["qkv_w"], pl.qkv, bias=blk["qkv_b"], epi=ops.EPI_QK_RMSNORM,
               rms_wq=blk["norm_q"], rms_wk=blk["norm_k"], rms_q_cols=D, rms_k_cols=D)
             main.wait_event(ev_side)
-            ops.attn_varlen(pl.src_img, pl.src_ctx, *pl.joint_plan, H, scale)
+            ops.attn_varlen(pl.src_img, pl.src_ctx, *pl.joint_plan, scale)
             ev_main.record(main)
             if not last:
                 with torch.cuda.stream(side):
@@ -314,7 +314,7 @@ class B200SD3Transformer2DModel(torch.nn.Module):
             if dual:
                 G(pl.xn2, blk["qkv2_w"], pl.qkv, bias=blk["qkv2_b"], epi=ops.EPI_QK_RMSNORM,
                   rms_wq=blk["norm_q2"], rms_wk=blk["norm_k2"], rms_q_cols=D, rms_k_cols=D)
-                ops.attn_varlen(pl.src_img, None, *pl.self_plan, H, scale)
+                ops.attn_varlen(pl.src_img, None, *pl.self_plan, scale)
                 G(pl.att, blk["out2_w"], pl.x, bias=blk["out2_b"], epi=ops.EPI_GATE_RESID,
                   resid=pl.x, gate=mod[:, m + 8 * D:m + 9 * D], row_group=pl.row_group)
             ops.layernorm_mod(pl.x, pl.xn, eps=1e-6, mod=mod, row_group=pl.row_group,

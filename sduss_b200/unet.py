@@ -99,8 +99,8 @@ class _Plan:
         for l, lay in enumerate(self.levels):
             selfp = [(lay.row_off[i], lay.rows[i], 0, 0, lay.row_off[i], lay.rows[i], 0, 0) for i in range(L)]
             crossp = [(lay.row_off[i], lay.rows[i], 0, 0, 0, 0, i * ctx_len, ctx_len) for i in range(L)]
-            self.self_plan[l] = ops.build_attn_plan(selfp, dev)
-            self.cross_plan[l] = ops.build_attn_plan(crossp, dev)
+            self.self_plan[l] = ops.build_attn_plan(selfp, dev, cfg.num_heads[l])
+            self.cross_plan[l] = ops.build_attn_plan(crossp, dev, cfg.num_heads[l])
         self.gn_ws = ops.groupnorm_workspace(self.levels[0].T, L, dev)
         self.bufs: Dict[str, torch.Tensor] = {}
         self.maps: Dict[tuple, torch.Tensor] = {}
@@ -316,7 +316,7 @@ class B200UNet(torch.nn.Module):
             b = f"{name}.transformer_blocks.{j}"
             ops.layernorm_mod(h, ln, eps=1e-5, gamma=w[b + ".norm1.weight"], beta=w[b + ".norm1.bias"])
             G(ln, w[b + ".attn1.qkv.weight"], qkv)
-            ops.attn_varlen(pl.attn_src[key], None, *pl.self_plan[level], heads, 0.125)
+            ops.attn_varlen(pl.attn_src[key], None, *pl.self_plan[level], 0.125)
             G(att, w[b + ".attn1.out.weight"], h, bias=w[b + ".attn1.out.bias"], epi=ops.EPI_GATE_RESID, resid=h)
             ops.layernorm_mod(h, ln, eps=1e-5, gamma=w[b + ".norm2.weight"], beta=w[b + ".norm2.bias"])
             G(ln, w[b + ".attn2.q.weight"], q2)
@@ -324,7 +324,7 @@ class B200UNet(torch.nn.Module):
             src_kv = pl.attn_src.get((b, "kv"))
             if src_kv is None:
                 src_kv = pl.attn_src[(b, "kv")] = ops.attn_source(k=kv_all, k_col=ko, v=kv_all, v_col=ko + C)
-            ops.attn_varlen(pl.attn_src[(level, C, "q")], src_kv, *pl.cross_plan[level], heads, 0.125)
+            ops.attn_varlen(pl.attn_src[(level, C, "q")], src_kv, *pl.cross_plan[level], 0.125)
             G(att, w[b + ".attn2.out.weight"], h, bias=w[b + ".attn2.out.bias"], epi=ops.EPI_GATE_RESID, resid=h)
             ops.layernorm_mod(h, ln, eps=1e-5, gamma=w[b + ".norm3.weight"], beta=w[b + ".norm3.bias"])
             G(ln, w[b + ".ff1.weight"], ff, bias=w[b + ".ff1.bias"], epi=ops.EPI_GEGLU)

@@ -27,9 +27,13 @@ def _check(out, ref):
     assert cos > 0.9995, cos
 
 
+# max_ctas: None = one CTA per SM (these small cases then run one unit per CTA); 1 / 3 / 7 force the
+# persistent path: several units per CTA, with idle query tiles, partial tiles and 1-step units
+# in between full ones.
+@pytest.mark.parametrize("max_ctas", [None, 1, 3, 7])
 @pytest.mark.parametrize("img_lens,ctx_len", [((128,), 0), ((256, 1024), 0), ((1024, 256, 2304), 333),
-                                              ((256,), 45), ((200, 77), 50)])
-def test_joint_and_self(cuda, img_lens, ctx_len):
+                                              ((256,), 45), ((200, 77), 50), ((40, 700, 64, 1), 0)])
+def test_joint_and_self(cuda, img_lens, ctx_len, max_ctas):
     from sduss_b200 import ops
     L = len(img_lens)
     Ta, Tb = sum(img_lens), L * ctx_len
@@ -43,11 +47,11 @@ def test_joint_and_self(cuda, img_lens, ctx_len):
     for i, s in enumerate(img_lens):
         seqs.append((ra, s, i * ctx_len, ctx_len, ra, s, i * ctx_len, ctx_len))
         ra += s
-    table, work, n = ops.build_attn_plan(seqs, cuda)
+    plan = ops.build_attn_plan(seqs, cuda, H, max_ctas)
     sa = ops.attn_source(q=qkv_a, q_col=0, k=qkv_a, k_col=C, v=qkv_a, v_col=2 * C, out=out_a)
     sb = ops.attn_source(q=qkv_b, q_col=0, k=qkv_b, k_col=C, v=qkv_b, v_col=2 * C, out=out_b) if ctx_len else None
     scale = 1 / math.sqrt(64)
-    ops.attn_varlen(sa, sb, table, work, n, H, scale)
+    ops.attn_varlen(sa, sb, *plan, scale)
     torch.cuda.synchronize()
     ra = 0
     for i, s in enumerate(img_lens):
@@ -62,7 +66,8 @@ def test_joint_and_self(cuda, img_lens, ctx_len):
         ra += s
 
 
-def test_cross(cuda):
+@pytest.mark.parametrize("max_ctas", [None, 4])
+def test_cross(cuda, max_ctas):
     """SDXL cross attention: Q = image tokens (A), K/V = 77 text tokens (B)."""
     from sduss_b200 import ops
     img_lens, T = (1024, 4096, 256), 77
@@ -74,10 +79,10 @@ def test_cross(cuda):
     for i, s in enumerate(img_lens):
         seqs.append((ra, s, 0, 0, 0, 0, i * T, T))
         ra += s
-    table, work, n = ops.build_attn_plan(seqs, cuda)
+    plan = ops.build_attn_plan(seqs, cuda, H, max_ctas)
     sa = ops.attn_source(q=q, out=out)
     sb = ops.attn_source(k=kv, k_col=0, v=kv, v_col=C)
-    ops.attn_varlen(sa, sb, table, work, n, H, 0.125)
+    ops.attn_varlen(sa, sb, *plan, 0.125)
     torch.cuda.synchronize()
     ra = 0
     for i, s in enumerate(img_lens):
@@ -87,7 +92,7 @@ def test_cross(cuda):
         ra += s
 
 
-def _joint(cuda, qkv_a, qkv_b, img_lens, ctx_len, rows_a=None):
+def _joint(cuda, qkv_a, qkv_b, img_lens, ctx_len, max_ctas=None):
     """Runs the packed joint attention for sequences laid out back to back; returns (out_a, out_b)."""
     from sduss_b200 import ops
     C = H * 64
@@ -97,10 +102,10 @@ def _joint(cuda, qkv_a, qkv_b, img_lens, ctx_len, rows_a=None):
     for i, s in enumerate(img_lens):
         seqs.append((ra, s, i * ctx_len, ctx_len, ra, s, i * ctx_len, ctx_len))
         ra += s
-    table, work, n = ops.build_attn_plan(seqs, cuda)
+    plan = ops.build_attn_plan(seqs, cuda, H, max_ctas)
     sa = ops.attn_source(q=qkv_a, q_col=0, k=qkv_a, k_col=C, v=qkv_a, v_col=2 * C, out=out_a)
     sb = ops.attn_source(q=qkv_b, q_col=0, k=qkv_b, k_col=C, v=qkv_b, v_col=2 * C, out=out_b)
-    ops.attn_varlen(sa, sb, table, work, n, H, 0.125)
+    ops.attn_varlen(sa, sb, *plan, 0.125)
     torch.cuda.synchronize()
     return out_a, out_b
 
@@ -122,3 +127,7 @@ def test_deterministic_and_batch_invariant(cuda):
         assert torch.equal(a1, oa[ra:ra + s]), i
         assert torch.equal(b1, ob[i * ctx:(i + 1) * ctx]), i
         ra += s
+    # ... nor on how the units are spread over the CTAs (a unit's arithmetic is self-contained)
+    for m in (1, 5, 100000):
+        oa3, ob3 = _joint(cuda, qkv_a, qkv_b, img_lens, ctx, max_ctas=m)
+        assert torch.equal(oa, oa3) and torch.equal(ob, ob3), m

@@ -35,20 +35,27 @@ def test_level_layout_tables_match_reference_tables():
     assert all((c == 1).all() for c in cover)
 
 
-def test_attention_plan_covers_all_query_rows():
+def test_attention_schedule_covers_all_query_rows_once_per_head():
+    """b200_attn_build_schedule (host function of the library, no GPU): every (query row, head)
+    is in exactly one unit and the list is sorted longest first."""
     from sduss_b200 import ops
-    seqs = [(0, 1024, 0, 333, 0, 1024, 0, 333), (1024, 256, 333, 333, 1024, 256, 333, 333)]
-    table, work, n = ops.build_attn_plan(seqs, "cpu")
-    assert table.shape == (2, 8) and work.shape == (n, 4)
-    step = ops.ATTN_Q_TILE
-    rows = {(s, g): 0 for s in range(2) for g in range(2)}
-    for s, g, off, _ in work.numpy():
+    seqs = [(0, 1024, 0, 333, 0, 1024, 0, 333), (1024, 256, 333, 333, 1024, 256, 333, 333),
+            (1280, 4096, 666, 333, 1280, 4096, 666, 333)]
+    H, step = 5, ops.ATTN_Q_TILE
+    table, units, n_units, sched, max_ctas = ops.build_attn_plan(seqs, "cpu", H)
+    units = units.numpy()
+    assert table.shape == (3, 8) and units.shape == (n_units, 4) and max_ctas == 0
+    assert sched.shape == (2,) and sched.dtype == torch.int32 and not sched.any()
+    rows = {}
+    for s, g, off, h in units:
         qlen = seqs[s][2 * g + 1]
-        assert off % step == 0 and off < qlen
-        rows[(s, g)] += min(step, qlen - off)
-    assert rows == {(0, 0): 1024, (0, 1): 333, (1, 0): 256, (1, 1): 333}
-    kv = [seqs[s][5] + seqs[s][7] for s, _, _, _ in work.numpy()]
-    assert kv == sorted(kv, reverse=True)  # longest first
+        assert off % step == 0 and off < qlen and 0 <= h < H
+        rows[(s, g, h)] = rows.get((s, g, h), 0) + min(step, qlen - off)
+    assert rows == {(s, g, h): seqs[s][2 * g + 1] for s in range(3) for g in range(2) for h in range(H)}
+    cost = [(seqs[s][5] + seqs[s][7]) * -(-min(step, seqs[s][2 * g + 1] - off) // 128) for s, g, off, _ in units]
+    assert cost == sorted(cost, reverse=True)  # longest first
+    again = ops.build_attn_plan(seqs, "cpu", H)
+    assert torch.equal(again[1], torch.from_numpy(units))  # deterministic
 
 
 def test_standalone_schedulers_match_oracle_tables():

@@ -13,25 +13,24 @@ oa = torch.empty(Ta, C, device=dev, dtype=torch.bfloat16); ob = torch.empty(Tb, 
 seqs, ra = [], 0
 for i, s in enumerate(img):
     seqs.append((ra, s, i * ctx, ctx, ra, s, i * ctx, ctx)); ra += s
-table, work, n = ops.build_attn_plan(seqs, dev)
+plan = ops.build_attn_plan(seqs, dev, H)
 sa = ops.attn_source(q=qa, k=qa, k_col=C, v=qa, v_col=2 * C, out=oa)
 sb = ops.attn_source(q=qb, k=qb, k_col=C, v=qb, v_col=2 * C, out=ob)
-for _ in range(3): ops.attn_varlen(sa, sb, table, work, n, H, 0.125)
+for _ in range(3): ops.attn_varlen(sa, sb, *plan, 0.125)
 torch.cuda.synchronize()
 lib.b200_attn_debug_buffer.restype = ctypes.c_void_p
 ptr = lib.b200_attn_debug_buffer()
-host = torch.empty(n * H * 16, dtype=torch.int64)
+n = 148
+host = torch.empty(n * 32, dtype=torch.int64)
 import ctypes as C_
 cudart = C_.CDLL("/usr/local/cuda/lib64/libcudart.so.12")
-cudart.cudaMemcpy(C_.c_void_p(host.data_ptr()), C_.c_void_p(ptr), C_.c_size_t(n * H * 16 * 8), 2)
-d = host.numpy().reshape(-1, 2, 8)
-names = ["wait_s", "ld_s+free", "max(+token)", "exp", "wait_o(+resc)", "st_p+arrive"]
+cudart.cudaMemcpy(C_.c_void_p(host.data_ptr()), C_.c_void_p(ptr), C_.c_size_t(n * 32 * 8), 2)
+d = host.numpy().reshape(-1, 2, 16)
+names = ["wait_s", "ld_s+free", "max(+token)", "exp", "wait_o(+resc)", "st_p+arrive", "unit epilogue (total)"]
 for t in (0, 1):
     x = d[:, t, :]
     x = x[x[:, 7] > 0]
     tiles = x[:, 7].sum()
-    print(f"tile {'AB'[t]}: CTAs {len(x)}, tiles {tiles}, cycles/tile total {x[:, 6].sum() / tiles:.0f}")
+    print(f"tile {'AB'[t]}: CTAs {len(x)}, steps {tiles}, cycles/step total {x[:, 8].sum() / tiles:.0f}")
     for i, nme in enumerate(names):
-        print(f"   {nme:16s} {x[:, i].sum() / tiles:8.0f} clk/tile")
-
-
+        print(f"   {nme:24s} {x[:, i].sum() / tiles:8.1f} clk/step")

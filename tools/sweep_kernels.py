@@ -38,10 +38,10 @@ def attn_point(img_lens, ctx, H):
         ob = torch.empty(Tb, C, device=dev, dtype=torch.bfloat16)
     for i, s in enumerate(img_lens):
         seqs.append((ra, s, i * ctx, ctx, ra, s, i * ctx, ctx) if ctx else (ra, s, 0, 0, ra, s, 0, 0)); ra += s
-    table, work, n = ops.build_attn_plan(seqs, dev)
+    plan = ops.build_attn_plan(seqs, dev, H)
     sa = ops.attn_source(q=qa, k=qa, k_col=C, v=qa, v_col=2 * C, out=oa)
     sb = ops.attn_source(q=qb, k=qb, k_col=C, v=qb, v_col=2 * C, out=ob) if ctx else None
-    ms = timeit(lambda: ops.attn_varlen(sa, sb, table, work, n, H, 0.125))
+    ms = timeit(lambda: ops.attn_varlen(sa, sb, *plan, 0.125))
     fl = sum(4.0 * (x + ctx) ** 2 * 64 * H for x in img_lens)
     return ms, fl / ms / 1e9
 
