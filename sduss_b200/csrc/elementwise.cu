@@ -50,61 +50,76 @@ struct LnArgs {
 };
 
 constexpr int LN_MAXIT = 8;   // 8 iterations * 32 lanes * 8 elements = 2048 columns
-constexpr int LN_ROWS = 2;    // consecutive rows per warp; a block (8 warps) covers 16 rows
 constexpr int LN_MAXD = LN_MAXIT * 256;
+constexpr int LN_WARPS = 8;
 
-// NIT = ceil(D / 256) 16-byte chunks per lane. The per-column parameters (gamma/beta or the
-// per-request shift/scale vectors, up to 4x the bytes of a row) are staged ONCE per block in
-// shared memory for the request of the block's first row; rows of another request (only at
-// request boundaries) read them from global memory. Reading them per row through L1/L2 bounded
-// the first version at ~45% of the HBM roofline.
+// NIT = ceil(D / 256) 16-byte chunks per lane. A block owns a contiguous range of rows; its 8
+// warps take them round robin and keep the next TWO rows' vectors in flight (raw bf16, 4 registers
+// per chunk) while they reduce and write the current one (~100 KB of loads outstanding per SM); the first row is requested before the parameters are staged. The grid is sized
+// to one resident wave (the first version ran 16 rows per block, 3 waves of a load -> reduce ->
+// reduce -> store chain with 128 registers: 1.9 TB/s, profiles/r01_ncu_gemm_ln_sd3.txt).
+// The per-column parameters (gamma/beta or the per-request shift/scale vectors, up to 4x the
+// bytes of a row) are staged ONCE per block in shared memory for the request of the block's first
+// row; rows of another request (only at request boundaries) read them from global memory.
+// The arithmetic order per row is fixed (lane-local sums in column order, then a shuffle tree), so
+// a row's result does not depend on the batch around it.
 template <int NIT>
-__global__ void __launch_bounds__(256) ln_mod_kernel(LnArgs a) {
+__global__ void __launch_bounds__(256, (NIT <= 4 ? 3 : 2)) ln_mod_kernel(LnArgs a, int rows_per_block) {
   __shared__ uint4 sp[4][LN_MAXD / 8];  // [scale|gamma, shift|beta, scale2, shift2][chunk]
-  pdl_launch_dependents();
-  pdl_wait();
   const int wib = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nchunk = a.D >> 3;
   const bool affine = a.gamma != nullptr;
   const bool modulated = a.mod != nullptr;
   const bool dual = a.y2 != nullptr;
-  const int block_row0 = blockIdx.x * (8 * LN_ROWS);
-  const int g0 = (modulated && a.row_group) ? a.row_group[block_row0] : 0;
-  {
-    const __nv_bfloat16* mrow = modulated ? a.mod + size_t(g0) * a.ldm : nullptr;
+  const int block_row0 = blockIdx.x * rows_per_block;
+  const int block_end = min(block_row0 + rows_per_block, a.T);
+  if (affine) {  // weights: not written by the preceding kernel
     for (int c = threadIdx.x; c < nchunk; c += 256) {
-      if (affine) {
-        sp[0][c] = *reinterpret_cast<const uint4*>(a.gamma + c * 8);
-        sp[1][c] = *reinterpret_cast<const uint4*>(a.beta + c * 8);
-      }
-      if (modulated) {
-        sp[affine ? 2 : 0][c] = *reinterpret_cast<const uint4*>(mrow + a.scale_col + c * 8);
-        sp[affine ? 3 : 1][c] = *reinterpret_cast<const uint4*>(mrow + a.shift_col + c * 8);
-        if (dual) {
-          sp[2][c] = *reinterpret_cast<const uint4*>(mrow + a.scale2_col + c * 8);
-          sp[3][c] = *reinterpret_cast<const uint4*>(mrow + a.shift2_col + c * 8);
-        }
+      sp[0][c] = *reinterpret_cast<const uint4*>(a.gamma + c * 8);
+      sp[1][c] = *reinterpret_cast<const uint4*>(a.beta + c * 8);
+    }
+  }
+  pdl_launch_dependents();
+  pdl_wait();
+  int row = block_row0 + wib;
+  uint4 cur[NIT], nx1[NIT];  // rows row and row + 8; row + 16 is requested inside the loop
+  auto load_row = [&](uint4* dst, int r) {
+    if (r < block_end) {
+      const __nv_bfloat16* xr = a.x + size_t(r) * a.ldx;
+#pragma unroll
+      for (int i = 0; i < NIT; ++i)
+        if (lane + 32 * i < nchunk) dst[i] = *reinterpret_cast<const uint4*>(xr + (lane + 32 * i) * 8);
+    }
+  };
+  load_row(cur, row);
+  load_row(nx1, row + LN_WARPS);
+  const int g0 = (modulated && a.row_group) ? a.row_group[block_row0] : 0;
+  if (modulated) {
+    const __nv_bfloat16* mrow = a.mod + size_t(g0) * a.ldm;
+    for (int c = threadIdx.x; c < nchunk; c += 256) {
+      sp[affine ? 2 : 0][c] = *reinterpret_cast<const uint4*>(mrow + a.scale_col + c * 8);
+      sp[affine ? 3 : 1][c] = *reinterpret_cast<const uint4*>(mrow + a.shift_col + c * 8);
+      if (dual) {
+        sp[2][c] = *reinterpret_cast<const uint4*>(mrow + a.scale2_col + c * 8);
+        sp[3][c] = *reinterpret_cast<const uint4*>(mrow + a.shift2_col + c * 8);
       }
     }
   }
   __syncthreads();
-  const int row0 = block_row0 + wib * LN_ROWS;
   const float inv_d = 1.f / float(a.D);
-  const int row_end = min(row0 + LN_ROWS, a.T);
   const int ms = affine ? 2 : 0;  // smem slot of scale (modulation) -- affine+dual is rejected by the host
-#pragma unroll
-  for (int row = row0; row < row_end; ++row) {
-    const __nv_bfloat16* xr = a.x + size_t(row) * a.ldx;
-    float v[NIT][8];
+  for (; row < block_end; row += LN_WARPS) {
+    uint4 nx2[NIT];
+    load_row(nx2, row + 2 * LN_WARPS);
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NIT; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nchunk) {
-        unpack8(*reinterpret_cast<const uint4*>(xr + c * 8), v[i]);
+      if (lane + 32 * i < nchunk) {
+        float v[8];
+        unpack8(cur[i], v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s += v[i][j];
+        for (int j = 0; j < 8; ++j) s += v[j];
       }
     }
     const int g = (modulated && a.row_group) ? a.row_group[row] : 0;
@@ -114,11 +129,12 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(LnArgs a) {
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < NIT; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nchunk) {
+      if (lane + 32 * i < nchunk) {
+        float v[8];
+        unpack8(cur[i], v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float d = v[i][j] - mean;
+          const float d = v[j] - mean;
           q += d * d;
         }
       }
@@ -128,9 +144,10 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(LnArgs a) {
     for (int i = 0; i < NIT; ++i) {
       const int c = lane + 32 * i;
       if (c < nchunk) {
-        float n[8], o[8];
+        float v[8], n[8], o[8];
+        unpack8(cur[i], v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) n[j] = (v[i][j] - mean) * rstd;
+        for (int j = 0; j < 8; ++j) n[j] = (v[j] - mean) * rstd;
         if (affine) {
           float gg[8], bb[8];
           unpack8(sp[0][c], gg);
@@ -159,14 +176,22 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(LnArgs a) {
         }
       }
     }
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      cur[i] = nx1[i];
+      nx1[i] = nx2[i];
+    }
   }
 }
 
 template <int NIT>
 static int launch_ln(const LnArgs& a, cudaStream_t st) {
-  const int rows_per_block = 8 * LN_ROWS;
-  return launch_pdl(ln_mod_kernel<NIT>, dim3((a.T + rows_per_block - 1) / rows_per_block), dim3(256), 0,
-                    st, a);
+  // one resident wave (3 or 2 blocks per SM, see __launch_bounds__); at least one row per warp
+  const int max_blocks = (NIT <= 4 ? 3 : 2) * device_sm_count();
+  int rows_per_block = (a.T + max_blocks - 1) / max_blocks;
+  rows_per_block = ((rows_per_block + LN_WARPS - 1) / LN_WARPS) * LN_WARPS;
+  return launch_pdl(ln_mod_kernel<NIT>, dim3((a.T + rows_per_block - 1) / rows_per_block),
+                    dim3(256), 0, st, a, rows_per_block);
 }
 
 // ------------------------------------------------------------------ small elementwise

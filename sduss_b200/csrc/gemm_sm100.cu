@@ -21,14 +21,15 @@ template <int BN, int EPI>
 struct GemmCfg {
   // residual epilogues need two extra 16 KB staging tiles -> one pipeline stage less
   static constexpr bool kResid = EPI == EPI_GATE_RESID;
-  static constexpr int kStages = (BN == 256) ? (kResid ? 3 : 4) : (kResid ? 4 : 5);
+  // 128 x 192 tiles (40 KB stages) keep 4 stages even with the residual staging tiles: 230,656 B
+  static constexpr int kStages = (BN == 256) ? (kResid ? 3 : 4) : (BN == 192) ? 4 : (kResid ? 4 : 5);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // + 2 output staging tiles + 2 residual staging tiles (16 KB each) for the TMA epilogue
   static constexpr int kSmemBytes =
       kStages * kStageBytes + (kResid ? 4 : 2) * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (256 or 512)
+  static constexpr int kTmemCols = BN == 128 ? 256 : 512;  // two accumulator stages (power of two)
 };
 
 struct GemmShape {
@@ -321,8 +322,17 @@ extern "C" int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
 
   // 128 x 256 or 128 x 128 tiles: whichever the operand-traffic / occupancy model predicts faster
   static const bool mc_allowed0 = []() { const char* v = getenv("SDUSS_B200_NO_MULTICAST"); return !(v && v[0] == '1'); }();
-  const int BN = choose_tile_n((M + BM - 1) / BM, N, (K + BK - 1) / BK, sms, mc_allowed0 && M > BM);
-  const bool bn256 = BN == 256;
+  int BN = choose_tile_n((M + BM - 1) / BM, N, (K + BK - 1) / BK, sms, mc_allowed0 && M > BM);
+  // One-round problems that leave a quarter of the SMs idle with 256-wide tiles (SDXL level 2:
+  // M = 2560, N = 1280 -> 100 tiles) run as 128 x 192 tiles when those still fit one round (140
+  // tiles): every CTA then streams 25 % fewer operand bytes through its smem window, which is
+  // what bounds a single-tile CTA (load latency x bytes / window, not the tensor pipe).
+  {
+    static const bool no192 = []() { const char* v = getenv("SDUSS_B200_NO_BN192"); return v && v[0] == '1'; }();
+    const long mt = (M + BM - 1) / BM;
+    const long t256 = mt * ((N + 255) / 256), t192 = mt * ((N + 191) / 192);
+    if (!no192 && BN == 256 && t256 * 4 <= 3L * sms && t192 <= sms && t192 > t256) BN = 192;
+  }
 
   // pair CTAs (W-tile multicast) whenever there are at least two M tiles and enough pairs of
   // tiles to occupy the 74 SM pairs
@@ -375,6 +385,7 @@ extern "C" int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
       if (rc) return rc;
     }
   }
-  return bn256 ? dispatch_epi<256>(epi_mode, tmA, tmB, tmC, tmR, s, e, sms, stream, multicast)
-               : dispatch_epi<128>(epi_mode, tmA, tmB, tmC, tmR, s, e, sms, stream, multicast);
+  if (BN == 256) return dispatch_epi<256>(epi_mode, tmA, tmB, tmC, tmR, s, e, sms, stream, multicast);
+  if (BN == 192) return dispatch_epi<192>(epi_mode, tmA, tmB, tmC, tmR, s, e, sms, stream, multicast);
+  return dispatch_epi<128>(epi_mode, tmA, tmB, tmC, tmR, s, e, sms, stream, multicast);
 }

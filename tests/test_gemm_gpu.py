@@ -129,3 +129,23 @@ def test_gemm_rejects_bad_args(cuda):
     a, w = _rand((64, 36), cuda), _rand((64, 36), cuda)
     with pytest.raises(B200Error):
         ops.gemm(a, w)
+
+
+@pytest.mark.parametrize("M,N,K", [(2560, 1280, 1280), (2560, 1280, 5120), (1998, 1536, 1536), (2560, 1208, 320)])
+def test_gemm_one_round_shapes_use_192_wide_tiles(cuda, M, N, K):
+    """Problems whose 128 x 256 tiling leaves >= 1/4 of the SMs idle run as 128 x 192 tiles (SDXL
+    level 2, SD3 context rows): bias, in-place residual (TMA-staged residual tiles), N tails that
+    end inside a 64-column chunk, determinism."""
+    from sduss_b200 import ops
+    a, w, b = _rand((M, K), cuda, seed=1), _rand((N, K), cuda, 0.03, seed=2), _rand((N,), cuda, seed=3)
+    ref = a.float() @ w.float().t() + b.float()
+    outs = [ops.gemm(a, w, bias=b) for _ in range(3)]
+    for o in outs:
+        _close(o, ref)
+        assert torch.equal(o, outs[0])
+    resid = _rand((M, N), cuda, seed=6)
+    x = resid.clone()
+    ops.gemm(a, w, out=x, bias=b, epi=ops.EPI_GATE_RESID, resid=x)
+    _close(x, ref + resid.float())
+    out = ops.gemm(a, w, bias=b, epi=ops.EPI_GELU_TANH)
+    _close(out, torch.nn.functional.gelu(ref, approximate="tanh"))

@@ -98,6 +98,32 @@ def test_groupnorm(cuda, sizes, C, silu, eps):
     assert torch.equal(y, y2)  # deterministic (no atomics)
 
 
+@pytest.mark.parametrize("C", [320, 1280])
+def test_groupnorm_batch_invariant(cuda, C):
+    """A latent's GroupNorm output must not depend on the latents packed around it (the launch
+    geometry changes with the total row count; the summation order may not)."""
+    from sduss_b200 import ops
+    from sduss_b200.layout import LevelLayout
+    sizes = [(16, 16), (64, 64), (128, 128), (32, 32)]
+    lats = [(_rand((C, h, w), 40 + i) * (1 + i)).bfloat16().float() for i, (h, w) in enumerate(sizes)]
+    gam, bet = (1 + 0.1 * _rand((C,), 5)).cuda().bfloat16(), _rand((C,), 6).cuda().bfloat16()
+
+    def run(idx):
+        lay = LevelLayout([sizes[i] for i in idx], cuda)
+        x = _pack([lats[i] for i in idx]).cuda().bfloat16().contiguous()
+        y = torch.empty_like(x)
+        ws = ops.groupnorm_workspace(lay.T, lay.L, cuda)
+        ops.groupnorm_nhwc(x, y, gam, bet, lay.row_group, lay.lat_chunks, lay.L, ws, silu=True)
+        torch.cuda.synchronize()
+        return y, lay
+    mixed, lay = run(range(len(sizes)))
+    off = 0
+    for i, (h, w) in enumerate(sizes):
+        solo, _ = run([i])
+        assert torch.equal(mixed[off:off + h * w], solo), i
+        off += h * w
+
+
 def test_pack_scatter_upsample_copy(cuda):
     from sduss_b200 import ops
     from sduss_b200.layout import LevelLayout

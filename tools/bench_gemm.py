@@ -5,19 +5,22 @@ import torch
 from sduss_b200 import ops
 
 def timeit(fn, n=20):
+    """GPU time per call, replayed from a CUDA graph (host launch cost exceeds the small shapes)."""
     for _ in range(3): fn()
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n): fn()
+    g.replay(); torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(n): fn()
-    e.record(); torch.cuda.synchronize()
+    s.record(); g.replay(); e.record(); torch.cuda.synchronize()
     return s.elapsed_time(e) / n
 
 dev = torch.device("cuda")
 for (M, N, K) in [(14848, 4608, 1536), (14848, 1536, 1536), (14848, 6144, 1536), (14848, 1536, 6144),
                   (1998, 4608, 1536), (40960, 320, 2880), (8192, 8192, 8192),
                   # SDXL level-2 / level-1 token GEMMs (config-1: 2560 / 10240 rows)
-                  (2560, 1280, 1280), (2560, 1280, 5120), (2560, 3840, 1280), (2560, 10240, 1280),
+                  (2560, 1280, 1280), (2560, 1280, 5120), (1998, 1536, 1536), (1998, 1536, 6144), (2560, 3840, 1280), (2560, 10240, 1280),
                   (10240, 640, 640), (10240, 640, 2560), (10240, 1920, 640)]:
     a = torch.randn(M, K, device=dev).bfloat16(); w = (torch.randn(N, K, device=dev) * .05).bfloat16()
     out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
