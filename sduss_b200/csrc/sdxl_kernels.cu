@@ -30,64 +30,110 @@ __device__ __forceinline__ uint4 pack8s(const float* f) {
 // Exact per-request statistics over the WHOLE latent (the reference approximates the variance by
 // the mean of per-patch variances and races while doing so: kernels/norm_silu_concat.cu:361-386,
 // deviations D1 and the in-place race). Three launches:
-//   stats   : one CTA per 64-pixel chunk -> partial (sum, sumsq) per group      [chunks][G][2]
-//   finalize: one thread per (latent, group): fixed-order fp64 reduction         [L][G][2]
-//   apply   : y = (x - mean) * rstd * gamma + beta, optional SiLU, bf16
-constexpr int GN_CHUNK = 64;
+//   stats   : CTA (chunk, slice) -> partial (sum, sumsq) per group of the slice    [G][T/64][2]
+//   finalize: one warp per (latent, group): fixed-order fp64 reduction              [L][G][2]
+//   apply   : y = x * a + b per channel (a, b folded from mean, rstd, gamma, beta once per
+//             thread), optional SiLU, bf16
+// The two streaming kernels share one geometry: a CTA owns a 64-row chunk of ONE latent and a
+// slice of whole groups (S slices, S a function of C only), every thread owns ONE 16-byte channel
+// vector and the rows rl, rl + RL, ... of the chunk, so per-channel state lives in registers and a
+// thread's loads are independent (4 in flight, 4-5 CTAs per SM). The summation order is a function
+// of (C, row index inside the latent) only - never of the launch geometry - so a latent's output
+// does not depend on what is packed around it (batch invariance); no atomics (determinism).
+constexpr int GN_CHUNK = 64;   // rows per CTA == host-side unit of the latent tables (layout.py)
 constexpr int GN_MAXG = 32;
-
 constexpr int GN_MAXC = 2560;
+constexpr int GN_THREADS = 256;
 
-// Deterministic: every channel's column sum over the 64 rows is owned by one lane (fixed order),
-// then one thread per group adds its channels in index order. No atomics anywhere.
-__global__ void __launch_bounds__(256) gn_stats_kernel(const __nv_bfloat16* x, int ldx, int C,
-                                                       int cpg, int G, float* partial) {
-  __shared__ float ch_sum[GN_MAXC], ch_sq[GN_MAXC];
+struct GnMap {
+  int S;        // channel slices (grid.y); a slice holds G / S whole groups
+  int W;        // 16-byte vector columns per slice
+  int RL;       // row lanes: threads sharing one column
+  int threads;  // RL * W
+};
+inline GnMap gn_map(int C, int G) {
+  const int nvec = C >> 3, cpg = C / G;
+  GnMap m;
+  m.S = 1;
+  for (int s = 8; s > 1; s >>= 1)
+    if (G % s == 0 && ((G / s) * cpg) % 8 == 0 && nvec / s >= 32) {
+      m.S = s;
+      break;
+    }
+  m.W = nvec / m.S;
+  m.RL = m.W <= GN_THREADS ? GN_THREADS / m.W : 0;
+  if (m.RL > GN_CHUNK) m.RL = GN_CHUNK;
+  m.threads = m.RL * m.W;
+  return m;
+}
+
+__global__ void __launch_bounds__(GN_THREADS, 5) gn_stats_kernel(const __nv_bfloat16* x, int ldx,
+                                                                 int W, int RL, int cpg,
+                                                                 int gps, int n_chunks,
+                                                                 float* partial) {
+  __shared__ float ch_sum[GN_THREADS * 8], ch_sq[GN_THREADS * 8];  // [RL][W * 8]
   pdl_launch_dependents();
-  pdl_wait();
-  const int chunk = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nvec = C >> 3;
-  const __nv_bfloat16* base = x + size_t(chunk) * GN_CHUNK * ldx;
-  for (int slot = warp; slot * 32 < nvec; slot += 8) {
-    const int vc = slot * 32 + lane;
-    if (vc < nvec) {
-      float sum[8], sq[8];
+  const int chunk = blockIdx.x, slice = blockIdx.y;
+  const int rl = threadIdx.x / W, col = threadIdx.x - rl * W;
+  const int CW = W * 8;  // channels of the slice
+  const __nv_bfloat16* base = x + size_t(chunk) * GN_CHUNK * ldx + size_t(slice) * CW + col * 8;
+  float sum[8], sq[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
-#pragma unroll 4
-      for (int r = 0; r < GN_CHUNK; ++r) {
+  for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
+  pdl_wait();
+  for (int r0 = rl; r0 < GN_CHUNK; r0 += 4 * RL) {  // fixed order: rows rl, rl + RL, ...
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = r0 + k * RL;
+      if (r < GN_CHUNK) v[k] = *reinterpret_cast<const uint4*>(base + size_t(r) * ldx);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (r0 + k * RL < GN_CHUNK) {
         float f[8];
-        unpack8s(*reinterpret_cast<const uint4*>(base + size_t(r) * ldx + vc * 8), f);
+        unpack8s(v[k], f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           sum[j] += f[j];
-          sq[j] += f[j] * f[j];
+          sq[j] = fmaf(f[j], f[j], sq[j]);
         }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        ch_sum[vc * 8 + j] = sum[j];
-        ch_sq[vc * 8 + j] = sq[j];
       }
     }
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ch_sum[rl * CW + col * 8 + j] = sum[j];
+    ch_sq[rl * CW + col * 8 + j] = sq[j];
+  }
   __syncthreads();
-  if (threadIdx.x < G) {
+  if (RL > 1) {
+    for (int c = threadIdx.x; c < CW; c += blockDim.x) {
+      float s = ch_sum[c], q = ch_sq[c];
+      for (int l = 1; l < RL; ++l) {
+        s += ch_sum[l * CW + c];
+        q += ch_sq[l * CW + c];
+      }
+      ch_sum[c] = s;
+      ch_sq[c] = q;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < gps) {
     float s = 0.f, q = 0.f;
     for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
       s += ch_sum[c];
       q += ch_sq[c];
     }
-    partial[(size_t(chunk) * GN_MAXG + threadIdx.x) * 2] = s;
-    partial[(size_t(chunk) * GN_MAXG + threadIdx.x) * 2 + 1] = q;
+    const int g = slice * gps + threadIdx.x;
+    *reinterpret_cast<float2*>(partial + (size_t(g) * n_chunks + chunk) * 2) = make_float2(s, q);
   }
 }
 
-// lat: [L][4] = {first chunk, number of chunks, 0, 0}. One warp per (latent, group): lanes stride
-// the chunk list, then a fixed-order fp64 shuffle tree (deterministic).
+// lat: [L][4] = {first 64-row chunk, number of chunks, 0, 0}. One warp per (latent, group): lanes
+// stride the latent's chunks (coalesced float2 reads), then a fixed-order fp64 shuffle tree.
 __global__ void gn_finalize_kernel(const float* partial, const int4* lat, int L, int G, int cpg,
-                                   float eps, float* stats) {
+                                   int n_chunks, float eps, float* stats) {
   pdl_launch_dependents();
   pdl_wait();
   const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -95,10 +141,13 @@ __global__ void gn_finalize_kernel(const float* partial, const int4* lat, int L,
   if (idx >= L * G) return;
   const int l = idx / G, g = idx % G;
   const int4 d = lat[l];
+  const float2* p = reinterpret_cast<const float2*>(partial) + size_t(g) * n_chunks + d.x;
   double s = 0.0, q = 0.0;
+#pragma unroll 4
   for (int c = lane; c < d.y; c += 32) {
-    s += double(partial[(size_t(d.x + c) * GN_MAXG + g) * 2]);
-    q += double(partial[(size_t(d.x + c) * GN_MAXG + g) * 2 + 1]);
+    const float2 v = p[c];
+    s += double(v.x);
+    q += double(v.y);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -115,33 +164,56 @@ __global__ void gn_finalize_kernel(const float* partial, const int4* lat, int L,
   }
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* x, int ldx, long T,
-                                                       int C, int cpg, int G, const float* stats,
-                                                       const int* row_group,
-                                                       const __nv_bfloat16* gamma,
-                                                       const __nv_bfloat16* beta, int silu,
-                                                       __nv_bfloat16* y, int ldy) {
+// SiLU as h + h * tanh(h), h = v / 2: one MUFU op per element instead of ex2 + rcp (+ the Newton
+// steps of an IEEE division); tanh.approx is accurate to 2^-11, below the bf16 rounding of y.
+template <bool SILU>
+__global__ void __launch_bounds__(GN_THREADS, 4) gn_apply_kernel(
+    const __nv_bfloat16* x, int ldx, int W, int RL, int cpg, int G, const float* stats,
+    const int* row_group, const __nv_bfloat16* gamma, const __nv_bfloat16* beta, __nv_bfloat16* y,
+    int ldy) {
   pdl_launch_dependents();
+  const int rl = threadIdx.x / W, col = threadIdx.x - rl * W;
+  const int ch0 = (blockIdx.y * W + col) * 8;  // first channel of this thread's vector
+  const size_t row0 = size_t(blockIdx.x) * GN_CHUNK;
+  const __nv_bfloat16* xb = x + row0 * ldx + ch0;
+  __nv_bfloat16* yb = y + row0 * ldy + ch0;
+  float a[8], b[8];
+  unpack8s(*reinterpret_cast<const uint4*>(gamma + ch0), a);  // parameters: not written by the
+  unpack8s(*reinterpret_cast<const uint4*>(beta + ch0), b);   // preceding kernels
   pdl_wait();
-  const int nvec = C >> 3;
-  const long i = blockIdx.x * long(blockDim.x) + threadIdx.x;
-  if (i >= T * nvec) return;
-  const long row = i / nvec;
-  const int vc = int(i - row * nvec);
-  const float* st = stats + size_t(row_group[row]) * G * 2;
-  float f[8], ga[8], be[8];
-  unpack8s(*reinterpret_cast<const uint4*>(x + row * ldx + vc * 8), f);
-  unpack8s(*reinterpret_cast<const uint4*>(gamma + vc * 8), ga);
-  unpack8s(*reinterpret_cast<const uint4*>(beta + vc * 8), be);
+  const float* st = stats + size_t(row_group[row0]) * G * 2;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int g = (vc * 8 + j) / cpg;
-    const float mean = st[g * 2], rstd = st[g * 2 + 1];
-    float v = (f[j] - mean) * rstd * ga[j] + be[j];
-    if (silu) v = v / (1.f + __expf(-v));
-    f[j] = v;
+    const float2 mr = *reinterpret_cast<const float2*>(st + ((ch0 + j) / cpg) * 2);
+    a[j] *= mr.y;
+    b[j] = fmaf(-mr.x, a[j], b[j]);
+    if (SILU) {
+      a[j] *= 0.5f;
+      b[j] *= 0.5f;
+    }
   }
-  *reinterpret_cast<uint4*>(y + row * ldy + vc * 8) = pack8s(f);
+  for (int r0 = rl; r0 < GN_CHUNK; r0 += 4 * RL) {
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = r0 + k * RL;
+      if (r < GN_CHUNK) v[k] = *reinterpret_cast<const uint4*>(xb + size_t(r) * ldx);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = r0 + k * RL;
+      if (r < GN_CHUNK) {
+        float f[8];
+        unpack8s(v[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float h = fmaf(f[j], a[j], b[j]);
+          f[j] = SILU ? fmaf(h, tanh_approx(h), h) : h;
+        }
+        *reinterpret_cast<uint4*>(yb + size_t(r) * ldy) = pack8s(f);
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------ latent pack for conv_in
@@ -267,20 +339,23 @@ extern "C" int b200_groupnorm_nhwc_bf16(const void* x, int ldx, long long T, int
     return B200_ERR_INVALID;
   const int cpg = C / groups;
   const int chunks = int(T / GN_CHUNK);
+  const GnMap m = gn_map(C, groups);
+  if (m.RL < 1) return B200_ERR_INVALID;
   float* partial = static_cast<float*>(workspace);
   float* stats = partial + size_t(chunks) * GN_MAXG * 2;
-  int rc = launch_pdl(gn_stats_kernel, dim3(chunks), dim3(256), 0, ST(stream),
-                      static_cast<const bf16*>(x), ldx, C, cpg, groups, partial);
+  int rc = launch_pdl(gn_stats_kernel, dim3(chunks, m.S), dim3(m.threads), 0, ST(stream),
+                      static_cast<const bf16*>(x), ldx, m.W, m.RL, cpg, groups / m.S, chunks,
+                      partial);
   if (rc) return rc;
   rc = launch_pdl(gn_finalize_kernel, dim3((n_latents * groups + 3) / 4), dim3(128), 0, ST(stream),
                   static_cast<const float*>(partial), reinterpret_cast<const int4*>(lat_chunks),
-                  n_latents, groups, cpg, eps, stats);
+                  n_latents, groups, cpg, chunks, eps, stats);
   if (rc) return rc;
-  const long total = T * (C >> 3);
-  return launch_pdl(gn_apply_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, ST(stream),
-                    static_cast<const bf16*>(x), ldx, long(T), C, cpg, groups,
+  auto kern = silu ? gn_apply_kernel<true> : gn_apply_kernel<false>;
+  return launch_pdl(kern, dim3(chunks, m.S), dim3(m.threads), 0, ST(stream),
+                    static_cast<const bf16*>(x), ldx, m.W, m.RL, cpg, groups,
                     static_cast<const float*>(stats), row_group, static_cast<const bf16*>(gamma),
-                    static_cast<const bf16*>(beta), silu, static_cast<bf16*>(y), ldy);
+                    static_cast<const bf16*>(beta), static_cast<bf16*>(y), ldy);
 }
 
 extern "C" int b200_pack_im2col3x3(const uint64_t* lat_ptr, const int32_t* desc, int n_latents,

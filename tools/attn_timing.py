@@ -26,7 +26,8 @@ import ctypes as C_
 cudart = C_.CDLL("/usr/local/cuda/lib64/libcudart.so.12")
 cudart.cudaMemcpy(C_.c_void_p(host.data_ptr()), C_.c_void_p(ptr), C_.c_size_t(n * 32 * 8), 2)
 d = host.numpy().reshape(-1, 2, 16)
-names = ["wait_s", "ld_s+free", "max(+token)", "exp", "wait_o(+resc)", "st_p+arrive", "unit epilogue (total)"]
+names = (["wait_s", "ref update / first max", "exp row (2 halves)", "st_p+arrive", "-", "-", "unit epilogue (total)"] if ops.ATTN_Q_TILE == 512 else
+         ["wait_s", "ld_s+free", "max(+token)", "exp", "wait_o(+resc)", "st_p+arrive", "unit epilogue (total)"])
 for t in (0, 1):
     x = d[:, t, :]
     x = x[x[:, 7] > 0]
