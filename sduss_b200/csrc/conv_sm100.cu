@@ -21,13 +21,14 @@ constexpr int CV_BM = 128, CV_BK = 64, CV_TW = 8, CV_TH = 16, CV_THREADS = 256;
 
 template <int BN, int EPI>
 struct ConvCfg {
-  static constexpr bool kResid = EPI == EPI_GATE_RESID;
-  static constexpr int kStages = (BN == 256) ? (kResid ? 3 : 4) : (kResid ? 4 : 5);
+  // residual chunks are TMA-loaded into the output staging tiles and updated in place (see
+  // gemm_sm100.cu): the residual epilogue costs no pipeline stage
+  static constexpr int kStages = (BN == 256) ? 4 : 5;
   static constexpr int kABytes = CV_BM * CV_BK * 2;
   static constexpr int kBBytes = BN * CV_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSmemBytes =
-      kStages * kStageBytes + (kResid ? 4 : 2) * EPI_STAGE_BYTES + 1024 + 256;
+      kStages * kStageBytes + 2 * EPI_STAGE_BYTES + 1024 + 256;
   static constexpr int kTmemCols = 2 * BN;
 };
 
@@ -50,8 +51,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + Cfg::kStages * Cfg::kABytes;
   uint8_t* stageC = smem + Cfg::kStages * Cfg::kStageBytes;
-  uint8_t* stageR = stageC + 2 * EPI_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stageR + (Cfg::kResid ? 2 : 0) * EPI_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stageC + 2 * EPI_STAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::kStages;
   uint64_t* tfull = bars + 2 * Cfg::kStages;
@@ -166,16 +166,18 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
       const int4 tl = a.tiles[t / tiles_n];
       const int4 ld = a.lat[tl.x];
       const int n0 = (t % tiles_n) * BN;
-      if (has_resid && leader) {
+      if (has_resid && leader) {  // residual chunks 0 and 1 fly while the main loop finishes
+        tma_store_wait_read<0>();   // both staging tiles have left for HBM (previous tile)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           if (c < NCH && n0 + c * 64 < a.Cout) {
             const int rb = (chunk_ctr + c) & 1;
             mbar_expect_tx(&rfull[rb], EPI_STAGE_BYTES);
-            tma_load_3d(stageR + rb * EPI_STAGE_BYTES, a.res_maps + tl.x, &rfull[rb], n0 + c * 64, tl.z, tl.y);
+            tma_load_3d(stageC + rb * EPI_STAGE_BYTES, a.res_maps + tl.x, &rfull[rb], n0 + c * 64, tl.z, tl.y);
           }
         }
       }
+      __syncwarp();
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
       const int y = tl.y + r / CV_TW, x = tl.z + r % CV_TW;
@@ -187,6 +189,16 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
         const int nc = n0 + c * 64;
         if (nc >= a.Cout) break;
         const int b = (chunk_ctr + c) & 1;
+        if (has_resid && c >= 1 && c + 1 < NCH && nc + 64 < a.Cout) {
+          // residual of chunk c + 1 -> the tile chunk c - 1 was stored from, once that store has
+          // read it; it lands while this chunk is processed
+          if (leader) {
+            tma_store_wait_read<0>();
+            mbar_expect_tx(&rfull[b ^ 1], EPI_STAGE_BYTES);
+            tma_load_3d(stageC + (b ^ 1) * EPI_STAGE_BYTES, a.res_maps + tl.x, &rfull[b ^ 1], nc + 64, tl.z, tl.y);
+          }
+          __syncwarp();
+        }
         float v[64];
         tmem_ld32(t_row + c * 64, reinterpret_cast<uint32_t*>(v));
         tmem_ld32(t_row + c * 64 + 32, reinterpret_cast<uint32_t*>(v) + 32);
@@ -195,7 +207,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
           mbar_wait(&rfull[b], (b ? ruse1 : ruse0) & 1);
           if (b) ++ruse1; else ++ruse0;
         }
-        epilogue_math64<EPI>(e, v, row, row_ok, nc, a.Cout, has_resid ? stageR + b * EPI_STAGE_BYTES : nullptr, r);
+        epilogue_math64<EPI>(e, v, row, row_ok, nc, a.Cout, has_resid ? stageC + b * EPI_STAGE_BYTES : nullptr, r);
         epilogue_stage64<EPI>(stageC + b * EPI_STAGE_BYTES, v, r);
         fence_proxy_async();
         if (leader) tma_store_wait_read<0>();
@@ -203,10 +215,6 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
         if (leader) {
           tma_store_3d(a.out_maps + tl.x, stageC + b * EPI_STAGE_BYTES, nc, tl.z, tl.y);
           tma_store_commit();
-          if (has_resid && c + 2 < NCH && nc + 128 < a.Cout) {
-            mbar_expect_tx(&rfull[b], EPI_STAGE_BYTES);
-            tma_load_3d(stageR + b * EPI_STAGE_BYTES, a.res_maps + tl.x, &rfull[b], nc + 128, tl.z, tl.y);
-          }
         }
       }
       {

@@ -19,16 +19,16 @@ constexpr int GEMM_THREADS = 256;
 
 template <int BN, int EPI>
 struct GemmCfg {
-  // residual epilogues need two extra 16 KB staging tiles -> one pipeline stage less
-  static constexpr bool kResid = EPI == EPI_GATE_RESID;
-  // 128 x 192 tiles (40 KB stages) keep 4 stages even with the residual staging tiles: 230,656 B
-  static constexpr int kStages = (BN == 256) ? (kResid ? 3 : 4) : (BN == 192) ? 4 : (kResid ? 4 : 5);
+  // The residual chunk of a gate*y + residual epilogue is TMA-loaded INTO the output staging tile
+  // and updated in place, so that epilogue costs no pipeline stage (a 3-stage 128 x 256 main loop
+  // lost 27 % on the K = 1536 out-projections: operand latency, not the tensor pipe).
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192) ? 4 : 5;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // + 2 output staging tiles + 2 residual staging tiles (16 KB each) for the TMA epilogue
+  // + 2 staging tiles (16 KB each) for the TMA epilogue
   static constexpr int kSmemBytes =
-      kStages * kStageBytes + (kResid ? 4 : 2) * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+      kStages * kStageBytes + 2 * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = BN == 128 ? 256 : 512;  // two accumulator stages (power of two)
 };
 
@@ -50,9 +50,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                              ~uintptr_t(1023));
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + Cfg::kStages * Cfg::kABytes;
-  uint8_t* stageC = smem + Cfg::kStages * Cfg::kStageBytes;  // [2][16 KB] output chunks
-  uint8_t* stageR = stageC + 2 * EPI_STAGE_BYTES;            // [2][16 KB] residual chunks (kResid)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stageR + (Cfg::kResid ? 2 : 0) * EPI_STAGE_BYTES);
+  uint8_t* stageC = smem + Cfg::kStages * Cfg::kStageBytes;  // [2][16 KB] residual in / output out
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stageC + 2 * EPI_STAGE_BYTES);
   uint64_t* full = bars;                       // [kStages]
   uint64_t* empty = bars + Cfg::kStages;       // [kStages]
   uint64_t* tfull = bars + 2 * Cfg::kStages;   // [2]
@@ -167,7 +166,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;
     const int r = q * 32 + lane;          // row inside the tile == TMEM lane
     const bool leader = threadIdx.x == 128;
-    const bool has_resid = (EPI == EPI_GATE_RESID) && e.resid != nullptr;
+    const bool has_resid = (EPI == EPI_GATE_RESID) && e.resid != nullptr && !e.out_fp32;
     constexpr int NCH = BN / 64;
     uint32_t ruse0 = 0, ruse1 = 0;
     // Staging buffers alternate over ALL chunks this CTA stores, not per tile: a tile with an odd
@@ -185,15 +184,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int m0 = ((t / tiles_n) * MC + int(rank)) * BM;
       const int n0 = (t % tiles_n) * BN;
       if (has_resid && leader) {  // residual chunks 0 and 1 fly while the main loop finishes
+        tma_store_wait_read<0>();   // both staging tiles have left for HBM (previous tile)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           if (c < NCH && n0 + c * 64 < s.N) {
             const int rb = (chunk_ctr + c) & 1;
             mbar_expect_tx(&rfull[rb], EPI_STAGE_BYTES);
-            tma_load_2d(stageR + rb * EPI_STAGE_BYTES, &tmR, &rfull[rb], n0 + c * 64, m0);
+            tma_load_2d(stageC + rb * EPI_STAGE_BYTES, &tmR, &rfull[rb], n0 + c * 64, m0);
           }
         }
       }
+      __syncwarp();
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
       const int row = m0 + r;
@@ -203,6 +204,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int nc = n0 + c * 64;
         if (nc >= s.N) break;
         const int b = (chunk_ctr + c) & 1;
+        if (has_resid && c >= 1 && c + 1 < NCH && nc + 64 < s.N) {
+          // residual of chunk c + 1 -> the tile chunk c - 1 was stored from, once that store has
+          // read it; it lands while this chunk is processed
+          if (leader) {
+            tma_store_wait_read<0>();
+            mbar_expect_tx(&rfull[b ^ 1], EPI_STAGE_BYTES);
+            tma_load_2d(stageC + (b ^ 1) * EPI_STAGE_BYTES, &tmR, &rfull[b ^ 1], nc + 64, m0);
+          }
+          __syncwarp();
+        }
         float v[64];
         tmem_ld32(t_row + c * 64, reinterpret_cast<uint32_t*>(v));
         tmem_ld32(t_row + c * 64 + 32, reinterpret_cast<uint32_t*>(v) + 32);
@@ -215,7 +226,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&rfull[b], (b ? ruse1 : ruse0) & 1);
           if (b) ++ruse1; else ++ruse0;
         }
-        epilogue_math64<EPI>(e, v, row, row < s.M, nc, s.N, has_resid ? stageR + b * EPI_STAGE_BYTES : nullptr, r);
+        epilogue_math64<EPI>(e, v, row, row < s.M, nc, s.N, has_resid ? stageC + b * EPI_STAGE_BYTES : nullptr, r);
         epilogue_stage64<EPI>(stageC + b * EPI_STAGE_BYTES, v, r);
         fence_proxy_async();                       // smem writes -> visible to the TMA engine
         if (leader) tma_store_wait_read<0>();      // chunk c-1 has left its staging tile
@@ -223,10 +234,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (leader) {
           tma_store_2d(&tmC, stageC + b * EPI_STAGE_BYTES, EPI == EPI_GEGLU ? (nc >> 1) : nc, m0);
           tma_store_commit();
-          if (has_resid && c + 2 < NCH && nc + 128 < s.N) {  // stageR[b] was fully read before the barrier
-            mbar_expect_tx(&rfull[b], EPI_STAGE_BYTES);
-            tma_load_2d(stageR + b * EPI_STAGE_BYTES, &tmR, &rfull[b], nc + 128, m0);
-          }
         }
       }
       {
