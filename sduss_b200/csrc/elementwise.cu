@@ -3,6 +3,8 @@
 // CFG-combine + scheduler update. All are coalesced 16-byte-vector streams; row reductions use
 // warp shuffles only (one warp per token row).
 #include "../../include/sduss_b200.h"
+#include <cstdlib>
+
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -53,145 +55,238 @@ constexpr int LN_MAXIT = 8;   // 8 iterations * 32 lanes * 8 elements = 2048 col
 constexpr int LN_MAXD = LN_MAXIT * 256;
 constexpr int LN_WARPS = 8;
 
-// NIT = ceil(D / 256) 16-byte chunks per lane. A block owns a contiguous range of rows; its 8
-// warps take them round robin and keep the next TWO rows' vectors in flight (raw bf16, 4 registers
-// per chunk) while they reduce and write the current one (~100 KB of loads outstanding per SM); the first row is requested before the parameters are staged. The grid is sized
-// to one resident wave (the first version ran 16 rows per block, 3 waves of a load -> reduce ->
-// reduce -> store chain with 128 registers: 1.9 TB/s, profiles/r01_ncu_gemm_ln_sd3.txt).
-// The per-column parameters (gamma/beta or the per-request shift/scale vectors, up to 4x the
-// bytes of a row) are staged ONCE per block in shared memory for the request of the block's first
-// row; rows of another request (only at request boundaries) read them from global memory.
-// The arithmetic order per row is fixed (lane-local sums in column order, then a shuffle tree), so
-// a row's result does not depend on the batch around it.
-template <int NIT>
-__global__ void __launch_bounds__(256, (NIT <= 4 ? 3 : 2)) ln_mod_kernel(LnArgs a, int rows_per_block) {
-  __shared__ uint4 sp[4][LN_MAXD / 8];  // [scale|gamma, shift|beta, scale2, shift2][chunk]
+// NIT = ceil(D / 256) 16-byte chunks per lane (FULL: D == NIT * 256, no column predicates). A block
+// owns a contiguous range of rows (one resident wave); its 8 warps take them round robin and keep
+// the next PF rows' vectors in flight (raw bf16) while the current row is reduced and written.
+// Every output is y = n * A + B with n = (x - mean) * rstd and per-column A, B folded from
+// gamma / beta / (1 + scale) / shift ONCE per block into shared memory as fp32 (for the requests
+// of the block's first and last row; a row of a third request - only when requests are shorter
+// than a block's row range - folds them on the fly with the same arithmetic). The first version
+// of this kernel re-unpacked the row three times and converted the bf16 parameters per element:
+// 1250 warp instructions per row, issue-bound at 63 % (profiles/r01_ncu_norm_v2.txt); this one
+// unpacks once and spends ~8 instructions per element.
+// The arithmetic order per row is fixed (lane-local sums over 4 interleaved accumulators in column
+// order, then a shuffle tree), so a row's result does not depend on the batch around it.
+constexpr int LN_THREADS = 256;
+
+// A, B of output `which` (0: y, 1: y2) for the 8 columns of chunk c and request g.
+__device__ __forceinline__ void ln_fold_params(const LnArgs& a, int g, int c, int which, float* A,
+                                               float* B) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    A[j] = 1.f;
+    B[j] = 0.f;
+  }
+  if (a.gamma != nullptr) {
+    unpack8(*reinterpret_cast<const uint4*>(a.gamma + c * 8), A);
+    unpack8(*reinterpret_cast<const uint4*>(a.beta + c * 8), B);
+  }
+  if (a.mod != nullptr) {
+    const __nv_bfloat16* mrow = a.mod + size_t(g) * a.ldm;
+    float sc[8], sh[8];
+    unpack8(*reinterpret_cast<const uint4*>(mrow + (which ? a.scale2_col : a.scale_col) + c * 8), sc);
+    unpack8(*reinterpret_cast<const uint4*>(mrow + (which ? a.shift2_col : a.shift_col) + c * 8), sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float m = 1.f + sc[j];
+      B[j] = fmaf(B[j], m, sh[j]);
+      A[j] = A[j] * m;
+    }
+  }
+}
+
+// Row statistics on the unpacked row: v becomes x - mean; returns rstd. Shared by the fast and the
+// slow path so both round identically.
+template <int NIT, bool FULL>
+__device__ __forceinline__ float ln_center(float* v, int lane, int nchunk, float inv_d, float eps) {
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < NIT * 8; ++k) s4[k & 3] += v[k];
+  const float mean = warp_sum((s4[0] + s4[1]) + (s4[2] + s4[3])) * inv_d;
+  float q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < NIT; ++i) {
+    if (FULL || lane + 32 * i < nchunk) {  // padded columns must not add mean^2
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[8 * i + j] - mean;
+        v[8 * i + j] = d;
+        q4[j & 3] = fmaf(d, d, q4[j & 3]);
+      }
+    }
+  }
+  return rsqrtf(warp_sum((q4[0] + q4[1]) + (q4[2] + q4[3])) * inv_d + eps);
+}
+
+template <int NIT, bool FULL>
+__device__ __forceinline__ void ln_unpack_row(const uint4* raw, float* v, int lane, int nchunk) {
+#pragma unroll
+  for (int i = 0; i < NIT; ++i) {
+    if (FULL || lane + 32 * i < nchunk) {
+      unpack8(raw[i], v + 8 * i);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[8 * i + j] = 0.f;
+    }
+  }
+}
+
+// A row whose request is neither of the two staged ones (requests shorter than a block's row
+// range): the whole row again from global memory, parameters folded on the fly. Out of line so
+// that its registers do not count against the main loop.
+template <int NIT, bool FULL>
+__device__ __noinline__ void ln_row_slow(const LnArgs& a, int row, int g, int lane) {
+  const int nchunk = a.D >> 3;
+  const __nv_bfloat16* xr = a.x + size_t(row) * a.ldx;
+  float v[NIT * 8];
+  {
+    uint4 raw[NIT];
+#pragma unroll
+    for (int i = 0; i < NIT; ++i)
+      if (FULL || lane + 32 * i < nchunk) raw[i] = *reinterpret_cast<const uint4*>(xr + (lane + 32 * i) * 8);
+    ln_unpack_row<NIT, FULL>(raw, v, lane, nchunk);
+  }
+  const float rstd = ln_center<NIT, FULL>(v, lane, nchunk, 1.f / float(a.D), a.eps);
+  const int nout = a.y2 != nullptr ? 2 : 1;
+#pragma unroll 1
+  for (int i = 0; i < NIT; ++i) {
+    const int c = lane + 32 * i;
+    if (FULL || c < nchunk) {
+      for (int w = 0; w < nout; ++w) {
+        float A[8], B[8], o[8];
+        ln_fold_params(a, g, c, w, A, B);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(v[8 * i + j] * rstd, A[j], B[j]);
+        __nv_bfloat16* yr = w ? a.y2 + size_t(row) * a.ldy2 : a.y + size_t(row) * a.ldy;
+        *reinterpret_cast<uint4*>(yr + c * 8) = pack8(o);
+      }
+    }
+  }
+}
+
+template <int NIT, bool FULL, int PF, int MB>
+__global__ void __launch_bounds__(LN_THREADS, MB)
+ln_mod_kernel(const __grid_constant__ LnArgs a, int rows_per_block) {
+  // [slot 0..1][output 0..nout-1][A lo, A hi, B lo, B hi][nchunk] float4 (lo / hi = columns 0-3 /
+  // 4-7 of a chunk: consecutive lanes read consecutive 16-byte words, conflict-free)
+  extern __shared__ float4 sp[];
   const int wib = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nchunk = a.D >> 3;
-  const bool affine = a.gamma != nullptr;
-  const bool modulated = a.mod != nullptr;
-  const bool dual = a.y2 != nullptr;
+  const bool has_params = a.gamma != nullptr || a.mod != nullptr;
+  const int nout = a.y2 != nullptr ? 2 : 1;
   const int block_row0 = blockIdx.x * rows_per_block;
   const int block_end = min(block_row0 + rows_per_block, a.T);
-  if (affine) {  // weights: not written by the preceding kernel
-    for (int c = threadIdx.x; c < nchunk; c += 256) {
-      sp[0][c] = *reinterpret_cast<const uint4*>(a.gamma + c * 8);
-      sp[1][c] = *reinterpret_cast<const uint4*>(a.beta + c * 8);
-    }
-  }
   pdl_launch_dependents();
   pdl_wait();
   int row = block_row0 + wib;
-  uint4 cur[NIT], nx1[NIT];  // rows row and row + 8; row + 16 is requested inside the loop
+  uint4 cur[NIT], nx[PF][NIT];  // rows row, row + 8 (, row + 16): raw bf16
   auto load_row = [&](uint4* dst, int r) {
     if (r < block_end) {
       const __nv_bfloat16* xr = a.x + size_t(r) * a.ldx;
 #pragma unroll
       for (int i = 0; i < NIT; ++i)
-        if (lane + 32 * i < nchunk) dst[i] = *reinterpret_cast<const uint4*>(xr + (lane + 32 * i) * 8);
+        if (FULL || lane + 32 * i < nchunk) dst[i] = *reinterpret_cast<const uint4*>(xr + (lane + 32 * i) * 8);
     }
   };
   load_row(cur, row);
-  load_row(nx1, row + LN_WARPS);
-  const int g0 = (modulated && a.row_group) ? a.row_group[block_row0] : 0;
-  if (modulated) {
-    const __nv_bfloat16* mrow = a.mod + size_t(g0) * a.ldm;
-    for (int c = threadIdx.x; c < nchunk; c += 256) {
-      sp[affine ? 2 : 0][c] = *reinterpret_cast<const uint4*>(mrow + a.scale_col + c * 8);
-      sp[affine ? 3 : 1][c] = *reinterpret_cast<const uint4*>(mrow + a.shift_col + c * 8);
-      if (dual) {
-        sp[2][c] = *reinterpret_cast<const uint4*>(mrow + a.scale2_col + c * 8);
-        sp[3][c] = *reinterpret_cast<const uint4*>(mrow + a.shift2_col + c * 8);
+#pragma unroll
+  for (int p = 0; p < PF; ++p) load_row(nx[p], row + (p + 1) * LN_WARPS);
+  const bool grouped = a.mod != nullptr && a.row_group != nullptr;
+  const int g0 = grouped ? a.row_group[block_row0] : 0;
+  const int g1 = grouped ? a.row_group[block_end - 1] : 0;
+  if (has_params) {
+    for (int slot = 0; slot < (g1 != g0 ? 2 : 1); ++slot) {
+      for (int c = threadIdx.x; c < nchunk; c += LN_THREADS) {
+        for (int w = 0; w < nout; ++w) {
+          float A[8], B[8];
+          ln_fold_params(a, slot ? g1 : g0, c, w, A, B);
+          float4* d = sp + size_t((slot * nout + w) * 4) * nchunk + c;
+          d[0] = make_float4(A[0], A[1], A[2], A[3]);
+          d[nchunk] = make_float4(A[4], A[5], A[6], A[7]);
+          d[2 * nchunk] = make_float4(B[0], B[1], B[2], B[3]);
+          d[3 * nchunk] = make_float4(B[4], B[5], B[6], B[7]);
+        }
       }
     }
   }
   __syncthreads();
   const float inv_d = 1.f / float(a.D);
-  const int ms = affine ? 2 : 0;  // smem slot of scale (modulation) -- affine+dual is rejected by the host
   for (; row < block_end; row += LN_WARPS) {
-    uint4 nx2[NIT];
-    load_row(nx2, row + 2 * LN_WARPS);
-    float s = 0.f;
+    float v[NIT * 8];
+    ln_unpack_row<NIT, FULL>(cur, v, lane, nchunk);
+    // the row after the prefetched ones takes the registers the unpacked row has just left
 #pragma unroll
-    for (int i = 0; i < NIT; ++i) {
-      if (lane + 32 * i < nchunk) {
-        float v[8];
-        unpack8(cur[i], v);
+    for (int i = 0; i < NIT; ++i) cur[i] = nx[0][i];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s += v[j];
-      }
+    for (int p = 0; p + 1 < PF; ++p)
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) nx[p][i] = nx[p + 1][i];
+    load_row(nx[PF - 1], row + (PF + 1) * LN_WARPS);
+    const int g = grouped ? a.row_group[row] : 0;
+    const int slot = g == g0 ? 0 : (g == g1 ? 1 : -1);
+    if (has_params && slot < 0) {  // warp-uniform
+      ln_row_slow<NIT, FULL>(a, row, g, lane);
+      continue;
     }
-    const int g = (modulated && a.row_group) ? a.row_group[row] : 0;
-    const bool fast = g == g0;
-    const __nv_bfloat16* mrow = modulated ? a.mod + size_t(g) * a.ldm : nullptr;
-    const float mean = warp_sum(s) * inv_d;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < NIT; ++i) {
-      if (lane + 32 * i < nchunk) {
-        float v[8];
-        unpack8(cur[i], v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float d = v[j] - mean;
-          q += d * d;
-        }
-      }
-    }
-    const float rstd = rsqrtf(warp_sum(q) * inv_d + a.eps);
+    const float rstd = ln_center<NIT, FULL>(v, lane, nchunk, inv_d, a.eps);
+    const float4* sp_row = sp + size_t(slot * nout * 4) * nchunk;
 #pragma unroll
     for (int i = 0; i < NIT; ++i) {
       const int c = lane + 32 * i;
-      if (c < nchunk) {
-        float v[8], n[8], o[8];
-        unpack8(cur[i], v);
+      if (FULL || c < nchunk) {
+        float n[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) n[j] = (v[j] - mean) * rstd;
-        if (affine) {
-          float gg[8], bb[8];
-          unpack8(sp[0][c], gg);
-          unpack8(sp[1][c], bb);
+        for (int j = 0; j < 8; ++j) n[j] = v[8 * i + j] * rstd;
+        for (int w = 0; w < nout; ++w) {
+          float o[8];
+          if (!has_params) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) n[j] = n[j] * gg[j] + bb[j];
-        }
-        if (modulated) {
-          float sc[8], sh[8];
-          unpack8(fast ? sp[ms][c] : *reinterpret_cast<const uint4*>(mrow + a.scale_col + c * 8), sc);
-          unpack8(fast ? sp[ms + 1][c] : *reinterpret_cast<const uint4*>(mrow + a.shift_col + c * 8), sh);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = n[j] * (1.f + sc[j]) + sh[j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = n[j];
-        }
-        *reinterpret_cast<uint4*>(a.y + size_t(row) * a.ldy + c * 8) = pack8(o);
-        if (dual) {
-          float sc[8], sh[8];
-          unpack8(fast ? sp[2][c] : *reinterpret_cast<const uint4*>(mrow + a.scale2_col + c * 8), sc);
-          unpack8(fast ? sp[3][c] : *reinterpret_cast<const uint4*>(mrow + a.shift2_col + c * 8), sh);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = n[j] * (1.f + sc[j]) + sh[j];
-          *reinterpret_cast<uint4*>(a.y2 + size_t(row) * a.ldy2 + c * 8) = pack8(o);
+            for (int j = 0; j < 8; ++j) o[j] = n[j];
+          } else {
+            const float4* d = sp_row + size_t(w * 4) * nchunk + c;
+            const float4 a0 = d[0], a1 = d[nchunk], b0 = d[2 * nchunk], b1 = d[3 * nchunk];
+            o[0] = fmaf(n[0], a0.x, b0.x); o[1] = fmaf(n[1], a0.y, b0.y);
+            o[2] = fmaf(n[2], a0.z, b0.z); o[3] = fmaf(n[3], a0.w, b0.w);
+            o[4] = fmaf(n[4], a1.x, b1.x); o[5] = fmaf(n[5], a1.y, b1.y);
+            o[6] = fmaf(n[6], a1.z, b1.z); o[7] = fmaf(n[7], a1.w, b1.w);
+          }
+          __nv_bfloat16* yr = w ? a.y2 + size_t(row) * a.ldy2 : a.y + size_t(row) * a.ldy;
+          *reinterpret_cast<uint4*>(yr + c * 8) = pack8(o);
         }
       }
-    }
-#pragma unroll
-    for (int i = 0; i < NIT; ++i) {
-      cur[i] = nx1[i];
-      nx1[i] = nx2[i];
     }
   }
 }
 
-template <int NIT>
-static int launch_ln(const LnArgs& a, cudaStream_t st) {
-  // one resident wave (3 or 2 blocks per SM, see __launch_bounds__); at least one row per warp
-  const int max_blocks = (NIT <= 4 ? 3 : 2) * device_sm_count();
+template <int NIT, bool FULL, int PF, int MB>
+static int launch_ln_v(const LnArgs& a, cudaStream_t st) {
+  // one resident wave (MB blocks per SM, see __launch_bounds__); at least one row per warp
+  const int max_blocks = MB * device_sm_count();
   int rows_per_block = (a.T + max_blocks - 1) / max_blocks;
   rows_per_block = ((rows_per_block + LN_WARPS - 1) / LN_WARPS) * LN_WARPS;
-  return launch_pdl(ln_mod_kernel<NIT>, dim3((a.T + rows_per_block - 1) / rows_per_block),
-                    dim3(256), 0, st, a, rows_per_block);
+  const int nout = a.y2 ? 2 : 1;
+  const bool has_params = a.gamma || a.mod;
+  const size_t smem = has_params ? size_t(2) * nout * 4 * (a.D >> 3) * sizeof(float4) : 0;
+  auto kern = ln_mod_kernel<NIT, FULL, PF, MB>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2 * 4 * LN_MAXIT * 32 * 16) != cudaSuccess)
+      return B200_ERR_DRIVER;
+    configured = true;
+  }
+  return launch_pdl(kern, dim3((a.T + rows_per_block - 1) / rows_per_block), dim3(LN_THREADS), smem, st,
+                    a, rows_per_block);
+}
+
+// Registers decide the shape: a row of NIT * 8 floats plus (PF + 1) raw rows must stay below the
+// limit of MB blocks per SM without spilling (spills cost 25-80 % here, profiles/r01_norm_microbench.txt).
+template <int NIT>
+static int launch_ln(const LnArgs& a, cudaStream_t st) {
+  const bool full = a.D == NIT * 256;
+  constexpr int PF = NIT <= 3 ? 2 : 1;
+  constexpr int MB = 2;
+  return full ? launch_ln_v<NIT, true, PF, MB>(a, st) : launch_ln_v<NIT, false, PF, MB>(a, st);
 }
 
 // ------------------------------------------------------------------ small elementwise

@@ -29,6 +29,33 @@ def test_layernorm_mod(cuda):
         assert (y.float() - ref).abs().max() < 0.06
 
 
+def test_layernorm_row_result_independent_of_packing(cuda):
+    """A row's output must not depend on which rows / requests surround it: the kernel stages the
+    folded parameters of two requests per block in shared memory and folds them on the fly for
+    rows of any other request (slow path) - both must round identically (bit-exact)."""
+    from sduss_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    for T, D in ((512, 1536), (512, 640)):
+        x = (torch.randn(T, D, generator=g) * 2 + 0.5).cuda().bfloat16()
+        mod = torch.randn(4, 6 * D, generator=g).cuda().bfloat16()
+        grp_sorted = (torch.arange(T) * 4 // T).int()
+        kw = dict(eps=1e-6, mod=mod, shift_col=0, scale_col=D, shift2_col=2 * D, scale2_col=3 * D)
+        y, y2 = torch.empty_like(x), torch.empty_like(x)
+        ops.layernorm_mod(x, y, row_group=grp_sorted.cuda(), y2=y2, **kw)
+        # interleave the requests row by row: every block now sees all four requests
+        perm = torch.arange(T).view(4, T // 4).t().reshape(-1)
+        xp = x[perm.cuda()].contiguous()
+        yp, yp2 = torch.empty_like(x), torch.empty_like(x)
+        ops.layernorm_mod(xp, yp, row_group=grp_sorted[perm].contiguous().cuda(), y2=yp2, **kw)
+        assert torch.equal(yp, y[perm.cuda()]) and torch.equal(yp2, y2[perm.cuda()])
+        # and a single request on its own
+        rows = slice(T // 4, T // 2)
+        ys = torch.empty_like(x[rows])
+        ops.layernorm_mod(x[rows].contiguous(), ys, row_group=torch.ones(T // 4, dtype=torch.int32).cuda(),
+                          eps=1e-6, mod=mod, shift_col=0, scale_col=D)
+        assert torch.equal(ys, y[rows])
+
+
 def test_timestep_embedding_and_silu(cuda):
     from oracle.sd3_mmdit import timestep_embedding
     from sduss_b200 import ops
