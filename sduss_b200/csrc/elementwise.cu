@@ -17,13 +17,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
+  unpack_bf16x2(u.x, f[0], f[1]);
+  unpack_bf16x2(u.y, f[2], f[3]);
+  unpack_bf16x2(u.z, f[4], f[5]);
+  unpack_bf16x2(u.w, f[6], f[7]);
 }
 __device__ __forceinline__ uint4 pack8(const float* f) {
   uint4 u;

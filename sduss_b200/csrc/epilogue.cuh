@@ -47,14 +47,11 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
 }
 
 __device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float* out) {
-  uint4 v = *reinterpret_cast<const uint4*>(p);
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 f = __bfloat1622float2(h[i]);
-    out[2 * i] = f.x;
-    out[2 * i + 1] = f.y;
-  }
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  unpack_bf16x2(v.x, out[0], out[1]);
+  unpack_bf16x2(v.y, out[2], out[3]);
+  unpack_bf16x2(v.z, out[4], out[5]);
+  unpack_bf16x2(v.w, out[6], out[7]);
 }
 
 // acc: 64 fp32 accumulator columns of one row; n0 = first global column of this chunk.

@@ -309,6 +309,12 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// bf16 pair -> two floats in one ALU op each (shift / mask; __bfloat1622float2 compiles to a
+// PRMT + shift per element on sm_100a, which made the HBM-bound kernels issue-bound).
+__device__ __forceinline__ void unpack_bf16x2(uint32_t u, float& lo, float& hi) {
+  lo = __uint_as_float(u << 16);
+  hi = __uint_as_float(u & 0xffff0000u);
+}
 // tanh.approx.f32: one MUFU op, max relative error 2^-11.
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
