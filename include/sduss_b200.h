@@ -229,6 +229,22 @@ int b200_split_patches(const uint64_t* lat_ptr, const int32_t* ldesc, const int3
 int b200_concat_patches(const void* patches, const int32_t* ldesc, const int32_t* pdesc,
                         int n_patches, int C, int ps, const uint64_t* out_ptr, void* stream);
 
+/* ---- VAE decode stage (post_inference, pipeline_stable_diffusion_xl_esymred.py:
+ * 406-462 and pipeline_stable_diffusion_3_esymred.py:391-415). The decoder's convolutions, GroupNorms,
+ * upsamples and linears run on the kernels above; these two are what the stage adds. */
+/* out_l[co, p] = bias[co] + sum_ci weight[co, ci] * in_l[ci, p] on NCHW bf16 latents (fp32 math):
+ * `latents / scaling_factor (+ shift_factor)` and the 1x1 post_quant_conv folded into one per-pixel
+ * affine map. weight fp32 [c_out, c_in], bias fp32 [c_out], c_in, c_out <= 16;
+ * desc int32 [n][4] = {row offset, H, W, 0}; in_ptr / out_ptr: device arrays of latent pointers. */
+int b200_latent_affine(const uint64_t* in_ptr, const uint64_t* out_ptr, const int32_t* desc,
+                       int n_latents, int max_pixels, int c_in, int c_out, const float* weight,
+                       const float* bias, void* stream);
+/* p[r, :] = softmax(scale * s[r, :]): fp32 logits (GEMM output) -> bf16 probabilities, the softmax of
+ * the decoder's single-head mid-block attention (diffusers Attention, head_dim = channels = 512).
+ * cols % 4 == 0, cols <= 16384; lds / ldp in elements. */
+int b200_softmax_rows(const float* s, long long lds, int rows, int cols, float scale, void* p,
+                      long long ldp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,10 @@ SIGNATURES = {
     "b200_split_patches": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "b200_concat_patches": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                             c_void_p],
+    "b200_latent_affine": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                           c_void_p, c_void_p],
+    "b200_softmax_rows": [c_void_p, ctypes.c_longlong, c_int, c_int, c_float, c_void_p,
+                          ctypes.c_longlong, c_void_p],
 }
 
 

@@ -101,12 +101,6 @@ struct AttnArgs {
 #define ATT_ACC(slot, a, b)
 #endif
 
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
 // One work unit, decoded from the tables (written once per plan, not by the preceding kernel:
 // safe to read before pdl_wait()).
 struct AttnUnit {

@@ -315,6 +315,11 @@ __device__ __forceinline__ void unpack_bf16x2(uint32_t u, float& lo, float& hi) 
   lo = __uint_as_float(u << 16);
   hi = __uint_as_float(u & 0xffff0000u);
 }
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // tanh.approx.f32: one MUFU op, max relative error 2^-11.
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;

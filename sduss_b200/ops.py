@@ -421,6 +421,27 @@ def upsample2x(x, in_desc, out_desc, n_latents, max_out_pixels, C, y):
         _ev.record()
 
 
+def latent_affine(in_ptr, out_ptr, desc, n_latents, max_pixels, c_in, c_out, weight, bias):
+    """out_l = weight @ in_l + bias per pixel on NCHW bf16 latents (un-scaling + post_quant_conv)."""
+    _ev = _count("b200_latent_affine")
+    check(lib.b200_latent_affine(_ptr(in_ptr), _ptr(out_ptr), _ptr(desc), n_latents, max_pixels,
+                                 c_in, c_out, _ptr(weight), _ptr(bias), _stream()), "b200_latent_affine")
+    if _ev is not None:
+        _ev.record()
+
+
+def softmax_rows(s, p, scale):
+    """p = softmax(scale * s, dim=-1); s fp32 [rows, cols], p bf16 [rows, cols] (row strides free)."""
+    assert s.dtype == torch.float32 and p.dtype == torch.bfloat16 and s.shape == p.shape
+    assert s.stride(1) == 1 and p.stride(1) == 1
+    _ev = _count("b200_softmax_rows")
+    check(lib.b200_softmax_rows(_ptr(s), s.stride(0), s.shape[0], s.shape[1], ctypes.c_float(scale),
+                                _ptr(p), p.stride(0), _stream()), "b200_softmax_rows")
+    if _ev is not None:
+        _ev.record()
+    return p
+
+
 def copy_cols(src, dst, cols):
     """dst[:, :cols] = src[:, :cols]; src / dst are 2-D views (any row stride)."""
     _req(src), _req(dst)

@@ -30,6 +30,14 @@ def _next_timestep(st) -> float:
     return float(ts[st.timestep_idx])
 
 
+class B200PipelineOutput:
+    """Stands in for StableDiffusion{XL,3}EsymredPipelineOutput (images, nsfw_content_detected)."""
+
+    def __init__(self, images, nsfw_content_detected=None):
+        self.images = images
+        self.nsfw_content_detected = nsfw_content_detected
+
+
 class _StepState:
     """Per batch-composition host staging for the fused CFG + scheduler kernel."""
 
@@ -58,9 +66,36 @@ class B200DenoisingPipelineBase:
     step_mode = 0           # b200_cfg_scheduler_step mode
     default_guidance = 7.0
 
-    def __init__(self, model, scheduler):
+    def __init__(self, model, scheduler, vae=None):
         self.model = model
         self.scheduler = scheduler
+        self.vae = vae  # optional sduss_b200.vae.B200VAEDecoder (post_inference, row f-4)
+
+    # -- post stage --------------------------------------------------------------------
+    @torch.inference_mode()
+    def post_inference(self, worker_reqs: Dict[str, List], output_type: str = "pt") -> None:
+        """VAE decode of the finished requests' latents; sets `req.output.images` like
+        ESyMReDStableDiffusionXLPipeline.post_inference (pipeline_stable_diffusion_xl_esymred.py:
+        406-462) and its SD3 twin (pipeline_stable_diffusion_3_esymred.py:391-415), but for ALL
+        resolutions of the batch in one pass instead of one `vae.decode` per resolution.
+        output_type "pt": float image [3, H, W] in [0, 1]; "np": [H, W, 3]; "pil": PIL.Image."""
+        if self.vae is None:
+            raise RuntimeError("post_inference needs a B200VAEDecoder (pipeline built without vae)")
+        if output_type == "latent":
+            raise NotImplementedError("latent output is not supported (as in the reference)")
+        res_list = self._sorted_res(worker_reqs)
+        lat = {res: torch.cat([r.sampling_params.latents for r in worker_reqs[res]], dim=0) for res in res_list}
+        images = self.vae.decode(lat, _borrow=True)
+        for res in res_list:
+            img = (images[res].float() / 2 + 0.5).clamp(0, 1)  # VaeImageProcessor.denormalize
+            for i, req in enumerate(worker_reqs[res]):
+                one = img[i]
+                if output_type in ("np", "pil"):
+                    one = one.permute(1, 2, 0).cpu().numpy()
+                if output_type == "pil":
+                    from PIL import Image
+                    one = Image.fromarray((one * 255).round().astype("uint8"))
+                req.output = B200PipelineOutput(images=one)
 
     # -- helpers -----------------------------------------------------------------------
     @staticmethod
