@@ -177,7 +177,10 @@ class B200VAEDecoder(torch.nn.Module):
             if i != len(ch) - 1:
                 conv3(f"decoder.up_blocks.{i}.upsamplers.0.conv")
         norm("decoder.conv_norm_out")
-        self.n_out_pad = 8
+        # conv_out (3 channels) padded to 64: the epilogue's TMA store then writes whole 128-byte
+        # pixel rows; with 8 channels (16-byte rows) this one layer took 1.13 ms instead of 0.48 ms
+        # on 1.3 M pixels (profiles/r01_vae_decode.txt)
+        self.n_out_pad = 64
         conv3("decoder.conv_out", pad_out=self.n_out_pad)
         self._plans = ops.PlanCache(self.device)
         self.use_graphs = ops.graphs_enabled()
