@@ -44,10 +44,10 @@ def run_plan(model, plan):
     into a CUDA graph and replayed; per-launch profiling (ops.profile) forces the eager path."""
     global launch_count
     if not getattr(model, "use_graphs", False) or profile is not None:
-        model._run(plan)
+        _run_eager(model, plan)
         return
     if plan.graph is None:
-        model._run(plan)                      # eager: allocates workspaces, encodes tensor maps
+        _run_eager(model, plan)               # eager: allocates workspaces, encodes tensor maps
         torch.cuda.current_stream().synchronize()
         n0 = launch_count
         g = torch.cuda.CUDAGraph()
@@ -59,6 +59,24 @@ def run_plan(model, plan):
         return                                # the eager run already produced this call's result
     plan.graph.replay()
     launch_count += plan.graph_launches
+
+
+class ArenaOverflow(RuntimeError):
+    def __init__(self, need):
+        super().__init__(f"arena too small: {need} bytes needed so far")
+        self.need = need
+
+
+def _run_eager(model, plan):
+    """model._run(plan); plans that bump-allocate their workspaces from the model's Arena restart
+    on a larger block when it overflows (a handful of times per process: the block doubles)."""
+    while True:
+        try:
+            return model._run(plan)
+        except ArenaOverflow as e:
+            torch.cuda.current_stream().synchronize()  # kernels of the partial run still use the old views
+            plan.reset_workspaces()
+            model.arena.grow(e.need)
 
 
 class PlanCache:
@@ -150,6 +168,25 @@ class Arena:
             n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
             out[name] = self.block[off:off + n].view(dtype).view(*shape)
         return out, self.block
+
+    # -- bump allocation for plans that discover their workspaces while they run (UNet, VAE) --
+    def alloc(self, plan, shape, dtype):
+        """Next `shape` tensor of `plan` on the current block; ArenaOverflow if the block is
+        missing, has been replaced since the plan started, or is full (see _run_eager)."""
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        if getattr(plan, "block", None) is None:
+            plan.block, plan.arena_off = self.block, 0
+        end = plan.arena_off + (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        if self.block is None or plan.block is not self.block or end > self.block.numel():
+            raise ArenaOverflow(end)
+        t = self.block[plan.arena_off:plan.arena_off + n].view(dtype).view(*shape)
+        plan.arena_off = end
+        return t
+
+    def grow(self, need):
+        have = 0 if self.block is None else self.block.numel()
+        self.block = None  # plans captured on the old block keep it alive; nothing else does
+        self.block = torch.empty((max(2 * need, 2 * have, 1 << 30),), dtype=torch.uint8, device=self.device)
 
 
 def _stream():

@@ -102,6 +102,7 @@ class _Plan:
             self.self_plan[l] = ops.build_attn_plan(selfp, dev, cfg.num_heads[l])
             self.cross_plan[l] = ops.build_attn_plan(crossp, dev, cfg.num_heads[l])
         self.gn_ws = ops.groupnorm_workspace(self.levels[0].T, L, dev)
+        self.arena, self.block, self.arena_off = model.arena, None, 0
         self.bufs: Dict[str, torch.Tensor] = {}
         self.maps: Dict[tuple, torch.Tensor] = {}
         self.attn_src: Dict[tuple, object] = {}
@@ -115,10 +116,16 @@ class _Plan:
 
     def buf(self, name, rows, cols):
         t = self.bufs.get(name)
-        if t is None:
-            t = self.bufs[name] = torch.empty((rows, cols), device=self.device, dtype=torch.bfloat16)
+        if t is None:  # bump-allocated from the model's shared arena (ops.Arena.alloc)
+            t = self.bufs[name] = self.arena.alloc(self, (rows, cols), torch.bfloat16)
         assert t.shape == (rows, cols), (name, t.shape, rows, cols)
         return t
+
+    def reset_workspaces(self):
+        """Forget every arena view and everything that captured its address (ops._run_eager)."""
+        self.bufs, self.maps, self.block, self.arena_off = {}, {}, None, 0
+        if hasattr(self, "attn_src"):
+            self.attn_src = {}
 
     def conv_maps(self, x, cin, level, stride):
         key = (x.data_ptr(), x.stride(0), cin, level, stride)
@@ -249,6 +256,7 @@ class B200UNet(torch.nn.Module):
         put("kv_all.weight", torch.cat(kv_w, 0))
         self.kv_cols = kcol
         self._plans = ops.PlanCache(self.device)
+        self.arena = ops.Arena(self.device)  # per-step workspaces of all plans overlap here
         self.use_graphs = ops.graphs_enabled()
 
     @classmethod

@@ -81,9 +81,7 @@ class _Plan:
         as_dev = lambda p: torch.tensor(p, dtype=torch.int64).to(dev)
         self.in_ptr, self.z_ptr, self.out_ptr = as_dev(ip), as_dev(zp), as_dev(op)
         self.gn_ws = ops.groupnorm_workspace(self.levels[-1].T, L, dev)
-        nmax = self.levels[0].max_pixels
-        self.attn_s = torch.empty((nmax * nmax,), device=dev, dtype=torch.float32)
-        self.attn_p = torch.empty((nmax * nmax,), **bf)
+        self.arena, self.block, self.arena_off = model.arena, None, 0
         self.bufs: Dict[str, torch.Tensor] = {}
         self.maps: Dict[tuple, torch.Tensor] = {}
         self.device = dev
@@ -92,10 +90,22 @@ class _Plan:
 
     def buf(self, name, rows, cols):
         t = self.bufs.get(name)
-        if t is None:
-            t = self.bufs[name] = torch.empty((rows, cols), device=self.device, dtype=torch.bfloat16)
+        if t is None:  # bump-allocated from the model's shared arena (ops.Arena.alloc)
+            t = self.bufs[name] = self.arena.alloc(self, (rows, cols), torch.bfloat16)
         assert t.shape == (rows, cols), (name, t.shape, rows, cols)
         return t
+
+    def ws(self, name, numel, dtype):
+        t = self.bufs.get(name)
+        if t is None:
+            t = self.bufs[name] = self.arena.alloc(self, (numel,), dtype)
+        return t
+
+    def reset_workspaces(self):
+        """Forget every arena view and everything that captured its address (ops._run_eager)."""
+        self.bufs, self.maps, self.block, self.arena_off = {}, {}, None, 0
+        if hasattr(self, "attn_src"):
+            self.attn_src = {}
 
     def conv_maps(self, x, cin, level):
         key = (x.data_ptr(), x.stride(0), cin, level)
@@ -183,6 +193,7 @@ class B200VAEDecoder(torch.nn.Module):
         self.n_out_pad = 64
         conv3("decoder.conv_out", pad_out=self.n_out_pad)
         self._plans = ops.PlanCache(self.device)
+        self.arena = ops.Arena(self.device)  # per-step workspaces of all plans overlap here
         self.use_graphs = ops.graphs_enabled()
 
     @classmethod
@@ -233,10 +244,13 @@ class B200VAEDecoder(torch.nn.Module):
         o = pl.buf("attn_o", T, C)
         vt = pl.buf("attn_vt", C, lay.max_pixels)
         wv = self.w[name + ".qkv.weight"][2 * C:]
+        nmax = lay.max_pixels
+        attn_s = pl.ws("attn_s", nmax * nmax, torch.float32)
+        attn_p = pl.ws("attn_p", nmax * nmax, torch.bfloat16)
         for i in range(lay.L):
             r0, n = lay.row_off[i], lay.rows[i]
-            s = pl.attn_s[:n * n].view(n, n)
-            p = pl.attn_p[:n * n].view(n, n)
+            s = attn_s[:n * n].view(n, n)
+            p = attn_p[:n * n].view(n, n)
             G(qkv[r0:r0 + n, :C], qkv[r0:r0 + n, C:2 * C], s)            # fp32 logits
             ops.softmax_rows(s, p, 1.0 / math.sqrt(C))
             G(wv, t[r0:r0 + n], vt[:, :n])                                 # v^T = Wv t^T
