@@ -88,9 +88,11 @@ class PlanCache:
     re-created on demand. The reference allocates its activations from torch's caching allocator
     every step instead; here pointers must be stable for graph replay."""
 
-    def __init__(self, device, budget_fraction=0.35):
+    def __init__(self, device, budget_fraction=0.35, arena=None):
         import collections
         self.plans = collections.OrderedDict()
+        self.arena = arena          # plans carved from an older (smaller) block of it are stale
+        self.stale_dropped = 0
         total = torch.cuda.get_device_properties(device).total_memory if torch.cuda.is_available() else 1 << 40
         self.budget_bytes = int(total * budget_fraction)
         self.evictions = 0
@@ -127,7 +129,20 @@ class PlanCache:
         seen = set()
         return sum(self.plan_bytes(p, seen) for p in self.plans.values())
 
+    def _drop_stale(self):
+        """When the shared arena has grown, plans (and CUDA graphs) that live on its previous block
+        are dropped so that block is freed; they are rebuilt on the new one on demand. The arena
+        doubles, so this happens a handful of times per process."""
+        if self.arena is None or self.arena.block is None:
+            return
+        stale = [k for k, p in self.plans.items()
+                 if getattr(p, "block", None) is not None and p.block is not self.arena.block]
+        for k in stale:
+            del self.plans[k]
+        self.stale_dropped += len(stale)
+
     def get(self, key, factory):
+        self._drop_stale()
         plan = self.plans.get(key)
         if plan is not None:
             self.plans.move_to_end(key)
@@ -161,7 +176,8 @@ class Arena:
             offs.append(total)
             total += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         if self.block is None or self.block.numel() < total:
-            grow = 0 if self.block is None else int(self.block.numel() * 1.25)
+            grow = 0 if self.block is None else 2 * self.block.numel()
+            self.block = None
             self.block = torch.empty((max(total, grow),), dtype=torch.uint8, device=self.device)
         out = {}
         for (name, shape, dtype), off in zip(specs, offs):

@@ -205,8 +205,8 @@ class B200SD3Transformer2DModel(torch.nn.Module):
         self.mod_w = torch.cat(mod_w, 0).to(self.device, torch.bfloat16).contiguous()
         self.mod_b = torch.cat(mod_b, 0).to(self.device, torch.bfloat16).contiguous()
         self.proj_w, self.proj_b = w("proj_out.weight"), w("proj_out.bias")
-        self._plans = ops.PlanCache(self.device)
         self.arena = ops.Arena(self.device)
+        self._plans = ops.PlanCache(self.device, arena=self.arena)
         self.use_graphs = ops.graphs_enabled()
 
     @classmethod

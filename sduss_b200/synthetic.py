@@ -229,3 +229,71 @@ def random_unet_state_dict(cfg, device, seed=0, dtype=torch.bfloat16):
     norm("conv_norm_out", ch[0])
     conv("conv_out", ch[0], cfg.out_channels, 3)
     return sd
+
+
+def random_vae_state_dict(cfg, device, seed=0, dtype=torch.bfloat16):
+    """AutoencoderKL decoder-side state dict (diffusers names: post_quant_conv, decoder.*),
+    random-init on `device`. cfg: sduss_b200.vae.VAEDecoderConfig."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    sd = {}
+
+    def lin(name, fin, fout, gain=1.0):
+        sd[name + ".weight"] = (torch.randn(fout, fin, generator=g, device=device) * (gain / fin ** 0.5)).to(dtype)
+        sd[name + ".bias"] = (torch.randn(fout, generator=g, device=device) * 0.02).to(dtype)
+
+    def conv(name, cin, cout, k, gain=1.0):
+        sd[name + ".weight"] = (torch.randn(cout, cin, k, k, generator=g, device=device)
+                                * (gain / (cin * k * k) ** 0.5)).to(dtype)
+        sd[name + ".bias"] = (torch.randn(cout, generator=g, device=device) * 0.02).to(dtype)
+
+    def norm(name, c):
+        sd[name + ".weight"] = (1.0 + 0.1 * torch.randn(c, generator=g, device=device)).to(dtype)
+        sd[name + ".bias"] = (0.05 * torch.randn(c, generator=g, device=device)).to(dtype)
+
+    def resnet(name, cin, cout):
+        norm(name + ".norm1", cin)
+        conv(name + ".conv1", cin, cout, 3)
+        norm(name + ".norm2", cout)
+        conv(name + ".conv2", cout, cout, 3, 0.5)
+        if cin != cout:
+            conv(name + ".conv_shortcut", cin, cout, 1)
+
+    ch = list(reversed(cfg.block_out_channels))
+    top, C = ch[0], cfg.latent_channels
+    if cfg.use_post_quant_conv:
+        conv("post_quant_conv", C, C, 1)
+    conv("decoder.conv_in", C, top, 3)
+    resnet("decoder.mid_block.resnets.0", top, top)
+    a = "decoder.mid_block.attentions.0"
+    norm(a + ".group_norm", top)
+    for n in ("to_q", "to_k", "to_v"):
+        lin(f"{a}.{n}", top, top)
+    lin(a + ".to_out.0", top, top, 0.5)
+    resnet("decoder.mid_block.resnets.1", top, top)
+    prev = top
+    for i, c in enumerate(ch):
+        for j in range(cfg.layers_per_block + 1):
+            resnet(f"decoder.up_blocks.{i}.resnets.{j}", prev if j == 0 else c, c)
+        prev = c
+        if i != len(ch) - 1:
+            conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", c, c, 3)
+    norm("decoder.conv_norm_out", ch[-1])
+    conv("decoder.conv_out", ch[-1], cfg.out_channels, 3)
+    return sd
+
+
+def vae_decode_flops(cfg, h, w):
+    """2 x multiply-adds of one VAE decode of an h x w latent (convs, 1x1 shortcuts, attention)."""
+    ch = list(reversed(cfg.block_out_channels))
+    top, px = ch[0], h * w
+    res = lambda cin, cout, p: 2.0 * p * (9 * cin * cout + 9 * cout * cout + (cin * cout if cin != cout else 0))
+    fl = 2.0 * 9 * cfg.latent_channels * top * px + 2 * res(top, top, px) + 2.0 * px * 4 * top * top + 4.0 * px * px * top
+    prev = top
+    for i, c in enumerate(ch):
+        for j in range(cfg.layers_per_block + 1):
+            fl += res(prev if j == 0 else c, c, px)
+        prev = c
+        if i != len(ch) - 1:
+            px *= 4
+            fl += 2.0 * 9 * c * c * px
+    return fl + 2.0 * 9 * ch[-1] * cfg.out_channels * px

@@ -255,8 +255,8 @@ class B200UNet(torch.nn.Module):
         self.temb_cols = tcol
         put("kv_all.weight", torch.cat(kv_w, 0))
         self.kv_cols = kcol
-        self._plans = ops.PlanCache(self.device)
         self.arena = ops.Arena(self.device)  # per-step workspaces of all plans overlap here
+        self._plans = ops.PlanCache(self.device, arena=self.arena)
         self.use_graphs = ops.graphs_enabled()
 
     @classmethod

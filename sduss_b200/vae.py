@@ -126,7 +126,10 @@ class B200VAEDecoder(torch.nn.Module):
         self.config = config
         self.device = dev = torch.device(device)
         self.dtype = torch.bfloat16
-        sd = state_dict
+        # the decoder is small (50 M parameters): re-laid out on the host in fp32, whatever device /
+        # dtype the state dict arrives in (encoder and quant_conv entries are ignored)
+        sd = {k: v.detach().float().cpu() for k, v in state_dict.items()
+              if k.startswith(("decoder.", "post_quant_conv."))}
         self.w: Dict[str, torch.Tensor] = {}
 
         def put(name, t):
@@ -192,8 +195,8 @@ class B200VAEDecoder(torch.nn.Module):
         # on 1.3 M pixels (profiles/r01_vae_decode.txt)
         self.n_out_pad = 64
         conv3("decoder.conv_out", pad_out=self.n_out_pad)
-        self._plans = ops.PlanCache(self.device)
         self.arena = ops.Arena(self.device)  # per-step workspaces of all plans overlap here
+        self._plans = ops.PlanCache(self.device, arena=self.arena)
         self.use_graphs = ops.graphs_enabled()
 
     @classmethod

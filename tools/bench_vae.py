@@ -5,9 +5,9 @@ per-kernel / per-shape breakdown (eager pass with events around every launch).""
 import argparse, collections, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import vae_decoder as ov  # FLOP count + random-init weights only (bench tooling)
 from sduss_b200 import ops
-from sduss_b200.vae import B200VAEDecoder
+from sduss_b200.synthetic import random_vae_state_dict, vae_decode_flops
+from sduss_b200.vae import B200VAEDecoder, VAEDecoderConfig
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--model", default="sdxl", choices=["sdxl", "sd3"])
@@ -15,14 +15,15 @@ ap.add_argument("--spec", default="512:1,1024:1", help="resolution:count,...")
 ap.add_argument("--iters", type=int, default=10)
 a = ap.parse_args()
 dev = torch.device("cuda")
-cfg = ov.sdxl_vae_config() if a.model == "sdxl" else ov.sd3_vae_config()
-sd = ov.init_vae_decoder_weights(cfg, 0)
+cfg = VAEDecoderConfig() if a.model == "sdxl" else VAEDecoderConfig(
+    latent_channels=16, scaling_factor=1.5305, shift_factor=0.0609, use_post_quant_conv=False)
+sd = random_vae_state_dict(cfg, dev)
 model = B200VAEDecoder(sd, cfg, device=dev)
 spec = {r: int(n) for r, n in (kv.split(":") for kv in a.spec.split(","))}
 g = torch.Generator().manual_seed(0)
 lat = {r: (torch.randn(n, cfg.latent_channels, int(r) // 8, int(r) // 8, generator=g) * 0.8).bfloat16().to(dev)
        for r, n in sorted(spec.items(), key=lambda kv: int(kv[0]))}
-flops = sum(n * ov.vae_decode_flops(cfg, int(r) // 8, int(r) // 8) for r, n in spec.items())
+flops = sum(n * vae_decode_flops(cfg, int(r) // 8, int(r) // 8) for r, n in spec.items())
 for _ in range(3):
     out = model.decode(lat, _borrow=True)
 torch.cuda.synchronize()

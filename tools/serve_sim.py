@@ -2,7 +2,8 @@
 requests into sduss' `fcfs_mixed`-style continuous batching (every waiting request joins the
 running batch at the next step boundary, up to max_batchsize; sduss/worker/scheduler/policy),
 each request running `steps` denoising steps through this repo's drop-in `denoising_step`.
-Prepare (text encoders) and post-processing (VAE) are outside the hot path and not simulated.
+Prepare (text encoders) is not simulated; with SERVE_VAE=1 every finished request goes through the
+post stage on the B200 VAE decoder (row f-4) before it counts as served.
 Reports requests/s, latency percentiles, the number of distinct batch compositions and what
 building their plans cost.
 Usage: python tools/serve_sim.py sd3|sdxl [qps] [n_requests] [max_batchsize]"""
@@ -34,6 +35,13 @@ else:
     pipe = P(model, sch)
     step = lambda reqs: pipe.denoising_step(reqs, True, 0.0, 5.0, None, {}, None, None, None, True, 256)
 
+with_vae = os.environ.get("SERVE_VAE", "0") == "1"
+if with_vae:
+    from sduss_b200.synthetic import random_vae_state_dict
+    from sduss_b200.vae import B200VAEDecoder, VAEDecoderConfig
+    vcfg = VAEDecoderConfig() if which != "sd3" else VAEDecoderConfig(
+        latent_channels=16, scaling_factor=1.5305, shift_factor=0.0609, use_post_quant_conv=False)
+    pipe.vae = B200VAEDecoder(random_vae_state_dict(vcfg, dev), vcfg, device=dev)
 rng = random.Random(0)
 arrivals, t = [], 0.0
 for i in range(n_req):
@@ -63,18 +71,25 @@ while next_i < n_req or running:
     if len(model._plans) != n_plans or model._plans.evictions:   # a new composition: plan build + capture
         torch.cuda.synchronize(); plan_time += time.perf_counter() - ts if len(model._plans) != n_plans else 0.0
     n_steps += 1
-    keep = []
+    keep, finished = [], {}
     for i, ta in running:
         if objs[i].scheduler_states._step_index >= steps:
-            torch.cuda.synchronize()
-            done_lat.append(time.perf_counter() - t0 - ta)
+            finished.setdefault(arrivals[i][1], []).append(objs[i])
         else:
             keep.append((i, ta))
+    if finished:
+        if with_vae:
+            pipe.post_inference(finished, "pt")   # all resolutions that finished at this step, one pass
+        torch.cuda.synchronize()
+        for i, ta in running:
+            if objs[i].scheduler_states._step_index >= steps:
+                done_lat.append(time.perf_counter() - t0 - ta)
     running = keep
 torch.cuda.synchronize()
 wall = time.perf_counter() - t0
 lat = np.asarray(done_lat)
-print(f"{which}: {n_req} requests at {qps} req/s offered, {steps} steps each, max batch {max_bs}")
+print(f"{which}: {n_req} requests at {qps} req/s offered, {steps} steps each, max batch {max_bs}"
+      + (", VAE decode of finished requests included" if with_vae else ""))
 print(f"  wall {wall:.1f} s -> {n_req / wall:.2f} req/s served, {n_steps} batch steps ({n_steps / wall:.1f} steps/s, "
       f"{n_req * steps / wall:.0f} request-steps/s)")
 print(f"  latency mean {lat.mean():.2f} s  p50 {np.percentile(lat, 50):.2f}  p99 {np.percentile(lat, 99):.2f}")
