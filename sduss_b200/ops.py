@@ -74,7 +74,8 @@ def _run_eager(model, plan):
         try:
             return model._run(plan)
         except ArenaOverflow as e:
-            torch.cuda.current_stream().synchronize()  # kernels of the partial run still use the old views
+            if torch.cuda.is_available():  # kernels of the partial run still use the old views
+                torch.cuda.current_stream().synchronize()
             plan.reset_workspaces()
             model.arena.grow(e.need)
 
@@ -163,6 +164,7 @@ class Arena:
     larger plan arrives a new block is allocated; older plans keep (a reference to) the block
     their CUDA graph was captured on."""
     ALIGN = 1024
+    MIN_BLOCK = 1 << 30
 
     def __init__(self, device):
         self.device = device
@@ -202,7 +204,7 @@ class Arena:
     def grow(self, need):
         have = 0 if self.block is None else self.block.numel()
         self.block = None  # plans captured on the old block keep it alive; nothing else does
-        self.block = torch.empty((max(2 * need, 2 * have, 1 << 30),), dtype=torch.uint8, device=self.device)
+        self.block = torch.empty((max(2 * need, 2 * have, self.MIN_BLOCK),), dtype=torch.uint8, device=self.device)
 
 
 def _stream():

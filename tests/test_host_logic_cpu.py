@@ -169,6 +169,62 @@ def test_arena_views_are_aligned_disjoint_and_shared_between_plans():
     assert cache.total_bytes() == blk1.numel()                   # the shared block is counted once
 
 
+def test_arena_bump_allocation_restarts_on_overflow_and_stale_plans_are_dropped():
+    """UNet / VAE plans discover their workspaces while they run: `Arena.alloc` bump-allocates, an
+    overflow restarts the plan's warm-up run on a doubled block (`ops._run_eager`), and plans that
+    still live on the superseded block are dropped by the PlanCache (rebuilt on demand)."""
+    import torch
+    from sduss_b200 import ops
+
+    class Plan:
+        def __init__(self, arena, sizes):
+            self.arena, self.sizes = arena, sizes
+            self.bufs, self.maps, self.block, self.arena_off, self.graph = {}, {}, None, 0, None
+
+        def buf(self, name, n):
+            if name not in self.bufs:
+                self.bufs[name] = self.arena.alloc(self, (n,), torch.uint8)
+            return self.bufs[name]
+
+        def reset_workspaces(self):
+            self.bufs, self.maps, self.block, self.arena_off = {}, {}, None, 0
+
+    class Model:
+        use_graphs = False
+
+        def __init__(self):
+            self.arena = ops.Arena("cpu")
+            self.runs = 0
+
+        def _run(self, plan):
+            self.runs += 1
+            for i, n in enumerate(plan.sizes):
+                plan.buf(f"b{i}", n).fill_(i + 1)
+
+    m = Model()
+    m.arena.MIN_BLOCK = 1 << 16
+    cache = ops.PlanCache("cpu", arena=m.arena)
+    small = cache.get("small", lambda: Plan(m.arena, [100, 5000]))
+    ops.run_plan(m, small)
+    assert m.runs == 2                                   # first attempt overflowed the empty arena
+    blk = m.arena.block
+    assert small.block is blk and blk.numel() >= 1 << 16
+    a, b = small.bufs["b0"], small.bufs["b1"]
+    assert (b.data_ptr() - blk.data_ptr()) % ops.Arena.ALIGN == 0 and b.data_ptr() >= a.data_ptr() + 100
+    assert int(a[0]) == 1 and int(b[-1]) == 2
+    other = cache.get("other", lambda: Plan(m.arena, [300]))
+    ops.run_plan(m, other)                               # fits: same block, overlapping the first plan
+    assert m.runs == 3 and other.block is blk and other.bufs["b0"].data_ptr() == a.data_ptr()
+    big = cache.get("big", lambda: Plan(m.arena, [blk.numel() // 2, blk.numel()]))
+    ops.run_plan(m, big)                                 # overflows mid-run: restart on a doubled block
+    assert m.arena.block is not blk and m.arena.block.numel() >= 2 * blk.numel() and big.block is m.arena.block
+    assert set(cache.plans) == {"small", "other", "big"}
+    again = cache.get("small", lambda: Plan(m.arena, [100, 5000]))
+    assert again is not small and cache.stale_dropped == 2 and set(cache.plans) == {"big", "small"}
+    ops.run_plan(m, again)
+    assert again.block is m.arena.block
+
+
 def test_registry_plugin_overrides_only_the_hot_path(monkeypatch):
     """sduss_b200.plugin.make_b200_pipeline: the class sduss registers instead of its ESyMReD
     pipeline. Fakes stand in for the reference class and for the GPU modules."""

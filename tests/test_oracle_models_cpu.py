@@ -47,3 +47,30 @@ def test_flop_and_parameter_accounting_matches_survey():
         assert abs(got - want) < 2e-3
     assert abs(2 * (sdxl[1] + sdxl[3]) - 16.70) < 0.01      # config 1 step
     assert abs(2 * (sd3[1] + sd3[2] + sd3[3]) - 38.57) < 0.01  # config 2 step
+
+
+def test_vae_decoder_oracle_batch_independence_and_flops():
+    """oracle/vae_decoder.py (row f-4): every image is decoded on its own, shapes follow the 8x
+    upsampling, the two reference un-scalings are restated (SDXL: / scaling_factor; SD3: / scaling_factor
+    + shift_factor), and the FLOP count agrees with the product-side bench accounting."""
+    import torch
+    from oracle import vae_decoder as ov
+    from sduss_b200.synthetic import vae_decode_flops
+    from sduss_b200.vae import VAEDecoderConfig
+    cfg = ov.vae_tiny_config(latent_channels=16, shift=0.0609, pq=False)
+    sd = ov.init_vae_decoder_weights(cfg, 0)
+    g = torch.Generator().manual_seed(0)
+    lat = {"64": torch.randn(2, 16, 8, 8, generator=g), "96": torch.randn(1, 16, 16, 8, generator=g)}
+    out = ov.vae_decode(sd, cfg, lat)
+    assert out["64"].shape == (2, 3, 64, 64) and out["96"].shape == (1, 3, 128, 64)
+    solo = ov.vae_decode(sd, cfg, {"64": lat["64"][1:2]})
+    assert torch.equal(solo["64"][0], out["64"][1])
+    z = torch.ones(1, 16, 2, 2)
+    assert torch.allclose(ov.unscale_latents(cfg, z), z / cfg.scaling_factor + 0.0609)
+    assert torch.allclose(ov.unscale_latents(ov.sdxl_vae_config(), z[:, :4]), z[:, :4] / 0.13025)
+    img = ov.postprocess(out["64"])
+    assert img.min() >= 0 and img.max() <= 1
+    for ocfg, pcfg in ((ov.sdxl_vae_config(), VAEDecoderConfig()),
+                       (ov.sd3_vae_config(), VAEDecoderConfig(latent_channels=16, use_post_quant_conv=False))):
+        assert ov.vae_decode_flops(ocfg, 128, 128) == vae_decode_flops(pcfg, 128, 128)
+    assert 9e12 < ov.vae_decode_flops(ov.sdxl_vae_config(), 128, 128) < 12e12
