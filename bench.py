@@ -294,9 +294,10 @@ def run_b200(args, rank, world, local_rank):
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": (achieved / peak) if achieved else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one joint-attention launch of
-                     # this workload (ncu --set full, profiles/r01_ncu_attn_3x64.txt); algorithmic
-                     # bytes of that launch (Q, K, V in, O out): 207 MB
-                     "traffic": 155412736 + 35321600, "traffic_unit": "bytes per joint-attention launch",
+                     # this workload (ncu --set full of the final round-1 kernel,
+                     # profiles/r01_ncu_attn_final.txt); algorithmic bytes of that launch (Q, K, V in,
+                     # O out): 207 MB
+                     "traffic": 185323776 + 42830848, "traffic_unit": "bytes per joint-attention launch",
                      "peak_source": pk_src + ", sustained bf16",
                      "launches_timed": n_attn, "kernel_ms_per_step": attn_ms / args.steps,
                      "gemm_ms_per_step": gemm_ms / args.steps,
