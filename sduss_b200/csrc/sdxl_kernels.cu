@@ -78,13 +78,13 @@ __global__ void __launch_bounds__(GN_THREADS, 5) gn_stats_kernel(const __nv_bflo
 #pragma unroll
   for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
   pdl_wait();
-  for (int r0 = rl; r0 < GN_CHUNK; r0 += 4 * RL) {  // fixed order: rows rl, rl + RL, ...
-    uint4 v[4];
+  uint4 v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int r = r0 + k * RL;
-      if (r < GN_CHUNK) v[k] = *reinterpret_cast<const uint4*>(base + size_t(r) * ldx);
-    }
+  for (int k = 0; k < 4; ++k) {
+    const int r = rl + k * RL;
+    if (r < GN_CHUNK) v[k] = *reinterpret_cast<const uint4*>(base + size_t(r) * ldx);
+  }
+  for (int r0 = rl;;) {  // fixed order: rows rl, rl + RL, ...
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (r0 + k * RL < GN_CHUNK) {
@@ -96,6 +96,13 @@ __global__ void __launch_bounds__(GN_THREADS, 5) gn_stats_kernel(const __nv_bflo
           sq[j] = fmaf(f[j], f[j], sq[j]);
         }
       }
+    }
+    r0 += 4 * RL;
+    if (r0 >= GN_CHUNK) break;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = r0 + k * RL;
+      if (r < GN_CHUNK) v[k] = *reinterpret_cast<const uint4*>(base + size_t(r) * ldx);
     }
   }
 #pragma unroll
@@ -163,21 +170,30 @@ __global__ void gn_finalize_kernel(const float* partial, const int4* lat, int L,
 
 // SiLU as h + h * tanh(h), h = v / 2: one MUFU op per element instead of ex2 + rcp (+ the Newton
 // steps of an IEEE division); tanh.approx is accurate to 2^-11, below the bf16 rounding of y.
+// Chunks are walked from the END of the tensor (CTA 0 takes the last one): the statistics pass
+// has just streamed x front to back, so its tail is what the 126 MB L2 still holds when x is larger
+// than L2 (and the whole of x when it is not).
 template <bool SILU>
 __global__ void __launch_bounds__(GN_THREADS, 4) gn_apply_kernel(
-    const __nv_bfloat16* x, int ldx, int W, int RL, int cpg, int G, const float* stats,
-    const int* row_group, const __nv_bfloat16* gamma, const __nv_bfloat16* beta, __nv_bfloat16* y,
-    int ldy) {
+    const __nv_bfloat16* x, int ldx, int W, int RL, int cpg, int G, int n_chunks,
+    const float* stats, const int* row_group, const __nv_bfloat16* gamma,
+    const __nv_bfloat16* beta, __nv_bfloat16* y, int ldy) {
   pdl_launch_dependents();
   const int rl = threadIdx.x / W, col = threadIdx.x - rl * W;
   const int ch0 = (blockIdx.y * W + col) * 8;  // first channel of this thread's vector
-  const size_t row0 = size_t(blockIdx.x) * GN_CHUNK;
+  const size_t row0 = size_t(n_chunks - 1 - int(blockIdx.x)) * GN_CHUNK;
   const __nv_bfloat16* xb = x + row0 * ldx + ch0;
   __nv_bfloat16* yb = y + row0 * ldy + ch0;
   float a[8], b[8];
   unpack8s(*reinterpret_cast<const uint4*>(gamma + ch0), a);  // parameters: not written by the
   unpack8s(*reinterpret_cast<const uint4*>(beta + ch0), b);   // preceding kernels
   pdl_wait();
+  uint4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {  // first rows in flight while a, b are folded
+    const int r = rl + k * RL;
+    if (r < GN_CHUNK) v[k] = *reinterpret_cast<const uint4*>(xb + size_t(r) * ldx);
+  }
   const float* st = stats + size_t(row_group[row0]) * G * 2;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -189,13 +205,7 @@ __global__ void __launch_bounds__(GN_THREADS, 4) gn_apply_kernel(
       b[j] *= 0.5f;
     }
   }
-  for (int r0 = rl; r0 < GN_CHUNK; r0 += 4 * RL) {
-    uint4 v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int r = r0 + k * RL;
-      if (r < GN_CHUNK) v[k] = *reinterpret_cast<const uint4*>(xb + size_t(r) * ldx);
-    }
+  for (int r0 = rl;;) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int r = r0 + k * RL;
@@ -209,6 +219,13 @@ __global__ void __launch_bounds__(GN_THREADS, 4) gn_apply_kernel(
         }
         *reinterpret_cast<uint4*>(yb + size_t(r) * ldy) = pack8s(f);
       }
+    }
+    r0 += 4 * RL;
+    if (r0 >= GN_CHUNK) break;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = r0 + k * RL;
+      if (r < GN_CHUNK) v[k] = *reinterpret_cast<const uint4*>(xb + size_t(r) * ldx);
     }
   }
 }
@@ -350,7 +367,7 @@ extern "C" int b200_groupnorm_nhwc_bf16(const void* x, int ldx, long long T, int
   if (rc) return rc;
   auto kern = silu ? gn_apply_kernel<true> : gn_apply_kernel<false>;
   return launch_pdl(kern, dim3(chunks, m.S), dim3(m.threads), 0, ST(stream),
-                    static_cast<const bf16*>(x), ldx, m.W, m.RL, cpg, groups,
+                    static_cast<const bf16*>(x), ldx, m.W, m.RL, cpg, groups, chunks,
                     static_cast<const float*>(stats), row_group, static_cast<const bf16*>(gamma),
                     static_cast<const bf16*>(beta), static_cast<bf16*>(y), ldy);
 }

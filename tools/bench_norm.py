@@ -47,6 +47,18 @@ for lvl, C in ((0, 320), (0, 640), (0, 960), (1, 640), (1, 1280), (1, 1920), (2,
     mk = lambda i: (lambda: ops.groupnorm_nhwc(xs[i], ys[i], g, b, lay.row_group, lay.lat_chunks, lay.L, ws, silu=True))
     report(f"groupnorm T={lay.T} C={C}", 2 * lay.T * C * 2, timeit([mk(0)]), timeit([mk(i) for i in range(nbuf)], 3 * nbuf))
 
+print("## GroupNorm + SiLU on the VAE decoder levels (512^2 + 1024^2 images: latents 64^2 + 128^2, levels x4 and x8)")
+for up, C in ((8, 128), (8, 256), (4, 256), (4, 512), (2, 512)):
+    sizes = [(64 * up, 64 * up), (128 * up, 128 * up)]
+    lay = LevelLayout(sizes, dev)
+    xs = [torch.randn(lay.T, C, device=dev).bfloat16() for _ in range(2)]
+    ys = [torch.empty_like(x) for x in xs]
+    g, b = torch.randn(C, device=dev).bfloat16(), torch.randn(C, device=dev).bfloat16()
+    ws = ops.groupnorm_workspace(lay.T, lay.L, dev)
+    mk = lambda i: (lambda: ops.groupnorm_nhwc(xs[i], ys[i], g, b, lay.row_group, lay.lat_chunks, lay.L, ws, silu=True))
+    report(f"groupnorm T={lay.T} C={C}", 2 * lay.T * C * 2, timeit([mk(0)], 10), timeit([mk(0), mk(1)], 10))
+    del xs, ys
+
 print("## LayerNorm rows")
 for T, D, kind in ((10240, 640, "affine"), (2560, 1280, "affine"), (14848, 1536, "mod"), (14848, 1536, "dual"),
                    (1998, 1536, "mod"), (59392, 1536, "mod")):
