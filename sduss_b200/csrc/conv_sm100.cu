@@ -13,23 +13,31 @@
 // Same warp roles / pipeline / epilogues as gemm_sm100.cu.
 #include "../../include/sduss_b200.h"
 #include "epilogue.cuh"
+#include <cstdlib>
+
 #include "host_util.h"
 
 namespace b200 {
 
 constexpr int CV_BM = 128, CV_BK = 64, CV_TW = 8, CV_TH = 16, CV_THREADS = 256;
 
-template <int BN, int EPI>
+// MT = 2: the CTA runs TWO M tiles (two entries of the tile list, any two pixel blocks) against ONE
+// weight tile per k-step. A 128 x 128 tile loads 32 KB of operands per 2.1 MFLOP, more than L2
+// delivers per SM (the 128-channel convolutions of the VAE decoder ran at 0.8 PFLOP/s); with two
+// M tiles the ratio is that of the 128 x 256 configuration (48 KB per 4.2 MFLOP).
+template <int BN, int EPI, int MT = 1>
 struct ConvCfg {
+  static_assert(MT == 1 || BN == 128, "two M tiles: 2 x 2 x 128 TMEM columns");
   // residual chunks are TMA-loaded into the output staging tiles and updated in place (see
   // gemm_sm100.cu): the residual epilogue costs no pipeline stage
-  static constexpr int kStages = (BN == 256) ? 4 : 5;
-  static constexpr int kABytes = CV_BM * CV_BK * 2;
+  static constexpr int kStages = (BN == 256 || MT == 2) ? 4 : 5;
+  static constexpr int kATile = CV_BM * CV_BK * 2;
+  static constexpr int kABytes = MT * kATile;
   static constexpr int kBBytes = BN * CV_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSmemBytes =
       kStages * kStageBytes + 2 * EPI_STAGE_BYTES + 1024 + 256;
-  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kTmemCols = 2 * MT * BN;
 };
 
 struct ConvArgs {
@@ -41,10 +49,10 @@ struct ConvArgs {
   int n_mtiles, Cin, Cout, stride;
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, int MT>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, int M_total) {
-  using Cfg = ConvCfg<BN, EPI>;
+  using Cfg = ConvCfg<BN, EPI, MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
@@ -62,7 +70,8 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_n = (a.Cout + BN - 1) / BN;
-  const int num_tiles = a.n_mtiles * tiles_n;
+  const int m_items = (a.n_mtiles + MT - 1) / MT;  // work item = MT consecutive M tiles x one N tile
+  const int num_tiles = m_items * tiles_n;
   const int cblocks = a.Cin / CV_BK;
   const int num_kb = 9 * cblocks;
 
@@ -95,23 +104,30 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
     int stage = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int4 tl = a.tiles[t / tiles_n];
+      const int m0 = (t / tiles_n) * MT;
+      const int nmt = min(MT, a.n_mtiles - m0);
       const int n0 = (t % tiles_n) * BN;
-      const CUtensorMap* im = a.in_maps + tl.x;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * CV_BK;
         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
         mbar_wait(&empty[stage], phase ^ 1);
         if (lane == 0) {
-          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-          void* dstA = smemA + stage * Cfg::kABytes;
-          if (a.stride == 1) {
-            tma_load_3d(dstA, im, &full[stage], c0, tl.z + dx, tl.y + dy);
-          } else {
-            // input pixel (2y+dy, 2x+dx) = (parity, half index): -1 -> (1, i-1); 0 -> (0, i); 1 -> (1, i)
-            const int py = dy == 0 ? 0 : 1, px = dx == 0 ? 0 : 1;
-            tma_load_5d(dstA, im, &full[stage], c0, px, tl.z + (dx < 0 ? -1 : 0), py,
-                        tl.y + (dy < 0 ? -1 : 0));
+          mbar_expect_tx(&full[stage], nmt * Cfg::kATile + Cfg::kBBytes);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            if (mt < nmt) {
+              const int4 tl = a.tiles[m0 + mt];
+              const CUtensorMap* im = a.in_maps + tl.x;
+              void* dstA = smemA + stage * Cfg::kABytes + mt * Cfg::kATile;
+              if (a.stride == 1) {
+                tma_load_3d(dstA, im, &full[stage], c0, tl.z + dx, tl.y + dy);
+              } else {
+                // input pixel (2y+dy, 2x+dx) = (parity, half index): -1 -> (1, i-1); 0 -> (0, i); 1 -> (1, i)
+                const int py = dy == 0 ? 0 : 1, px = dx == 0 ? 0 : 1;
+                tma_load_5d(dstA, im, &full[stage], c0, px, tl.z + (dx < 0 ? -1 : 0), py,
+                            tl.y + (dy < 0 ? -1 : 0));
+              }
+            }
           }
           tma_load_2d(smemB + stage * Cfg::kBBytes, &tmW, &full[stage], kb * CV_BK, n0);
         }
@@ -129,17 +145,23 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
       const int acc = it & 1;
       mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
+      const uint32_t d_tmem = tmem_base + acc * (MT * BN);
+      const int nmt = min(MT, a.n_mtiles - (t / tiles_n) * MT);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint64_t da = make_sdesc_sw128(smem_u32(smemA + stage * Cfg::kABytes));
           const uint64_t db = make_sdesc_sw128(smem_u32(smemB + stage * Cfg::kBBytes));
 #pragma unroll
-          for (int k = 0; k < CV_BK / 16; ++k)
-            umma_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc,
-                    (kb | k) != 0 ? 1u : 0u);
+          for (int mt = 0; mt < MT; ++mt) {
+            if (mt < nmt) {
+              const uint64_t da = make_sdesc_sw128(smem_u32(smemA + stage * Cfg::kABytes + mt * Cfg::kATile));
+#pragma unroll
+              for (int k = 0; k < CV_BK / 16; ++k)
+                umma_ss(d_tmem + mt * BN, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc,
+                        (kb | k) != 0 ? 1u : 0u);
+            }
+          }
           umma_commit(&empty[stage]);
           if (kb == num_kb - 1) umma_commit(&tfull[acc]);
         }
@@ -163,63 +185,70 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
-      const int4 tl = a.tiles[t / tiles_n];
-      const int4 ld = a.lat[tl.x];
+      const int m0 = (t / tiles_n) * MT;
+      const int nmt = min(MT, a.n_mtiles - m0);
       const int n0 = (t % tiles_n) * BN;
-      if (has_resid && leader) {  // residual chunks 0 and 1 fly while the main loop finishes
-        tma_store_wait_read<0>();   // both staging tiles have left for HBM (previous tile)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          if (c < NCH && n0 + c * 64 < a.Cout) {
-            const int rb = (chunk_ctr + c) & 1;
-            mbar_expect_tx(&rfull[rb], EPI_STAGE_BYTES);
-            tma_load_3d(stageC + rb * EPI_STAGE_BYTES, a.res_maps + tl.x, &rfull[rb], n0 + c * 64, tl.z, tl.y);
-          }
-        }
-      }
-      __syncwarp();
-      mbar_wait(&tfull[acc], (it >> 1) & 1);
-      tc_fence_after();
-      const int y = tl.y + r / CV_TW, x = tl.z + r % CV_TW;
-      const bool row_ok = y < ld.y && x < ld.z;
-      const int row = row_ok ? ld.x + y * ld.z + x : M_total;
-      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < NCH; ++c) {
-        const int nc = n0 + c * 64;
-        if (nc >= a.Cout) break;
-        const int b = (chunk_ctr + c) & 1;
-        if (has_resid && c >= 1 && c + 1 < NCH && nc + 64 < a.Cout) {
-          // residual of chunk c + 1 -> the tile chunk c - 1 was stored from, once that store has
-          // read it; it lands while this chunk is processed
-          if (leader) {
-            tma_store_wait_read<0>();
-            mbar_expect_tx(&rfull[b ^ 1], EPI_STAGE_BYTES);
-            tma_load_3d(stageC + (b ^ 1) * EPI_STAGE_BYTES, a.res_maps + tl.x, &rfull[b ^ 1], nc + 64, tl.z, tl.y);
+      for (int mt = 0; mt < nmt; ++mt) {
+        const int4 tl = a.tiles[m0 + mt];
+        const int4 ld = a.lat[tl.x];
+        if (has_resid && leader) {  // residual chunks 0 and 1 fly while the main loop finishes
+          tma_store_wait_read<0>();   // both staging tiles have left for HBM (previous tile)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            if (c < NCH && n0 + c * 64 < a.Cout) {
+              const int rb = (chunk_ctr + c) & 1;
+              mbar_expect_tx(&rfull[rb], EPI_STAGE_BYTES);
+              tma_load_3d(stageC + rb * EPI_STAGE_BYTES, a.res_maps + tl.x, &rfull[rb], n0 + c * 64, tl.z, tl.y);
+            }
           }
-          __syncwarp();
         }
-        float v[64];
-        tmem_ld32(t_row + c * 64, reinterpret_cast<uint32_t*>(v));
-        tmem_ld32(t_row + c * 64 + 32, reinterpret_cast<uint32_t*>(v) + 32);
-        tmem_wait_ld();
-        if (has_resid) {
-          mbar_wait(&rfull[b], (b ? ruse1 : ruse0) & 1);
-          if (b) ++ruse1; else ++ruse0;
+        __syncwarp();
+        if (mt == 0) {
+          mbar_wait(&tfull[acc], (it >> 1) & 1);
+          tc_fence_after();
         }
-        epilogue_math64<EPI>(e, v, row, row_ok, nc, a.Cout, has_resid ? stageC + b * EPI_STAGE_BYTES : nullptr, r);
-        epilogue_stage64<EPI>(stageC + b * EPI_STAGE_BYTES, v, r);
-        fence_proxy_async();
-        if (leader) tma_store_wait_read<0>();
-        named_barrier<1, 128>();
-        if (leader) {
-          tma_store_3d(a.out_maps + tl.x, stageC + b * EPI_STAGE_BYTES, nc, tl.z, tl.y);
-          tma_store_commit();
+        const int y = tl.y + r / CV_TW, x = tl.z + r % CV_TW;
+        const bool row_ok = y < ld.y && x < ld.z;
+        const int row = row_ok ? ld.x + y * ld.z + x : M_total;
+        const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * (MT * BN) + mt * BN;
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          const int nc = n0 + c * 64;
+          if (nc >= a.Cout) break;
+          const int b = (chunk_ctr + c) & 1;
+          if (has_resid && c >= 1 && c + 1 < NCH && nc + 64 < a.Cout) {
+            // residual of chunk c + 1 -> the tile chunk c - 1 was stored from, once that store has
+            // read it; it lands while this chunk is processed
+            if (leader) {
+              tma_store_wait_read<0>();
+              mbar_expect_tx(&rfull[b ^ 1], EPI_STAGE_BYTES);
+              tma_load_3d(stageC + (b ^ 1) * EPI_STAGE_BYTES, a.res_maps + tl.x, &rfull[b ^ 1], nc + 64, tl.z, tl.y);
+            }
+            __syncwarp();
+          }
+          float v[64];
+          tmem_ld32(t_row + c * 64, reinterpret_cast<uint32_t*>(v));
+          tmem_ld32(t_row + c * 64 + 32, reinterpret_cast<uint32_t*>(v) + 32);
+          tmem_wait_ld();
+          if (has_resid) {
+            mbar_wait(&rfull[b], (b ? ruse1 : ruse0) & 1);
+            if (b) ++ruse1; else ++ruse0;
+          }
+          epilogue_math64<EPI>(e, v, row, row_ok, nc, a.Cout, has_resid ? stageC + b * EPI_STAGE_BYTES : nullptr, r);
+          epilogue_stage64<EPI>(stageC + b * EPI_STAGE_BYTES, v, r);
+          fence_proxy_async();
+          if (leader) tma_store_wait_read<0>();
+          named_barrier<1, 128>();
+          if (leader) {
+            tma_store_3d(a.out_maps + tl.x, stageC + b * EPI_STAGE_BYTES, nc, tl.z, tl.y);
+            tma_store_commit();
+          }
         }
-      }
-      {
-        const int left = (a.Cout - n0 + 63) / 64;
-        chunk_ctr += uint32_t(left < NCH ? left : NCH);
+        {
+          const int left = (a.Cout - n0 + 63) / 64;
+          chunk_ctr += uint32_t(left < NCH ? left : NCH);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -236,11 +265,11 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
   }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int MT>
 static int launch_conv(const CUtensorMap& tmW, const ConvArgs& a, const EpiArgs& e, int M_total,
                        int num_sms, cudaStream_t stream) {
-  using Cfg = ConvCfg<BN, EPI>;
-  auto kern = conv3x3_kernel<BN, EPI>;
+  using Cfg = ConvCfg<BN, EPI, MT>;
+  auto kern = conv3x3_kernel<BN, EPI, MT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t err =
@@ -248,18 +277,18 @@ static int launch_conv(const CUtensorMap& tmW, const ConvArgs& a, const EpiArgs&
     if (err != cudaSuccess) return static_cast<int>(err);
     configured = true;
   }
-  const int tiles = a.n_mtiles * ((a.Cout + BN - 1) / BN);
+  const int tiles = ((a.n_mtiles + MT - 1) / MT) * ((a.Cout + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
   return launch_pdl(kern, dim3(grid), dim3(CV_THREADS), Cfg::kSmemBytes, stream, tmW, a, e, M_total);
 }
 
-template <int BN>
+template <int BN, int MT>
 static int dispatch_conv(int epi, const CUtensorMap& tmW, const ConvArgs& a, const EpiArgs& e,
                          int M_total, int sms, cudaStream_t st) {
   switch (epi) {
-    case EPI_BIAS: return launch_conv<BN, EPI_BIAS>(tmW, a, e, M_total, sms, st);
-    case EPI_GATE_RESID: return launch_conv<BN, EPI_GATE_RESID>(tmW, a, e, M_total, sms, st);
-    case EPI_ROWVEC: return launch_conv<BN, EPI_ROWVEC>(tmW, a, e, M_total, sms, st);
+    case EPI_BIAS: return launch_conv<BN, EPI_BIAS, MT>(tmW, a, e, M_total, sms, st);
+    case EPI_GATE_RESID: return launch_conv<BN, EPI_GATE_RESID, MT>(tmW, a, e, M_total, sms, st);
+    case EPI_ROWVEC: return launch_conv<BN, EPI_ROWVEC, MT>(tmW, a, e, M_total, sms, st);
     default: return B200_ERR_UNSUPPORTED;
   }
 }
@@ -335,6 +364,11 @@ extern "C" int b200_conv3x3_bf16(const void* in_maps_dev, const void* out_maps_d
   e.rms_wq = nullptr; e.rms_wk = nullptr; e.rms_q_cols = 0; e.rms_k_cols = 0;
   e.rms_eps = 0.f; e.q_scale = 1.f;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
-  return bn256 ? dispatch_conv<256>(epi_mode, tmW, a, e, M_total, sms, st)
-               : dispatch_conv<128>(epi_mode, tmW, a, e, M_total, sms, st);
+  if (bn256) return dispatch_conv<256, 1>(epi_mode, tmW, a, e, M_total, sms, st);
+  // 128-wide tiles with enough M tiles to keep every SM busy for several rounds of pairs: two M
+  // tiles per CTA share each weight tile (halves the operand bytes per FLOP, see ConvCfg)
+  static const bool no_mt2 = []() { const char* v = getenv("SDUSS_B200_CONV_NO_MT2"); return v && v[0] == '1'; }();
+  const long items2 = long((n_mtiles + 1) / 2) * ((Cout + 127) / 128);
+  if (!no_mt2 && items2 >= 4L * sms) return dispatch_conv<128, 2>(epi_mode, tmW, a, e, M_total, sms, st);
+  return dispatch_conv<128, 1>(epi_mode, tmW, a, e, M_total, sms, st);
 }

@@ -39,6 +39,10 @@ def _rand(shape, seed, scale=1.0):
     # tile (Cout = 320 = 256 + 64; Cout = 8): regression for the epilogue staging-buffer reuse
     ([(128, 128), (128, 128), (64, 64)], 64, 320, 1),
     ([(128, 128), (128, 128)], 64, 8, 1),
+    # enough 128-wide work items for the two-M-tiles-per-CTA variant (VAE decoder levels), with an
+    # odd number of M tiles (the last pair is half empty), stride 1 and 2
+    ([(512, 320), (16, 8)], 64, 128, 1),
+    ([(1024, 640), (32, 16)], 64, 64, 2),
 ])
 def test_conv3x3(cuda, sizes, cin, cout, stride):
     from sduss_b200 import ops
