@@ -365,8 +365,10 @@ extern "C" int b200_conv3x3_bf16(const void* in_maps_dev, const void* out_maps_d
   e.rms_eps = 0.f; e.q_scale = 1.f;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   if (bn256) return dispatch_conv<256, 1>(epi_mode, tmW, a, e, M_total, sms, st);
-  // 128-wide tiles with enough M tiles to keep every SM busy for several rounds of pairs: two M
-  // tiles per CTA share each weight tile (halves the operand bytes per FLOP, see ConvCfg)
+  // 128-wide tiles with several rounds of tile pairs: two M tiles per CTA share each weight tile
+  // (halves the operand bytes per FLOP, see ConvCfg). Preferring this over 256-wide tiles where it
+  // saves a round (Cout = 320: 3 x 128 columns in 4 rounds instead of 2 x 256 in 5) was measured
+  // and is slower (SDXL level 0: 834 -> 721 TFLOP/s): not done.
   static const bool no_mt2 = []() { const char* v = getenv("SDUSS_B200_CONV_NO_MT2"); return v && v[0] == '1'; }();
   const long items2 = long((n_mtiles + 1) / 2) * ((Cout + 127) / 128);
   if (!no_mt2 && items2 >= 4L * sms) return dispatch_conv<128, 2>(epi_mode, tmW, a, e, M_total, sms, st);
