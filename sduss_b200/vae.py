@@ -17,7 +17,7 @@ packed attention kernel), `b200_softmax_rows`, `b200_scatter_nchw`. No PyTorch a
 """
 import math
 from dataclasses import dataclass, fields
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 

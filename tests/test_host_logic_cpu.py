@@ -286,3 +286,28 @@ def test_registry_plugin_overrides_only_the_hot_path(monkeypatch):
     import pytest
     with pytest.raises(ValueError):
         plugin.make_b200_pipeline(FakeReference, "sd15")
+
+
+def test_post_inference_contract_without_gpu():
+    """post_inference mirrors the reference's error behaviour: no decoder attached -> loud failure
+    (never a silent fallback), output_type "latent" -> NotImplementedError (xl_esymred.py:461)."""
+    import pytest
+    from sduss_b200.pipelines import B200PipelineOutput, B200StableDiffusionXLPipeline
+    pipe = B200StableDiffusionXLPipeline(None, None)
+    with pytest.raises(RuntimeError):
+        pipe.post_inference({"512": []})
+    pipe.vae = object()
+    with pytest.raises(NotImplementedError):
+        pipe.post_inference({"512": []}, output_type="latent")
+    out = B200PipelineOutput(images="x")
+    assert out.images == "x" and out.nsfw_content_detected is None
+
+
+def test_vae_decoder_config_from_diffusers_like_config():
+    from types import SimpleNamespace
+    from sduss_b200.vae import VAEDecoderConfig
+    hf = dict(latent_channels=16, block_out_channels=[128, 256, 512, 512], scaling_factor=1.5305,
+              shift_factor=0.0609, use_post_quant_conv=False, sample_size=1024, act_fn="silu")
+    for cfg in (VAEDecoderConfig.from_any(hf), VAEDecoderConfig.from_any(SimpleNamespace(**hf))):
+        assert cfg.latent_channels == 16 and cfg.block_out_channels == (128, 256, 512, 512)
+        assert cfg.shift_factor == 0.0609 and cfg.use_post_quant_conv is False and cfg.layers_per_block == 2
