@@ -374,7 +374,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
 #ifdef ATT_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_begin = clock64();
-    long long n_steps = 0;
+    long long n_steps = 0, n_units = 0, wait_s_first = 0, wait_o_max = 0;
 #endif
     for (uint32_t it = 0;; ++it) {
       const int u = take_unit(it);
@@ -493,10 +493,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
         ATT_T(c6);
         ATT_ACC(0, c0, c1); ATT_ACC(1, c1, c2); ATT_ACC(2, c2, c3); ATT_ACC(3, c3, c4);
         ATT_ACC(4, c4, c5); ATT_ACC(5, c5, c6);
+#ifdef ATT_TIMING
+        if (j == 0) wait_s_first += c1 - c0;   // the unit-boundary share of wait_s
+        if (c5 - c4 > wait_o_max) wait_o_max = c5 - c4;
+#endif
       }
       g += uint32_t(w.n_tiles);
 #ifdef ATT_TIMING
       n_steps += w.n_tiles;
+      ++n_units;
 #endif
       // Output of the unit. The first P V of the next unit overwrites O_t, but it needs p_full of
       // that unit, which these warps only give after this read has completed.
@@ -532,6 +537,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
       for (int i = 0; i < 7; ++i) d[i] = tacc[i];
       d[7] = n_steps;
       d[8] = clock64() - t_begin;
+      d[9] = wait_s_first;
+      d[10] = n_units;
+      d[11] = wait_o_max;
     }
 #endif
   }

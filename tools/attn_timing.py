@@ -35,3 +35,8 @@ for t in (0, 1):
     print(f"tile {'AB'[t]}: CTAs {len(x)}, steps {tiles}, cycles/step total {x[:, 8].sum() / tiles:.0f}")
     for i, nme in enumerate(names):
         print(f"   {nme:24s} {x[:, i].sum() / tiles:8.1f} clk/step")
+    if x[:, 10].sum() > 0:
+        units = x[:, 10].sum()
+        print(f"   wait_s on the FIRST step of a unit: {x[:, 9].sum() / units:8.0f} clk per unit ({units} units, "
+              f"{100 * x[:, 9].sum() / max(1, x[:, 0].sum()):.0f} % of all wait_s); steady-state wait_s "
+              f"{(x[:, 0].sum() - x[:, 9].sum()) / max(1, tiles - units):.1f} clk/step; longest single wait_o {x[:, 11].max()} clk")
