@@ -68,7 +68,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Probe first: mbarrier.try_wait costs ~143 cycles even when the phase is already complete,
+// test_wait ~15 (tools/micro/handover.cu, profiles/r01_micro_handover.txt). Most waits of the
+// pipelines here find their data ready (the MMA / TMA was issued most of a step earlier), and in
+// the attention softmax two of them sit on every step's dependent chain.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_test_wait(bar, parity)) return;
   while (!mbar_try_wait(bar, parity)) {
   }
 }
