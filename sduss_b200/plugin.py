@@ -14,6 +14,9 @@ overrides exactly the two members that belong to the hot path:
 Everything else -- get_sampling_params_cls, __post_init__, prepare_inference (text encoders),
 post_inference (VAE), class attributes -- is inherited untouched, so `_ModelRunner`
 (sduss/worker/runner/_model_runner.py:109-114,238-264) cannot tell the difference.
+With `b200_vae=True` the `vae` sub-module is additionally wrapped in `B200VAEProxy`: the inherited
+post_inference is still the reference's code, but its `self.vae.decode(...)` runs on the B200
+kernels.
 """
 from typing import Type
 
@@ -24,7 +27,7 @@ _KINDS = {
 }
 
 
-def make_b200_pipeline(reference_cls: Type, kind: str, device: str = "cuda") -> Type:
+def make_b200_pipeline(reference_cls: Type, kind: str, device: str = "cuda", b200_vae: bool = False) -> Type:
     if kind not in _KINDS:
         raise ValueError(f"kind must be one of {sorted(_KINDS)}, got {kind!r}")
     module_key, mod_name, model_name, step_name = _KINDS[kind]
@@ -40,6 +43,11 @@ def make_b200_pipeline(reference_cls: Type, kind: str, device: str = "cuda") -> 
             assert module is not None, f"sub_modules has no {module_key!r}"
             model_cls = getattr(importlib.import_module(mod_name), model_name)
             sub_modules[module_key] = model_cls.from_diffusers(module, device=device)
+            if b200_vae and sub_modules.get("vae") is not None:
+                # row f-4: the inherited post_inference keeps calling self.vae.decode(...), which
+                # now runs on the B200 kernels (sduss_b200.vae.B200VAEProxy)
+                from .vae import B200VAEProxy
+                sub_modules["vae"] = B200VAEProxy(sub_modules["vae"], device=device)
             return cls(**sub_modules)
 
         def _b200_step(self):

@@ -166,6 +166,13 @@ class B200VAEDecoder(torch.nn.Module):
             A, b = Wpq @ A, Wpq @ b + sd["post_quant_conv.bias"].double()
         self.pre_w = A.float().contiguous().to(dev)
         self.pre_b = b.float().contiguous().to(dev)
+        # the same map for latents the caller has already un-scaled (the reference's post_inference
+        # does `latents / scaling_factor (+ shift_factor)` itself before `vae.decode`): B200VAEProxy
+        Au, bu = torch.eye(C, dtype=torch.float64), torch.zeros(C, dtype=torch.float64)
+        if cfg.use_post_quant_conv:
+            Au, bu = Wpq, sd["post_quant_conv.bias"].double()
+        self.pre_w_unscaled = Au.float().contiguous().to(dev)
+        self.pre_b_unscaled = bu.float().contiguous().to(dev)
         # conv_in as a GEMM on im2col rows: [Cout, Cin*9] padded to a multiple of 64
         k_in = C * 9
         self.k_in_pad = ((k_in + 63) // 64) * 64
@@ -262,14 +269,22 @@ class B200VAEDecoder(torch.nn.Module):
                  epi=ops.EPI_GATE_RESID, resid=x)
 
     # ------------------------------------------------------------------ forward
-    def _plan(self, latents) -> _Plan:
+    def _plan(self, latents, unscaled=False) -> _Plan:
         comp = tuple((res, t.shape[0], t.shape[-2], t.shape[-1])
                      for res, t in latents.items() if t is not None and t.shape[0] > 0)
-        return self._plans.get(comp, lambda: _Plan(self, comp))
+
+        def make():
+            pl = _Plan(self, comp)
+            pl.unscaled = unscaled
+            return pl
+        return self._plans.get((comp, unscaled), make)
 
     @torch.no_grad()
-    def decode(self, latents: Dict[str, torch.Tensor], _borrow: bool = False) -> Dict[str, torch.Tensor]:
-        pl = self._plan(latents)
+    def decode(self, latents: Dict[str, torch.Tensor], _borrow: bool = False,
+               unscaled: bool = False) -> Dict[str, torch.Tensor]:
+        """unscaled=True: `latents` are already `latents / scaling_factor (+ shift_factor)` (what the
+        reference hands to `vae.decode`); default: scheduler-space latents, un-scaled here."""
+        pl = self._plan(latents, unscaled)
         for res, _, _, _ in pl.comp:
             pl.stage_in[res].copy_(latents[res])
         ops.run_plan(self, pl)
@@ -279,7 +294,9 @@ class B200VAEDecoder(torch.nn.Module):
         cfg, w, ch = self.cfg, self.w, self.ch
         L, l0 = pl.L, pl.levels[0]
         C = cfg.latent_channels
-        ops.latent_affine(pl.in_ptr, pl.z_ptr, l0.desc, L, l0.max_pixels, C, C, self.pre_w, self.pre_b)
+        pre_w, pre_b = ((self.pre_w_unscaled, self.pre_b_unscaled) if getattr(pl, "unscaled", False)
+                        else (self.pre_w, self.pre_b))
+        ops.latent_affine(pl.in_ptr, pl.z_ptr, l0.desc, L, l0.max_pixels, C, C, pre_w, pre_b)
         cols = pl.buf("im2col", l0.T, self.k_in_pad)
         ops.pack_im2col3x3(pl.z_ptr, l0.desc, L, l0.max_pixels, C, cols)
         x = ops.gemm(cols, w["decoder.conv_in.weight"], pl.buf("act0_a", l0.T, ch[0]),
@@ -311,3 +328,25 @@ def postprocess(image: torch.Tensor) -> torch.Tensor:
     """VaeImageProcessor.postprocess up to the float image (denormalize, NHWC); the PIL conversion
     and the mp.Queue hand-over stay with the reference's runner (runner/wrappers.py:58-66)."""
     return (image.float() / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1)
+
+
+class B200VAEProxy:
+    """Stands in for the diffusers AutoencoderKL a sduss pipeline holds as `self.vae`, so that the
+    reference's own `post_inference` (pipeline_stable_diffusion_xl_esymred.py:406-462,
+    pipeline_stable_diffusion_3_esymred.py:391-415) runs unmodified: `decode(z)` takes the latents
+    the reference has already un-scaled and returns `(image,)` / an object with `.sample`; every
+    other attribute (`config`, `dtype`, `to`, ...) is the wrapped module's."""
+
+    def __init__(self, vae, decoder: "B200VAEDecoder" = None, device="cuda"):
+        self.__dict__["_vae"] = vae
+        self.__dict__["_decoder"] = decoder if decoder is not None else B200VAEDecoder.from_diffusers(vae, device)
+
+    def __getattr__(self, name):
+        return getattr(self.__dict__["_vae"], name)
+
+    def decode(self, z, return_dict: bool = True, generator=None):
+        image = self.__dict__["_decoder"].decode({"_": z}, unscaled=True)["_"]
+        if not return_dict:
+            return (image,)
+        from types import SimpleNamespace
+        return SimpleNamespace(sample=image)

@@ -311,3 +311,23 @@ def test_vae_decoder_config_from_diffusers_like_config():
     for cfg in (VAEDecoderConfig.from_any(hf), VAEDecoderConfig.from_any(SimpleNamespace(**hf))):
         assert cfg.latent_channels == 16 and cfg.block_out_channels == (128, 256, 512, 512)
         assert cfg.shift_factor == 0.0609 and cfg.use_post_quant_conv is False and cfg.layers_per_block == 2
+
+
+def test_vae_proxy_forwards_attributes_and_wraps_decode():
+    """B200VAEProxy without a GPU: attribute access goes to the wrapped vae, decode() goes to the
+    B200 decoder with unscaled=True and returns the reference's two result shapes."""
+    from types import SimpleNamespace
+    from sduss_b200.vae import B200VAEProxy
+    calls = []
+
+    class FakeDecoder:
+        def decode(self, latents, unscaled=False, _borrow=False):
+            calls.append((list(latents), unscaled))
+            return {k: ("img", v) for k, v in latents.items()}
+
+    vae = SimpleNamespace(config=SimpleNamespace(scaling_factor=0.5), dtype="float32")
+    proxy = B200VAEProxy(vae, FakeDecoder())
+    assert proxy.config.scaling_factor == 0.5 and proxy.dtype == "float32"
+    assert proxy.decode("z", return_dict=False) == (("img", "z"),)
+    assert proxy.decode("z").sample == ("img", "z")
+    assert calls == [(["_"], True), (["_"], True)]

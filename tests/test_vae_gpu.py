@@ -112,3 +112,26 @@ def test_post_inference_sets_outputs(cuda):
             img = r.output.images
             assert img.shape == (3, 8 * int(res) // 8, 8 * int(res) // 8) and 0 <= img.min() and img.max() <= 1
             assert (img.cpu() - ov.postprocess(ref[res][i])).abs().max() < 0.06
+
+
+def test_vae_proxy_decodes_unscaled_latents_like_vae_decode(cuda):
+    """B200VAEProxy.decode(z) == reference `vae.decode(z)` semantics: z is already un-scaled
+    (xl_esymred.py:441 / 3_esymred.py:408 do that before calling decode)."""
+    from types import SimpleNamespace
+    from oracle import vae_decoder as ov
+    from sduss_b200.vae import B200VAEDecoder, B200VAEProxy
+    cfg = ov.vae_tiny_config(latent_channels=16, shift=0.0609, pq=True)
+    sd = {k: v.bfloat16().float() for k, v in ov.init_vae_decoder_weights(cfg, 0).items()}
+    fake_vae = SimpleNamespace(config=SimpleNamespace(scaling_factor=cfg.scaling_factor), marker=7)
+    proxy = B200VAEProxy(fake_vae, B200VAEDecoder(sd, cfg, device=cuda))
+    assert proxy.marker == 7 and proxy.config.scaling_factor == cfg.scaling_factor
+    g = torch.Generator().manual_seed(9)
+    lat = (torch.randn(2, 16, 16, 8, generator=g) * 0.5).bfloat16()
+    z = ov.unscale_latents(cfg, lat.float()).bfloat16()          # what the reference passes in
+    (img,) = proxy.decode(z.cuda(), return_dict=False)
+    assert proxy.decode(z.cuda()).sample.shape == img.shape == (2, 3, 128, 64)
+    ref = ov.decode_single(sd, cfg, z.float())
+    for i in range(2):
+        a, b = img[i].float().cpu().flatten(), ref[i].flatten()
+        assert torch.nn.functional.cosine_similarity(a, b, dim=0).item() >= 0.999
+        assert (a - b).abs().max() <= 0.06 * (b.max() - b.min())
