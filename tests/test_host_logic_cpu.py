@@ -331,3 +331,36 @@ def test_vae_proxy_forwards_attributes_and_wraps_decode():
     assert proxy.decode("z", return_dict=False) == (("img", "z"),)
     assert proxy.decode("z").sample == ("img", "z")
     assert calls == [(["_"], True), (["_"], True)]
+
+
+def test_vae_decoder_host_relayout_matches_oracle_semantics():
+    """B200VAEDecoder's host-side weight re-layout (no kernels run): the folded per-pixel affine
+    map equals `post_quant_conv(latents / scaling_factor + shift_factor)` of the oracle (and its
+    `unscaled` twin equals `post_quant_conv(z)`), conv weights are [Cout, (ky, kx, c)], conv_out is
+    zero-padded to 64 channels, the value bias is moved out of the fused qkv bias."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import vae_decoder as ov
+    from sduss_b200.vae import B200VAEDecoder
+    cfg = ov.vae_tiny_config(latent_channels=4, shift=0.25, pq=True)
+    sd = ov.init_vae_decoder_weights(cfg, 0)
+    m = B200VAEDecoder(sd, cfg, device="cpu")
+    g = torch.Generator().manual_seed(0)
+    lat = torch.randn(1, 4, 5, 7, generator=g)
+    ref = F.conv2d(ov.unscale_latents(cfg, lat), sd["post_quant_conv.weight"], sd["post_quant_conv.bias"])
+    got = torch.einsum("oc,nchw->nohw", m.pre_w, lat) + m.pre_b[None, :, None, None]
+    assert torch.allclose(got, ref, atol=1e-5)
+    ref_u = F.conv2d(lat, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"])
+    got_u = torch.einsum("oc,nchw->nohw", m.pre_w_unscaled, lat) + m.pre_b_unscaled[None, :, None, None]
+    assert torch.allclose(got_u, ref_u, atol=1e-5)
+    name = "decoder.mid_block.resnets.0.conv1"
+    w = sd[name + ".weight"]
+    assert torch.equal(m.w[name + ".weight"].float().view(w.shape[0], 3, 3, w.shape[1]),
+                       w.permute(0, 2, 3, 1).bfloat16().float())
+    wo = m.w["decoder.conv_out.weight"]
+    assert wo.shape[0] == m.n_out_pad == 64 and torch.count_nonzero(wo[cfg.out_channels:]) == 0
+    a = "decoder.mid_block.attentions.0"
+    C = cfg.block_out_channels[-1]
+    assert torch.count_nonzero(m.w[a + ".qkv.bias"][2 * C:]) == 0
+    assert torch.equal(m.w[a + ".v.bias"].float(), sd[a + ".to_v.bias"].bfloat16().float())
+    assert m.w["decoder.conv_in.weight"].shape == (C, 64)      # K = 4 * 9 = 36 padded to 64
