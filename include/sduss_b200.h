@@ -150,24 +150,55 @@ int b200_sd3_patchify(const uint64_t* lat_ptr, const int32_t* desc, int n_latent
 int b200_sd3_unpatchify(const void* tokens, int ldt, const int32_t* desc, int n_latents,
                         int max_tokens, int C, int p, const uint64_t* out_ptr, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Request-state kernels. Their per-request descriptors are HOST arrays that travel inside the
+ * kernel parameter block (32 requests per launch, longer lists are split): a denoising step issues
+ * no host->device copy and never drains the stream. The reference builds `torch.tensor(sigmas)` on
+ * the host and `.to(device)`s it 2-3 times per resolution and step
+ * (scheduling_euler_discrete.py:176,213,254; scheduling_flow_match_euler_discrete.py:183-189).
+ * ---------------------------------------------------------------------------------------- */
+enum B200DType { B200_DT_BF16 = 0, B200_DT_F16 = 1, B200_DT_F32 = 2 };
+
+typedef struct B200LatentRef {
+  const void* src;    /* DEVICE: current latent of the request, `elems` contiguous elements   */
+  void* dst;          /* DEVICE: where the updated latent goes (step only; may equal src)     */
+  int64_t elems;
+  int64_t off_a;      /* gather: element offset of the (uncond) copy in the staging buffer;   */
+                      /* step: element offset of the uncond prediction in eps (cfg only)      */
+  int64_t off_b;      /* gather: offset of the CFG duplicate, or -1; step: cond prediction    */
+  float sigma;        /* sigmas[_step_index]                                                  */
+  float sigma_next;   /* sigmas[_step_index + 1] (step only)                                  */
+} B200LatentRef;
+
+/* Gathers the latents of all requests (dtype: B200DType of the latents) into the model's bf16
+ * input staging buffer, writing each twice under CFG, and -- scale_input != 0 -- applies
+ * EulerDiscreteScheduler.batch_scale_model_input, x / sqrt(sigma^2 + 1), with the reference's
+ * rounding (sigma and every op in the latent dtype; scheduling_euler_discrete.py:161-184).
+ * Replaces the per-resolution torch.cat / torch.cat([x] * 2) of
+ * pipeline_stable_diffusion_3_esymred.py:270-291 and pipeline_stable_diffusion_xl_esymred.py:300-330. */
+int b200_gather_latents(const B200LatentRef* reqs_host, int n_requests, int dtype,
+                        int scale_input, void* staging_bf16, void* stream);
+
 /* Fused CFG combine + scheduler update, one pass over the latents of all requests.
  *   mode 0: flow-match Euler (scheduling_flow_match_euler_discrete.py:159-203)
  *   mode 1: Euler, epsilon prediction; mode 2: Euler, v_prediction
  *           (scheduling_euler_discrete.py:187-274)
- * cfg != 0: eps = u + guidance * (c - u) (pipeline_stable_diffusion_xl_esymred.py:382-385).
- * desc: int64 [R][4] = {element offset of request r in x/out, elements, offset of the uncond
- * prediction in eps, offset of the cond prediction in eps}; sigmas: fp32 [R][2] = {sigma,
- * sigma_next}. eps, x, out bf16. Arithmetic order and rounding follow the reference
- * (fp32 update, bf16 result). */
-int b200_cfg_scheduler_step(const void* eps, const void* x, void* out, const int64_t* desc,
-                            const float* sigmas, int n_requests, long long max_elems,
-                            float guidance, int cfg, int mode, void* stream);
+ * cfg != 0: eps = u + guidance * (c - u) (pipeline_stable_diffusion_xl_esymred.py:382-385) in the
+ * arithmetic of eps_dtype (B200_DT_BF16 or B200_DT_F32), each op rounded like the torch tensor op.
+ * The update runs in fp32 on the upcast sample in the reference's op order; the result is stored
+ * in the latent's dtype (the reference stores the model-output dtype: identical when they agree). */
+int b200_cfg_scheduler_step(const void* eps, int eps_dtype, const B200LatentRef* reqs_host,
+                            int n_requests, int latent_dtype, float guidance, int cfg, int mode,
+                            void* stream);
 
-/* y = x / sqrt(sigma_l^2 + 1) per latent (batch_scale_model_input,
- * scheduling_euler_discrete.py:161-184). desc: int64 [L][2] = {element offset, elements};
- * sigmas fp32 [L]. */
-int b200_euler_scale_input(const void* x, void* y, const int64_t* desc, const float* sigmas,
-                           int n_latents, long long max_elems, void* stream);
+/* dst[0:n] = vals_host[0:n] (fp32): the per-latent timesteps of the step. */
+int b200_write_f32(void* dst, const float* vals_host, int n, void* stream);
+
+/* dst + i * dst_stride_bytes <- src_host[i][0 : bytes_each), i < n: gathers per-request
+ * conditioning (cached projected text context, pooled embeddings) into the packed per-step
+ * buffers. src_host: HOST array of device pointers; sizes multiples of 4 bytes. */
+int b200_gather_rows(void* dst, long long dst_stride_bytes, const void* const* src_host, int n,
+                     long long bytes_each, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * SDXL UNet path, packed NHWC layout [sum_i H_i*W_i, C] bf16.

@@ -47,6 +47,18 @@ class AttnSource(ctypes.Structure):
     ]
 
 
+class LatentRef(ctypes.Structure):
+    """Mirror of B200LatentRef (include/sduss_b200.h): one request of a gather / step launch."""
+    _fields_ = [
+        ("src", c_void_p), ("dst", c_void_p), ("elems", ctypes.c_int64),
+        ("off_a", ctypes.c_int64), ("off_b", ctypes.c_int64),
+        ("sigma", c_float), ("sigma_next", c_float),
+    ]
+
+
+DT_BF16, DT_F16, DT_F32 = 0, 1, 2
+
+
 class B200Error(RuntimeError):
     pass
 
@@ -80,10 +92,12 @@ SIGNATURES = {
                           c_void_p],
     "b200_sd3_unpatchify": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                             c_void_p],
-    "b200_cfg_scheduler_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                                ctypes.c_longlong, c_float, c_int, c_int, c_void_p],
-    "b200_euler_scale_input": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, ctypes.c_longlong,
-                               c_void_p],
+    "b200_gather_latents": [ctypes.POINTER(LatentRef), c_int, c_int, c_int, c_void_p, c_void_p],
+    "b200_cfg_scheduler_step": [c_void_p, c_int, ctypes.POINTER(LatentRef), c_int, c_int, c_float,
+                                c_int, c_int, c_void_p],
+    "b200_write_f32": [c_void_p, ctypes.POINTER(c_float), c_int, c_void_p],
+    "b200_gather_rows": [c_void_p, ctypes.c_longlong, ctypes.POINTER(c_void_p), c_int,
+                         ctypes.c_longlong, c_void_p],
     "b200_conv3x3_encode_maps": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p],
     "b200_conv3x3_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                           c_int, c_void_p, c_int, c_int, ctypes.POINTER(EpilogueDesc), c_void_p],

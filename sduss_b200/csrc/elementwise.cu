@@ -351,79 +351,6 @@ __global__ void sd3_unpatchify_kernel(const __nv_bfloat16* tokens, int ldt, cons
   dst[idx] = tokens[size_t(d.x + tok) * ldt + k];
 }
 
-// ------------------------------------------------------------------ CFG + scheduler update
-// Per request r (one CTA column): eps = u + g (c - u) when cfg, then
-//   mode 0 (flow match, scheduling_flow_match_euler_discrete.py:159-203): x' = x + (s' - s) eps
-//   mode 1 (Euler epsilon,  scheduling_euler_discrete.py:187-274): x0 = x - s eps; d = (x - x0)/s;
-//          x' = x + d (s' - s)
-//   mode 2 (Euler v_prediction): x0 = eps * (-s / sqrt(s^2+1)) + x / (s^2+1); rest as mode 1
-// fp32 math on the fp32-upcast sample, result cast to the model dtype (bf16) exactly like the
-// reference; the CFG combine happens in bf16 arithmetic order of the reference (u + g*(c-u)
-// evaluated in fp32 then rounded to bf16).
-// desc[r] = {element offset of request r in x / out, elements, offset of uncond in eps, offset
-// of cond in eps}; sig[r] = {sigma, sigma_next}.
-struct StepArgs {
-  const __nv_bfloat16* eps; const __nv_bfloat16* x; __nv_bfloat16* out;
-  const long long* desc;  // [R][4]
-  const float* sig;       // [R][2]
-  float guidance; int cfg; int mode;
-};
-
-__global__ void cfg_step_kernel(StepArgs a) {
-  const int r = blockIdx.y;
-  const long long x_off = a.desc[r * 4], n = a.desc[r * 4 + 1];
-  const long long u_off = a.desc[r * 4 + 2], c_off = a.desc[r * 4 + 3];
-  const float s = a.sig[r * 2], sn = a.sig[r * 2 + 1];
-  for (long long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < n;
-       i += long(gridDim.x) * blockDim.x) {
-    float e;
-    if (a.cfg) {
-      const float u = __bfloat162float(a.eps[u_off + i]);
-      const float c = __bfloat162float(a.eps[c_off + i]);
-      // reference: bf16 tensor ops -> each op rounds to bf16
-      const float diff = __bfloat162float(__float2bfloat16(c - u));
-      const float sc = __bfloat162float(__float2bfloat16(a.guidance * diff));
-      e = __bfloat162float(__float2bfloat16(u + sc));
-    } else {
-      e = __bfloat162float(a.eps[c_off + i]);
-    }
-    const float x = __bfloat162float(a.x[x_off + i]);
-    float xn;
-    // explicit round-to-nearest mul/add (no FMA contraction): same op order as the reference
-    if (a.mode == 0) {
-      xn = __fadd_rn(x, __fmul_rn(__fsub_rn(sn, s), e));
-    } else {
-      float x0;
-      if (a.mode == 1) {
-        x0 = __fsub_rn(x, __fmul_rn(s, e));
-      } else {
-        const float s2p = __fadd_rn(__fmul_rn(s, s), 1.f);
-        x0 = __fadd_rn(__fmul_rn(e, __fdiv_rn(-s, __fsqrt_rn(s2p))), __fdiv_rn(x, s2p));
-      }
-      const float d = __fdiv_rn(__fsub_rn(x, x0), s);
-      xn = __fadd_rn(x, __fmul_rn(d, __fsub_rn(sn, s)));
-    }
-    a.out[x_off + i] = __float2bfloat16(xn);
-  }
-}
-
-// x / sqrt(sigma^2 + 1), sigma per latent (scheduling_euler_discrete.py:161-184). The reference
-// builds sigma in the sample dtype, so sigma is rounded to bf16 first.
-// desc[l] = {element offset, elements}; sig[l] = sigma of latent l.
-__global__ void scale_input_kernel(const __nv_bfloat16* x, __nv_bfloat16* y, const long long* desc,
-                                   const float* sig) {
-  const int l = blockIdx.y;
-  const long long off = desc[l * 2], n = desc[l * 2 + 1];
-  const float s = __bfloat162float(__float2bfloat16(sig[l]));
-  // bf16 op chain of the reference: s**2 -> +1 -> **0.5 -> divide, each rounded to bf16
-  const float s2 = __bfloat162float(__float2bfloat16(s * s));
-  const float s2p = __bfloat162float(__float2bfloat16(s2 + 1.f));
-  const float den = __bfloat162float(__float2bfloat16(sqrtf(s2p)));
-  for (long long i = blockIdx.x * long(blockDim.x) + threadIdx.x; i < n;
-       i += long(gridDim.x) * blockDim.x)
-    y[off + i] = __float2bfloat16(__fdiv_rn(__bfloat162float(x[off + i]), den));
-}
-
 }  // namespace b200
 
 using namespace b200;
@@ -492,32 +419,5 @@ extern "C" int b200_sd3_unpatchify(const void* tokens, int ldt, const int32_t* d
   sd3_unpatchify_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(tokens), ldt, reinterpret_cast<const int4*>(desc), C, p,
       reinterpret_cast<const unsigned long long*>(out_ptr));
-  return launch_status();
-}
-
-extern "C" int b200_cfg_scheduler_step(const void* eps, const void* x, void* out,
-                                       const int64_t* desc, const float* sigmas, int n_requests,
-                                       long long max_elems, float guidance, int cfg, int mode,
-                                       void* stream) {
-  if (!eps || !x || !out || !desc || !sigmas || n_requests <= 0 || max_elems <= 0 || mode < 0 ||
-      mode > 2)
-    return B200_ERR_INVALID;
-  StepArgs a{static_cast<const bf16*>(eps), static_cast<const bf16*>(x), static_cast<bf16*>(out),
-             reinterpret_cast<const long long*>(desc), sigmas, guidance, cfg, mode};
-  unsigned gx = unsigned((max_elems + 1023) / 1024);
-  if (gx > 256) gx = 256;
-  cfg_step_kernel<<<dim3(gx, n_requests), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
-  return launch_status();
-}
-
-extern "C" int b200_euler_scale_input(const void* x, void* y, const int64_t* desc,
-                                      const float* sigmas, int n_latents, long long max_elems,
-                                      void* stream) {
-  if (!x || !y || !desc || !sigmas || n_latents <= 0 || max_elems <= 0) return B200_ERR_INVALID;
-  unsigned gx = unsigned((max_elems + 1023) / 1024);
-  if (gx > 256) gx = 256;
-  scale_input_kernel<<<dim3(gx, n_latents), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(x), static_cast<bf16*>(y), reinterpret_cast<const long long*>(desc),
-      sigmas);
   return launch_status();
 }

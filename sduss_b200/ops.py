@@ -38,27 +38,71 @@ def graphs_enabled():
     return os.environ.get("SDUSS_B200_NO_GRAPH", "0") != "1"
 
 
-def run_plan(model, plan):
-    """Runs model._run(plan). All shapes and pointers of a plan are static, so after one eager
-    (warm-up) run the whole forward -- a few hundred to a few thousand launches -- is captured
-    into a CUDA graph and replayed; per-launch profiling (ops.profile) forces the eager path."""
+def capture_after():
+    """A plan's forward is captured into a CUDA graph on its N-th use (default 2): the first use of
+    a batch composition runs eagerly, so compositions a serving run sees only once never pay for a
+    capture + instantiation."""
+    return int(os.environ.get("SDUSS_B200_CAPTURE_AFTER", "2"))
+
+
+def run_plan(model, plan, prologue=None):
+    """Runs prologue(plan) (per-step inputs: by-value kernel arguments that change every step, never
+    captured) and then model._run(plan). All shapes and pointers of a plan are static, so the
+    forward -- a few hundred to a few thousand launches -- is captured into a CUDA graph on the
+    plan's second use and replayed from then on; per-launch profiling (ops.profile) forces the
+    eager path."""
     global launch_count
     if not getattr(model, "use_graphs", False) or profile is not None:
-        _run_eager(model, plan)
+        _run_eager(model, plan, prologue)
         return
+    plan.uses = getattr(plan, "uses", 0) + 1
     if plan.graph is None:
-        _run_eager(model, plan)               # eager: allocates workspaces, encodes tensor maps
-        torch.cuda.current_stream().synchronize()
+        if plan.uses < capture_after() or not getattr(plan, "warm", False):
+            _run_eager(model, plan, prologue)  # eager: allocates workspaces, encodes tensor maps
+            plan.warm = True
+            if plan.uses < capture_after():
+                return
+            torch.cuda.current_stream().synchronize()
+            eager_done = True
+        else:
+            eager_done = False
+            if prologue is not None:
+                prologue(plan)
         n0 = launch_count
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            model._run(plan)
+        plan.graph = _capture(model, plan)
         plan.graph_launches = launch_count - n0
         launch_count = n0
-        plan.graph = g
-        return                                # the eager run already produced this call's result
+        if eager_done:
+            return                            # the eager run already produced this call's result
+        plan.graph.replay()
+        launch_count += plan.graph_launches
+        return
+    if prologue is not None:
+        prologue(plan)
     plan.graph.replay()
     launch_count += plan.graph_launches
+
+
+def _capture(model, plan):
+    """Stream capture of model._run(plan) without torch.cuda.graph()'s entry cost (it runs
+    gc.collect(), a device-wide synchronize and empty_cache() on every capture: tens of ms, and the
+    emptied allocator cache is paid again by the next steps). A warm plan allocates nothing while
+    it runs, so none of that is needed. thread_local error mode: CUDA calls from other threads of
+    the runner process stay legal during the capture window."""
+    g = torch.cuda.CUDAGraph()
+    cur = torch.cuda.current_stream()
+    side = getattr(model, "_capture_stream", None)
+    if side is None:
+        side = model._capture_stream = torch.cuda.Stream(device=cur.device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        g.capture_begin(capture_error_mode="thread_local")
+        try:
+            model._run(plan)
+        finally:
+            g.capture_end()
+    cur.wait_stream(side)
+    return g
 
 
 class ArenaOverflow(RuntimeError):
@@ -67,17 +111,22 @@ class ArenaOverflow(RuntimeError):
         self.need = need
 
 
-def _run_eager(model, plan):
-    """model._run(plan); plans that bump-allocate their workspaces from the model's Arena restart
-    on a larger block when it overflows (a handful of times per process: the block doubles)."""
+def _run_eager(model, plan, prologue=None):
+    """prologue(plan); model._run(plan). Plans that bump-allocate their workspaces from the model's
+    Arena restart on a larger block when it overflows (a handful of times per process: the block
+    doubles); the prologue is re-run because it fills buffers of the block."""
     while True:
         try:
+            if prologue is not None:
+                prologue(plan)
             return model._run(plan)
         except ArenaOverflow as e:
             if torch.cuda.is_available():  # kernels of the partial run still use the old views
                 torch.cuda.current_stream().synchronize()
             plan.reset_workspaces()
             model.arena.grow(e.need)
+            if hasattr(model, "_plans"):
+                model._plans._drop_stale()
 
 
 class PlanCache:
@@ -127,7 +176,12 @@ class PlanCache:
         return n
 
     def total_bytes(self):
+        """Bytes the cached plans own themselves. The shared arena block is excluded: evicting a
+        plan never frees it, so counting it would make every get() drop all plans (and their CUDA
+        graphs) once the arena alone exceeds the budget."""
         seen = set()
+        if self.arena is not None and self.arena.block is not None:
+            seen.add(self.arena.block.untyped_storage().data_ptr())
         return sum(self.plan_bytes(p, seen) for p in self.plans.values())
 
     def _drop_stale(self):
@@ -366,19 +420,75 @@ def sd3_unpatchify(tokens, desc, n_latents, max_tokens, C, p, out_ptr):
         _ev.record()
 
 
-def cfg_scheduler_step(eps, x, out, desc, sigmas, n_requests, max_elems, guidance, cfg, mode):
+_DT = {torch.bfloat16: _lib.DT_BF16, torch.float16: _lib.DT_F16, torch.float32: _lib.DT_F32}
+
+
+def dtype_code(dtype):
+    try:
+        return _DT[dtype]
+    except KeyError:
+        raise TypeError(f"latents must be bf16, fp16 or fp32, got {dtype}") from None
+
+
+def latent_refs(rows):
+    """rows: iterable of (src_ptr, dst_ptr, elems, off_a, off_b, sigma, sigma_next) -> ctypes array
+    of B200LatentRef (host memory; it travels by value inside the kernel parameters)."""
+    rows = list(rows)
+    arr = (_lib.LatentRef * len(rows))()
+    for a, (src, dst, n, oa, ob, s, sn) in zip(arr, rows):
+        a.src, a.dst, a.elems, a.off_a, a.off_b, a.sigma, a.sigma_next = src, dst, n, oa, ob, s, sn
+    return arr
+
+
+def gather_latents(refs, dtype, staging, scale_input=False):
+    """Latents of all requests -> the model's bf16 input staging buffer (CFG duplicate, optional
+    Euler input scaling). refs: latent_refs(...) with off_a / off_b = element offsets in staging."""
+    _req(staging)
+    _ev = _count("b200_gather_latents")
+    check(lib.b200_gather_latents(refs, len(refs), dtype_code(dtype), int(scale_input),
+                                  _ptr(staging), _stream()), "b200_gather_latents")
+    if _ev is not None:
+        _ev.record()
+
+
+def cfg_scheduler_step(eps, refs, latent_dtype, guidance, cfg, mode):
+    """CFG combine + scheduler update of all requests in one launch. eps: the model's flat output
+    (bf16, or fp32 for the scheduler mixins on fp32 model outputs); refs: latent_refs(...) with
+    off_a / off_b = element offsets of the uncond / cond prediction in eps."""
+    assert eps.is_cuda and eps.dtype in (torch.bfloat16, torch.float32)
     _ev = _count("b200_cfg_scheduler_step")
-    check(lib.b200_cfg_scheduler_step(_ptr(eps), _ptr(x), _ptr(out), _ptr(desc), _ptr(sigmas),
-                                      n_requests, max_elems, ctypes.c_float(guidance), int(cfg),
+    check(lib.b200_cfg_scheduler_step(_ptr(eps), dtype_code(eps.dtype), refs, len(refs),
+                                      dtype_code(latent_dtype), ctypes.c_float(guidance), int(cfg),
                                       mode, _stream()), "b200_cfg_scheduler_step")
     if _ev is not None:
         _ev.record()
 
 
-def euler_scale_input(x, y, desc, sigmas, n_latents, max_elems):
-    _ev = _count("b200_euler_scale_input")
-    check(lib.b200_euler_scale_input(_ptr(x), _ptr(y), _ptr(desc), _ptr(sigmas), n_latents,
-                                     max_elems, _stream()), "b200_euler_scale_input")
+def write_f32(dst, values):
+    """dst[:len(values)] = values (fp32), passed by value: no host->device copy, no sync."""
+    _req(dst, torch.float32)
+    n = len(values)
+    assert dst.numel() >= n
+    arr = (ctypes.c_float * n)(*values)
+    _ev = _count("b200_write_f32")
+    check(lib.b200_write_f32(_ptr(dst), arr, n, _stream()), "b200_write_f32")
+    if _ev is not None:
+        _ev.record()
+
+
+def gather_rows(dst, srcs, bytes_each=None):
+    """dst[i] = srcs[i] for a list of equally sized contiguous device tensors (or raw pointers when
+    bytes_each is given); dst: [n, ...] with any row stride."""
+    n = len(srcs)
+    if bytes_each is None:
+        bytes_each = srcs[0].numel() * srcs[0].element_size()
+        ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in srcs])
+    else:
+        ptrs = (ctypes.c_void_p * n)(*srcs)
+    stride = dst.stride(0) * dst.element_size()
+    assert dst.shape[0] >= n and stride >= bytes_each
+    _ev = _count("b200_gather_rows")
+    check(lib.b200_gather_rows(_ptr(dst), stride, ptrs, n, bytes_each, _stream()), "b200_gather_rows")
     if _ev is not None:
         _ev.record()
 

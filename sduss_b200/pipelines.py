@@ -7,14 +7,33 @@ Mirrors, argument for argument and side effect for side effect:
   ESyMReDStableDiffusionXLPipeline.denoising_step
       sduss/model_executor/diffusers/pipelines/stable_diffusion_xl/pipeline_stable_diffusion_xl_esymred.py:260-403
 i.e. resolutions in ascending order, per resolution [uncond..., cond...] under CFG, the model
-forward on the dict of latents, CFG combine, per-request scheduler update, then
+forward on the latents, CFG combine, per-request scheduler update, then
 `req.sampling_params.latents` / `req.scheduler_states` are advanced in place.
+
+What is different from the reference is how the step talks to the GPU. The reference re-`cat`s
+latents, prompt embeddings and pooled embeddings of all requests every step, builds the timestep
+and sigma tensors on the host and copies them over (a pageable host->device copy drains the
+stream), and recomputes everything that depends only on the prompt. Here one step is:
+
+    b200_gather_latents      request latents -> the plan's bf16 input buffer (+ CFG duplicate,
+                             + Euler input scaling), descriptors passed BY VALUE
+    b200_write_f32           the per-latent timesteps, by value
+    b200_gather_rows (x2-3)  the requests' cached conditioning -> the plan's packed buffers
+    <CUDA-graph replay of the model forward>
+    b200_cfg_scheduler_step  CFG combine + scheduler update, sigma pairs by value, new latents
+                             written in the latents' own dtype
+
+No torch op, no host->device copy, no synchronisation. The prompt-only work (SD3: context_embedder
+on the 333 x 4096 embeddings; SDXL: text K/V of all 70 cross-attention layers) is done when a
+request is first seen and cached for its remaining steps (`_CondCache`).
 
 Requests are duck-typed like sduss' RunnerRequest (worker/runner/wrappers.py:19-36):
   req.request_id, req.sampling_params.{latents, prompt_embeds, negative_prompt_embeds},
   req.prepare_output.{pooled_prompt_embeds, negative_pooled_prompt_embeds[, add_time_ids,
   negative_add_time_ids]}, req.scheduler_states (see schedulers.SchedulerStates).
 """
+import collections
+import weakref
 from typing import Dict, List
 
 import numpy as np
@@ -23,11 +42,72 @@ import torch
 from . import ops
 
 
-def _next_timestep(st) -> float:
-    ts = getattr(st, "_timesteps_host", None)
-    if ts is None:  # one device->host read per request lifetime, not per step
-        ts = st._timesteps_host = st.timesteps.detach().float().cpu().numpy()
-    return float(ts[st.timestep_idx])
+class _HostTables:
+    """Host copies of each request's scheduler tables (timesteps live on the GPU in sduss:
+    `to_device`, scheduling_euler_discrete.py:57-66). One device->host read per request lifetime
+    instead of one per step; kept in a side table keyed by the states object (weakly), never on
+    the foreign object itself (the reference pickles / `to_numpy()`s its states for IPC)."""
+
+    def __init__(self):
+        self._weak = weakref.WeakKeyDictionary()
+        self._strong = collections.OrderedDict()  # for state classes that cannot be weak-referenced
+
+    @staticmethod
+    def _host(a):
+        if torch.is_tensor(a):
+            a = a.detach().float().cpu().numpy()
+        return np.asarray(a, dtype=np.float32)
+
+    def get(self, st):
+        try:
+            t = self._weak.get(st)
+            if t is None:
+                t = self._weak[st] = (self._host(st.timesteps), self._host(st.sigmas))
+            return t
+        except TypeError:
+            t = self._strong.get(id(st))
+            if t is None or t[0] is not st:
+                t = self._strong[id(st)] = (st, self._host(st.timesteps), self._host(st.sigmas))
+                while len(self._strong) > 1024:
+                    self._strong.popitem(last=False)
+            return t[1:]
+
+
+class _CondEntry:
+    __slots__ = ("refs", "versions", "ctx", "pooled", "ids")
+
+
+class _CondCache:
+    """Per-(request, CFG branch) conditioning that does not change over the request's steps: the
+    projected text context, the pooled embedding as bf16, SDXL's time ids as fp32. An entry is valid
+    while the request still holds the very same source tensors, unmodified (weak references + the
+    tensors' version counters: a recycled request id or an in-place edit is a miss)."""
+
+    def __init__(self, max_entries=512):
+        self.entries = collections.OrderedDict()
+        self.max_entries = max_entries
+        self.hits = self.misses = 0
+
+    def lookup(self, key, sources):
+        e = self.entries.get(key)
+        if e is not None and all(r() is s for r, s in zip(e.refs, sources)) and \
+                e.versions == tuple(s._version for s in sources):
+            self.entries.move_to_end(key)
+            self.hits += 1
+            return e
+        self.misses += 1
+        return None
+
+    def store(self, key, sources, ctx, pooled, ids):
+        e = _CondEntry()
+        e.refs = tuple(weakref.ref(s) for s in sources)
+        e.versions = tuple(s._version for s in sources)
+        e.ctx, e.pooled, e.ids = ctx, pooled, ids
+        self.entries[key] = e
+        self.entries.move_to_end(key)
+        while len(self.entries) > self.max_entries:
+            self.entries.popitem(last=False)
+        return e
 
 
 class B200PipelineOutput:
@@ -38,38 +118,20 @@ class B200PipelineOutput:
         self.nsfw_content_detected = nsfw_content_detected
 
 
-class _StepState:
-    """Per batch-composition host staging for the fused CFG + scheduler kernel."""
-
-    def __init__(self, plan, comp, elems_per_latent: Dict[str, int], cfg: bool, device):
-        R = sum(n // (2 if cfg else 1) for _, n, _, _ in comp)
-        desc, x_off = [], 0
-        for res, n, _, _ in comp:
-            per = n // (2 if cfg else 1)
-            e = elems_per_latent[res]
-            base = plan.out_elem_off[res]
-            for i in range(per):
-                u_off = base + i * e
-                c_off = base + (per + i) * e if cfg else u_off
-                desc.append((x_off, e, u_off, c_off))
-                x_off += e
-        self.R, self.total = R, x_off
-        self.max_elems = max(d[1] for d in desc)
-        self.desc = torch.tensor(desc, dtype=torch.int64).to(device)
-        self.device = device
-        self.spans = [(d[0], d[1]) for d in desc]
-
-
 class B200DenoisingPipelineBase:
     SUPPORT_MIXED_PRECISION = True
     SUPPORT_RESOLUTIONS = [256, 512, 768, 1024]
     step_mode = 0           # b200_cfg_scheduler_step mode
     default_guidance = 7.0
+    scale_input = False     # Euler: x / sqrt(sigma^2 + 1) fused into the latent gather
+    has_time_ids = False
 
     def __init__(self, model, scheduler, vae=None):
         self.model = model
         self.scheduler = scheduler
         self.vae = vae  # optional sduss_b200.vae.B200VAEDecoder (post_inference, row f-4)
+        self._tables = _HostTables()
+        self._cond = _CondCache()
 
     # -- post stage --------------------------------------------------------------------
     @torch.inference_mode()
@@ -102,38 +164,106 @@ class B200DenoisingPipelineBase:
     def _sorted_res(reqs: Dict[str, List]) -> List[str]:
         return sorted((r for r in reqs if len(reqs[r]) > 0), key=lambda s: int(s))
 
-    def _state(self, plan, cfg: bool):
-        # lives on the plan, so it goes away with it when the plan cache evicts the plan
-        states = plan.__dict__.setdefault("_step_states", {})
-        st = states.get(cfg)
-        if st is None:
-            elems = {res: t[0].numel() for res, t in plan.stage_out.items()}
-            st = states[cfg] = _StepState(plan, plan.comp, elems, cfg, self.model.device)
-        return st
+    def _conditioning(self, flat, cfg):
+        """[(entry_uncond | None, entry_cond)] per request, computing the misses in one batch."""
+        out, todo = [], []
+        for r in flat:
+            sp, po = r.sampling_params, r.prepare_output
+            pair = []
+            for neg in ((True, False) if cfg else (False,)):
+                emb = sp.negative_prompt_embeds if neg else sp.prompt_embeds
+                pooled = po.negative_pooled_prompt_embeds if neg else po.pooled_prompt_embeds
+                src = [emb, pooled]
+                if self.has_time_ids:
+                    src.append(po.negative_add_time_ids if neg else po.add_time_ids)
+                key = (r.request_id, neg)
+                e = self._cond.lookup(key, src)
+                if e is None:
+                    todo.append((key, src, len(out), len(pair)))
+                pair.append(e)
+            out.append(pair)
+        if todo:
+            dev = self.model.device
+            raw = torch.cat([s[0].reshape(1, s[0].shape[-2], s[0].shape[-1]) for _, s, _, _ in todo], 0)
+            ctx = self.model.project_context(raw.to(device=dev, dtype=torch.bfloat16))
+            for j, (key, src, i, k) in enumerate(todo):
+                pooled = src[1].reshape(-1).to(device=dev, dtype=torch.bfloat16).contiguous()
+                ids = src[2].reshape(-1).to(device=dev, dtype=torch.float32).contiguous() \
+                    if self.has_time_ids else None
+                out[i][k] = self._cond.store(key, src, ctx[j], pooled, ids)
+        return out
 
-    def _finish(self, plan, reqs_sorted, cfg: bool, guidance: float):
-        """CFG combine + scheduler update in one launch; writes latents / states back."""
-        st = self._state(plan, cfg)
-        flat = [r for _, rs in reqs_sorted for r in rs]
-        x = torch.cat([r.sampling_params.latents.reshape(-1) for r in flat]).to(torch.bfloat16)
-        # (sigma, sigma_next) per request. A fresh host tensor per call: the step is asynchronous
-        # (CUDA-graph replay), so a reused pinned staging buffer would be overwritten by the next
-        # call before this call's copy has run.
-        sig = np.empty((st.R, 2), dtype=np.float32)
-        for i, r in enumerate(flat):
-            ss = r.scheduler_states
-            sig[i, 0] = float(ss.sigmas[ss._step_index])
-            sig[i, 1] = float(ss.sigmas[ss._step_index + 1])
-        sig_dev = torch.from_numpy(sig).to(st.device)
-        out = torch.empty_like(x)
-        ops.cfg_scheduler_step(plan.flat_out, x, out, st.desc, sig_dev, st.R, st.max_elems,
-                               guidance, cfg, self.step_mode)
-        for (off, n), r in zip(st.spans, flat):
+    def _step(self, reqs: Dict[str, List], cfg: bool, guidance: float) -> None:
+        model = self.model
+        res_list = self._sorted_res(reqs)
+        flat = [r for res in res_list for r in reqs[res]]
+        lat0 = flat[0].sampling_params.latents
+        dtype, dup = lat0.dtype, (2 if cfg else 1)
+        comp = []
+        for res in res_list:
+            lat = reqs[res][0].sampling_params.latents
+            comp.append((res, dup * len(reqs[res]), lat.shape[-2], lat.shape[-1]))
+        plan = model.plan_for(tuple(comp), flat[0].sampling_params.prompt_embeds.shape[-2])
+        conds = self._conditioning(flat, cfg)
+
+        # per-request descriptors: where the latent goes in the model input (uncond copy, cond
+        # copy), where its predictions come out, its sigma pair and its timestep
+        total = sum(r.sampling_params.latents.numel() for r in flat)
+        new = torch.empty((total,), device=model.device, dtype=dtype)
+        esz = new.element_size()
+        gather, step, ts, views = [], [], [], []
+        ctx_ptrs, pooled_ptrs, id_ptrs = [], [], []
+        x_off = 0
+        for res in res_list:
+            rs = reqs[res]
+            per = len(rs)
+            t_res, c_res, p_res, i_res = [], [[], []], [[], []], [[], []]
+            for i, r in enumerate(rs):
+                lat = r.sampling_params.latents
+                if lat.dtype != dtype or not lat.is_contiguous() or not lat.is_cuda:
+                    raise ValueError("all request latents must be contiguous CUDA tensors of one dtype")
+                n = lat.numel()
+                ss = r.scheduler_states
+                tsteps, sigmas = self._tables.get(ss)
+                s, sn = float(sigmas[ss._step_index]), float(sigmas[ss._step_index + 1])
+                a_in = plan.in_elem_off[res] + i * n
+                a_out = plan.out_elem_off[res] + i * n
+                gather.append((lat.data_ptr(), 0, n, a_in, (a_in + per * n) if cfg else -1, s, sn))
+                step.append((lat.data_ptr(), new.data_ptr() + x_off * esz, n,
+                             a_out if cfg else -1, (a_out + per * n) if cfg else a_out, s, sn))
+                views.append((r, x_off, n, lat.shape))
+                x_off += n
+                t_res.append(float(tsteps[ss.timestep_idx]))
+                for k, e in enumerate(conds[len(views) - 1]):
+                    c_res[k].append(e.ctx.data_ptr())
+                    p_res[k].append(e.pooled.data_ptr())
+                    if self.has_time_ids:
+                        i_res[k].append(e.ids.data_ptr())
+            for k in range(dup):  # [uncond requests..., cond requests...] per resolution
+                ts += t_res
+                ctx_ptrs += c_res[k]
+                pooled_ptrs += p_res[k]
+                id_ptrs += i_res[k]
+        g_refs, s_refs = ops.latent_refs(gather), ops.latent_refs(step)
+        e0 = conds[0][0]
+        ctx_bytes = e0.ctx.numel() * 2
+        pooled_bytes = e0.pooled.numel() * 2
+
+        def prologue(pl):
+            ops.gather_latents(g_refs, dtype, pl.flat_in, scale_input=self.scale_input)
+            ops.write_f32(pl.t32, ts)
+            ops.gather_rows(self._ctx_buffer(pl), ctx_ptrs, ctx_bytes)
+            ops.gather_rows(self._pooled_buffer(pl), pooled_ptrs, pooled_bytes)
+            if self.has_time_ids:
+                ops.gather_rows(pl.ids32.view(pl.L, -1), id_ptrs, e0.ids.numel() * 4)
+
+        ops.run_plan(model, plan, prologue)
+        ops.cfg_scheduler_step(plan.flat_out, s_refs, dtype, guidance, cfg, self.step_mode)
+        for r, off, n, shape in views:
             ss = r.scheduler_states
             ss._step_index += 1
             ss.update_states_one_step()
-            lat = r.sampling_params.latents
-            r.sampling_params.latents = out[off:off + n].view(lat.shape).to(lat.dtype)
+            r.sampling_params.latents = new[off:off + n].view(shape)
 
 
 class B200StableDiffusion3Pipeline(B200DenoisingPipelineBase):
@@ -145,45 +275,37 @@ class B200StableDiffusion3Pipeline(B200DenoisingPipelineBase):
     def transformer(self):
         return self.model
 
+    @staticmethod
+    def _ctx_buffer(pl):
+        return pl.c.view(pl.L, -1)
+
+    @staticmethod
+    def _pooled_buffer(pl):
+        return pl.pooled
+
     @torch.inference_mode()
     def denoising_step(self, runner_reqs: Dict[str, List], do_classifier_free_guidance: bool = True,
                        guidance_scale: float = 7.0, is_sliced: bool = True, patch_size: int = 256) -> None:
-        res_list = self._sorted_res(runner_reqs)
-        cfg = do_classifier_free_guidance
-        lat_in, embeds, pooled, ts = {}, [], [], []
-        for res in res_list:
-            reqs = runner_reqs[res]
-            lat = torch.cat([r.sampling_params.latents for r in reqs], dim=0)
-            t = [_next_timestep(r.scheduler_states) for r in reqs]
-            if cfg:
-                lat_in[res] = torch.cat([lat, lat], dim=0)
-                embeds += [r.sampling_params.negative_prompt_embeds for r in reqs]
-                embeds += [r.sampling_params.prompt_embeds for r in reqs]
-                pooled += [r.prepare_output.negative_pooled_prompt_embeds for r in reqs]
-                pooled += [r.prepare_output.pooled_prompt_embeds for r in reqs]
-                ts += t + t
-            else:
-                lat_in[res] = lat
-                embeds += [r.sampling_params.prompt_embeds for r in reqs]
-                pooled += [r.prepare_output.pooled_prompt_embeds for r in reqs]
-                ts += t
-        ids = {res: [str(r.request_id) for r in runner_reqs[res]] for res in res_list}
-        self.model(hidden_states=lat_in, timestep=torch.tensor(ts, dtype=torch.float32).to(self.model.device, non_blocking=True),
-                   encoder_hidden_states=torch.cat(embeds, dim=0),
-                   pooled_projections=torch.cat(pooled, dim=0), return_dict=False,
-                   is_sliced=is_sliced, patch_size=patch_size, input_indices=ids, _borrow=True)
-        plan = self.model._plan(lat_in, embeds[0].shape[1])
-        self._finish(plan, [(res, runner_reqs[res]) for res in res_list], cfg, guidance_scale)
+        self._step(runner_reqs, do_classifier_free_guidance, guidance_scale)
 
 
 class B200StableDiffusionXLPipeline(B200DenoisingPipelineBase):
     """SDXL-base: Euler discrete (epsilon), guidance 5.0 (…_xl_esymred_utils.py:197)."""
     step_mode = 1
     default_guidance = 5.0
+    scale_input = True
+    has_time_ids = True
 
     @property
     def unet(self):
         return self.model
+
+    def _ctx_buffer(self, pl):
+        return self.model.kv_buffer(pl).view(pl.L, -1)
+
+    @staticmethod
+    def _pooled_buffer(pl):
+        return pl.text_embeds
 
     @torch.inference_mode()
     def denoising_step(self, worker_reqs: Dict[str, List], do_classifier_free_guidance: bool = True,
@@ -195,38 +317,12 @@ class B200StableDiffusionXLPipeline(B200DenoisingPipelineBase):
         if guidance_rescale > 0.0:
             raise NotImplementedError("guidance_rescale > 0 is not fused (reference default is 0.0)")
         assert timestep_cond is None and cross_attention_kwargs is None
-        res_list = self._sorted_res(worker_reqs)
-        cfg = do_classifier_free_guidance
-        lat_in, embeds, pooled, ids, ts = {}, [], [], [], []
         pt = getattr(getattr(self.scheduler, "config", None), "prediction_type",
                      getattr(self.scheduler, "prediction_type", "epsilon"))
+        if pt not in ("epsilon", "v_prediction"):
+            raise NotImplementedError(f"prediction_type {pt} is not supported by the fused step kernel")
         self.step_mode = 1 if pt == "epsilon" else 2
-        for res in res_list:
-            reqs = worker_reqs[res]
-            lat = torch.cat([r.sampling_params.latents for r in reqs], dim=0)
-            t = [_next_timestep(r.scheduler_states) for r in reqs]
-            if cfg:
-                lat = torch.cat([lat, lat], dim=0)
-                embeds += [r.sampling_params.negative_prompt_embeds for r in reqs]
-                embeds += [r.sampling_params.prompt_embeds for r in reqs]
-                pooled += [r.prepare_output.negative_pooled_prompt_embeds for r in reqs]
-                pooled += [r.prepare_output.pooled_prompt_embeds for r in reqs]
-                for r in reqs:  # reference interleaves (neg, pos) per request here: deviation D4
-                    ids += [r.prepare_output.negative_add_time_ids, r.prepare_output.add_time_ids]
-                ts += t + t
-            else:
-                embeds += [r.sampling_params.prompt_embeds for r in reqs]
-                pooled += [r.prepare_output.pooled_prompt_embeds for r in reqs]
-                ids += [r.prepare_output.add_time_ids for r in reqs]
-                ts += t
-            # scale_model_input: x / sqrt(sigma^2 + 1) per request (one launch per resolution)
-            lat_in[res] = self.scheduler.batch_scale_model_input(reqs, lat, None)
-        index = {res: [str(r.request_id) for r in worker_reqs[res]] for res in res_list}
-        t_dev = torch.tensor(ts, dtype=torch.float32).to(self.model.device, non_blocking=True)
-        self.model(lat_in, t_dev, encoder_hidden_states=torch.cat(embeds, dim=0),
-                   added_cond_kwargs={"text_embeds": torch.cat(pooled, dim=0),
-                                      "time_ids": torch.cat(ids, dim=0)},
-                   return_dict=False, is_sliced=is_sliced, patch_size=patch_size,
-                   input_indices=index, _borrow=True)
-        plan = self.model._plan(lat_in, embeds[0].shape[1])
-        self._finish(plan, [(res, worker_reqs[res]) for res in res_list], cfg, guidance_scale)
+        # add_time_ids order: the reference interleaves (neg, pos) per request while the latents are
+        # blocked [uncond..., cond...] (deviation D4, harmless there because neg == pos ids); here
+        # every latent gets the ids of its own branch.
+        self._step(worker_reqs, do_classifier_free_guidance, guidance_scale)

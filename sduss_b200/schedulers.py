@@ -49,20 +49,17 @@ class SchedulerStates:
         self.timesteps = self.timesteps.to(device=device)
 
 
-def _sigma_pairs(reqs) -> torch.Tensor:
+def _sigma_pairs(reqs):
     rows = []
     for r in reqs:
         st = r.scheduler_states
         rows.append((float(st.sigmas[st._step_index]), float(st.sigmas[st._step_index + 1])))
-    return torch.tensor(rows, dtype=torch.float32)
-
-
-def _flat_desc(n_rows: int, elems: int, dup: int = 1) -> torch.Tensor:
-    return torch.tensor([[i * elems, elems] for i in range(n_rows * dup)], dtype=torch.int64)
+    return rows
 
 
 class BatchStepMixin:
-    """batch_step via the fused kernel. `mode`: 0 flow match, 1 Euler epsilon, 2 Euler v."""
+    """batch_step via the fused kernel. `mode`: 0 flow match, 1 Euler epsilon, 2 Euler v.
+    The sigma pairs travel by value in the kernel arguments (no torch.tensor(...).to(device))."""
 
     _mode = 0
 
@@ -71,17 +68,19 @@ class BatchStepMixin:
 
     def _batch_step(self, reqs, model_outputs, samples):
         assert model_outputs.shape == samples.shape and model_outputs.shape[0] == len(reqs)
-        dev = model_outputs.device
         R, n = samples.shape[0], samples[0].numel()
-        x = samples.to(torch.bfloat16).contiguous()
-        e = model_outputs.to(torch.bfloat16).contiguous()
-        out = torch.empty_like(e)
-        desc = torch.tensor([[i * n, n, 0, i * n] for i in range(R)], dtype=torch.int64).to(dev)
-        sig = _sigma_pairs(reqs).to(dev)
-        ops.cfg_scheduler_step(e, x, out, desc, sig, R, n, 1.0, False, self._step_mode())
+        x = samples.contiguous()
+        e = model_outputs.contiguous()
+        if e.dtype not in (torch.bfloat16, torch.float32):
+            e = e.float()  # fp16 model outputs: exact upcast; no CFG arithmetic happens here
+        out = torch.empty_like(x)
+        xs, es = x.element_size(), n
+        refs = ops.latent_refs((x.data_ptr() + i * n * xs, out.data_ptr() + i * n * xs, n, -1, i * es, s, sn)
+                               for i, (s, sn) in enumerate(_sigma_pairs(reqs)))
+        ops.cfg_scheduler_step(e, refs, x.dtype, 1.0, False, self._step_mode())
         for r in reqs:
             r.scheduler_states._step_index += 1
-        return out.to(model_outputs.dtype)
+        return out.to(model_outputs.dtype)  # "cast sample back to model compatible dtype"
 
 
 class BatchEulerMixin(BatchStepMixin):
@@ -97,16 +96,17 @@ class BatchEulerMixin(BatchStepMixin):
         raise NotImplementedError(f"prediction_type {pt} is not supported by the fused step kernel")
 
     def batch_scale_model_input(self, worker_reqs, samples: torch.Tensor, timestep_list=None):
-        dev = samples.device
-        sig = torch.tensor([float(r.scheduler_states.sigmas[r.scheduler_states._step_index])
-                            for r in worker_reqs], dtype=torch.float32)
-        if samples.shape[0] == sig.shape[0] * 2:  # classifier free
-            sig = sig.repeat(2)
-        assert samples.shape[0] == sig.shape[0]
+        sig = [float(r.scheduler_states.sigmas[r.scheduler_states._step_index]) for r in worker_reqs]
+        if samples.shape[0] == len(sig) * 2:  # classifier free
+            sig = sig + sig
+        assert samples.shape[0] == len(sig)
         n = samples[0].numel()
-        x = samples.to(torch.bfloat16).contiguous()
-        y = torch.empty_like(x)
-        ops.euler_scale_input(x, y, _flat_desc(x.shape[0], n).to(dev), sig.to(dev), x.shape[0], n)
+        x = samples.contiguous()
+        y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)  # the model's input dtype
+        xs = x.element_size()
+        refs = ops.latent_refs((x.data_ptr() + i * n * xs, 0, n, i * n, -1, s, 0.0)
+                               for i, s in enumerate(sig))
+        ops.gather_latents(refs, x.dtype, y.view(-1), scale_input=True)
         return y.to(samples.dtype)
 
     def batch_step(self, worker_reqs, model_outputs, timestep_list, samples, s_churn=0.0,

@@ -94,12 +94,12 @@ class _Plan:
         views, self.block = model.arena.carve(specs)
         for name, t in views.items():
             setattr(self, name, t)
-        self.stage_in, self.stage_out, self.out_elem_off = {}, {}, {}
+        self.stage_in, self.stage_out, self.in_elem_off, self.out_elem_off = {}, {}, {}, {}
         oi = oo = 0
         for (res, n, h, w), ni, no in zip(comp, numel_in, numel_out):
             self.stage_in[res] = self.flat_in[oi:oi + ni].view(n, cfg.in_channels, h, w)
             self.stage_out[res] = self.flat_out[oo:oo + no].view(n, cfg.out_channels, h, w)
-            self.out_elem_off[res] = oo
+            self.in_elem_off[res], self.out_elem_off[res] = oi, oo
             oi, oo = oi + ni, oo + no
         in_ptr, out_ptr, desc = [], [], []
         for l, (res, i, ht, wt) in enumerate(lat):
@@ -225,8 +225,23 @@ class B200SD3Transformer2DModel(torch.nn.Module):
     def _plan(self, hidden_states, ctx_len) -> _Plan:
         comp = tuple((res, t.shape[0], t.shape[-2], t.shape[-1])
                      for res, t in hidden_states.items() if t is not None and t.shape[0] > 0)
-        key = (comp, ctx_len)
-        return self._plans.get(key, lambda: _Plan(self, comp, ctx_len))
+        return self.plan_for(comp, ctx_len)
+
+    def plan_for(self, comp, ctx_len) -> _Plan:
+        """comp: ((resolution key, latents, h, w), ...) in ascending resolution order."""
+        return self._plans.get((comp, ctx_len), lambda: _Plan(self, comp, ctx_len))
+
+    # ---- per-request conditioning, computed once per request (sduss_b200.pipelines caches it)
+    cond_kind = "sd3"
+
+    def project_context(self, ehs: torch.Tensor) -> torch.Tensor:
+        """context_embedder on raw prompt embeddings [n, ctx, 4096] -> [n, ctx, 1536]
+        (SD3Transformer.py:115). It does not depend on the timestep, so a request's projected
+        context is computed on first sight and re-used by all its steps."""
+        n, ctx, d = ehs.shape
+        out = torch.empty((n * ctx, self.cfg.inner_dim), device=self.device, dtype=torch.bfloat16)
+        ops.gemm(ehs.reshape(n * ctx, d), self.ctx_w, out, bias=self.ctx_b)
+        return out.view(n, ctx, -1)
 
     @torch.no_grad()
     def forward(self, hidden_states: Dict[str, torch.Tensor], encoder_hidden_states=None,
@@ -237,12 +252,16 @@ class B200SD3Transformer2DModel(torch.nn.Module):
         assert block_controlnet_hidden_states is None and skip_layers is None
         assert not joint_attention_kwargs, "joint_attention_kwargs (LoRA scale / IP-adapter) unsupported"
         plan = self._plan(hidden_states, encoder_hidden_states.shape[1])
-        for res, _, _, _ in plan.comp:
-            plan.stage_in[res].copy_(hidden_states[res])
-        plan.ehs.copy_(encoder_hidden_states.reshape(plan.Tc, -1))
-        plan.pooled.copy_(pooled_projections)
-        plan.t32.copy_(timestep.reshape(-1))
-        ops.run_plan(self, plan)
+
+        def load_inputs(pl):
+            for res, _, _, _ in pl.comp:
+                pl.stage_in[res].copy_(hidden_states[res])
+            pl.ehs.copy_(encoder_hidden_states.reshape(pl.Tc, -1))
+            pl.pooled.copy_(pooled_projections)
+            pl.t32.copy_(timestep.reshape(-1))
+            ops.gemm(pl.ehs, self.ctx_w, pl.c, bias=self.ctx_b)  # context_embedder
+
+        ops.run_plan(self, plan, load_inputs)
         out = plan.stage_out if _borrow else {k: v.clone() for k, v in plan.stage_out.items()}
         return (out,)
 
@@ -263,8 +282,7 @@ class B200SD3Transformer2DModel(torch.nn.Module):
           epi=ops.EPI_GATE_RESID, resid=pl.e2)
         ops.silu(pl.temb, pl.e1)
         G(pl.e1, self.mod_w, pl.mod, bias=self.mod_b)
-        # streams
-        G(pl.ehs, self.ctx_w, pl.c, bias=self.ctx_b)
+        # streams (pl.c already holds the projected context: forward() / the step's prologue)
         ops.sd3_patchify(pl.in_ptr, pl.desc, pl.L, pl.max_tokens, cfg.in_channels, p, pl.tokens)
         G(pl.tokens, self.pe_w, pl.x, bias=self.pe_b, epi=ops.EPI_GATE_RESID, resid=pl.pos_rows)
         mod = pl.mod

@@ -8,8 +8,10 @@ import torch
 
 
 def make_sd3_requests(cfg, spec: Dict[str, int], steps: int, scheduler, device, ctx_len=333,
-                      seed=0, dtype=torch.bfloat16, pin_host=False) -> Dict[str, List]:
-    """spec: resolution -> number of requests. Returns dict resolution -> [request]."""
+                      seed=0, dtype=torch.bfloat16, pin_host=False, latent_dtype=None) -> Dict[str, List]:
+    """spec: resolution -> number of requests. Returns dict resolution -> [request].
+    latent_dtype: dtype of the running latents (default: `dtype`); the values are drawn in `dtype`
+    first, so an fp32 latent starts exactly representable in the model's input dtype."""
     g = torch.Generator().manual_seed(seed)
     reqs, all_reqs, rid = {}, [], 0
     for res, n in spec.items():
@@ -25,7 +27,7 @@ def make_sd3_requests(cfg, spec: Dict[str, int], steps: int, scheduler, device, 
                 request_id=rid,
                 sampling_params=SimpleNamespace(
                     num_inference_steps=steps, resolution=int(res),
-                    latents=rnd(1, cfg.in_channels, side, side),
+                    latents=rnd(1, cfg.in_channels, side, side).to(latent_dtype or dtype),
                     prompt_embeds=rnd(1, ctx_len, cfg.joint_attention_dim),
                     negative_prompt_embeds=rnd(1, ctx_len, cfg.joint_attention_dim)),
                 prepare_output=SimpleNamespace(
@@ -40,7 +42,7 @@ def make_sd3_requests(cfg, spec: Dict[str, int], steps: int, scheduler, device, 
 
 
 def make_sdxl_requests(cfg, spec: Dict[str, int], steps: int, scheduler, device, seed=0,
-                       dtype=torch.bfloat16, pin_host=False) -> Dict[str, List]:
+                       dtype=torch.bfloat16, pin_host=False, latent_dtype=None) -> Dict[str, List]:
     g = torch.Generator().manual_seed(seed)
     reqs, all_reqs, rid = {}, [], 0
     for res, n in spec.items():
@@ -72,7 +74,8 @@ def make_sdxl_requests(cfg, spec: Dict[str, int], steps: int, scheduler, device,
     scheduler.batch_set_timesteps(all_reqs, device=device)
     # SDXL pipelines scale the initial noise by init_noise_sigma (prepare stage)
     for r in all_reqs:
-        r.sampling_params.latents = (r.sampling_params.latents.float() * scheduler.init_noise_sigma).to(dtype)
+        r.sampling_params.latents = (r.sampling_params.latents.float() * scheduler.init_noise_sigma).to(dtype) \
+            .to(latent_dtype or dtype)
         if pin_host:
             r.sampling_params.latents = r.sampling_params.latents.pin_memory()
     return reqs

@@ -80,12 +80,12 @@ class _Plan:
         numel_out = [n * cfg.out_channels * h * w for _, n, h, w in comp]
         self.flat_in = torch.empty((sum(numel_in),), **bf)
         self.flat_out = torch.empty((sum(numel_out),), **bf)
-        self.stage_in, self.stage_out, self.out_elem_off = {}, {}, {}
+        self.stage_in, self.stage_out, self.in_elem_off, self.out_elem_off = {}, {}, {}, {}
         oi = oo = 0
         for (res, n, h, w), ni, no in zip(comp, numel_in, numel_out):
             self.stage_in[res] = self.flat_in[oi:oi + ni].view(n, cfg.in_channels, h, w)
             self.stage_out[res] = self.flat_out[oo:oo + no].view(n, cfg.out_channels, h, w)
-            self.out_elem_off[res] = oo
+            self.in_elem_off[res], self.out_elem_off[res] = oi, oo
             oi, oo = oi + ni, oo + no
         ip, op = [], []
         for res, n, _, _ in comp:
@@ -344,8 +344,27 @@ class B200UNet(torch.nn.Module):
     def _plan(self, sample, ctx_len) -> _Plan:
         comp = tuple((res, t.shape[0], t.shape[-2], t.shape[-1])
                      for res, t in sample.items() if t is not None and t.shape[0] > 0)
-        key = (comp, ctx_len)
-        return self._plans.get(key, lambda: _Plan(self, comp, ctx_len))
+        return self.plan_for(comp, ctx_len)
+
+    def plan_for(self, comp, ctx_len) -> _Plan:
+        """comp: ((resolution key, latents, h, w), ...) in ascending resolution order."""
+        return self._plans.get((comp, ctx_len), lambda: _Plan(self, comp, ctx_len))
+
+    # ---- per-request conditioning, computed once per request (sduss_b200.pipelines caches it)
+    cond_kind = "sdxl"
+
+    def project_context(self, ehs: torch.Tensor) -> torch.Tensor:
+        """Text K / V of every cross-attention layer for raw prompt embeddings [n, 77, 2048] ->
+        [n, 77, kv_cols] (attn2.to_k / to_v of all 70 BasicTransformerBlocks, modules/attention.py:
+        73-96). They do not depend on the timestep nor on the image: once per request, not once per
+        patch and step as the reference computes them."""
+        n, ctx, d = ehs.shape
+        out = torch.empty((n * ctx, self.kv_cols), device=self.device, dtype=torch.bfloat16)
+        ops.gemm(ehs.reshape(n * ctx, d), self.w["kv_all.weight"], out)
+        return out.view(n, ctx, -1)
+
+    def kv_buffer(self, pl: _Plan) -> torch.Tensor:
+        return pl.buf("kv_all", pl.L * pl.ctx_len, self.kv_cols)
 
     @torch.no_grad()
     def forward(self, sample: Dict[str, torch.Tensor], timestep, encoder_hidden_states,
@@ -361,13 +380,18 @@ class B200UNet(torch.nn.Module):
                 and mid_block_additional_residual is None
                 and down_intrablock_additional_residuals is None and encoder_attention_mask is None)
         pl = self._plan(sample, encoder_hidden_states.shape[1])
-        for res, _, _, _ in pl.comp:
-            pl.stage_in[res].copy_(sample[res])
-        pl.ehs.copy_(encoder_hidden_states.reshape(pl.ehs.shape))
-        pl.t32.copy_(timestep.reshape(-1))
-        pl.ids32.copy_(added_cond_kwargs["time_ids"].reshape(-1))
-        pl.text_embeds.copy_(added_cond_kwargs["text_embeds"])
-        ops.run_plan(self, pl)
+
+        def load_inputs(pl):
+            for res, _, _, _ in pl.comp:
+                pl.stage_in[res].copy_(sample[res])
+            pl.ehs.copy_(encoder_hidden_states.reshape(pl.ehs.shape))
+            pl.t32.copy_(timestep.reshape(-1))
+            pl.ids32.copy_(added_cond_kwargs["time_ids"].reshape(-1))
+            pl.text_embeds.copy_(added_cond_kwargs["text_embeds"])
+            # text K/V of every cross-attention layer in one GEMM (once per latent, not per patch)
+            ops.gemm(pl.ehs, self.w["kv_all.weight"], self.kv_buffer(pl))
+
+        ops.run_plan(self, pl, load_inputs)
         out = pl.stage_out if _borrow else {k: v.clone() for k, v in pl.stage_out.items()}
         return (out,)
 
@@ -392,8 +416,8 @@ class B200UNet(torch.nn.Module):
                 bias=w["add_embedding.linear_2.bias"], epi=ops.EPI_GATE_RESID, resid=emb_t)
         semb = ops.silu(emb, pl.buf("semb", L, Tdim))
         temb_all = G(semb, w["temb_all.weight"], pl.buf("temb_all", L, self.temb_cols), bias=w["temb_all.bias"])
-        # ---- text K/V of every cross-attention layer in one GEMM (once per latent, not per patch)
-        kv_all = G(pl.ehs, w["kv_all.weight"], pl.buf("kv_all", pl.ehs.shape[0], self.kv_cols))
+        # ---- text K/V of every cross-attention layer: filled by forward() / the step's prologue
+        kv_all = self.kv_buffer(pl)
         # ---- conv_in
         l0 = pl.levels[0]
         cols = pl.buf("im2col", l0.T, self.k_in_pad)

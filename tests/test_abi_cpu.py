@@ -20,7 +20,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(_lib.lib, n), f"{n} declared in include/sduss_b200.h but not exported"
-    assert _lib.lib.b200_version() == 1
+    assert _lib.lib.b200_version() == 2
 
 
 def test_ctypes_signatures_cover_header():

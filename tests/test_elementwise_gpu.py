@@ -116,53 +116,107 @@ def test_sd3_pack_scatter_bit_exact(cuda):
         o += n * h * h
 
 
-def _desc(shapes):
-    off, rows = 0, []
-    for n in shapes:
-        rows.append((off, n))
-        off += n
-    return rows, off
+def _step_refs(ops, x, out, sig, eps_rows=None):
+    """One LatentRef per row of x (requests back to back); eps_rows[r] = (uncond row, cond row)."""
+    R, n = x.shape[0], x[0].numel()
+    xs = x.element_size()
+    rows = []
+    for r in range(R):
+        u, c = (-1, r) if eps_rows is None else eps_rows[r]
+        rows.append((x.data_ptr() + r * n * xs, out.data_ptr() + r * n * xs, n,
+                     u * n if u >= 0 else -1, c * n, float(sig[r][0]), float(sig[r][1])))
+    return ops.latent_refs(rows)
 
 
-def test_flow_match_step_matches_reference_golden(cuda):
+@pytest.mark.parametrize("dt", ["bf16", "f32"])
+def test_flow_match_step_matches_reference_golden(cuda, dt):
+    """FlowMatchEulerDiscreteScheduler.batch_step run by the reference's own code
+    (tools/make_golden.py): bit-exact, in bf16 and in fp32 (samples and model outputs)."""
     from oracle import schedulers as osch
     from sduss_b200 import ops
     z = np.load(os.path.join(G, "sched_flow_match.npz"))
-    steps, idx = z["bf16_steps"], z["bf16_idx"]
-    x = torch.from_numpy(z["bf16_x"]).cuda().bfloat16()
-    v = torch.from_numpy(z["bf16_v"]).cuda().bfloat16()
-    R, n = x.shape[0], x[0].numel()
+    tdt = torch.bfloat16 if dt == "bf16" else torch.float32
+    steps, idx = z[dt + "_steps"], z[dt + "_idx"]
+    x = torch.from_numpy(z[dt + "_x"]).cuda().to(tdt)
+    v = torch.from_numpy(z[dt + "_v"]).cuda().to(tdt)
     tabs = [osch.flow_match_sigmas(int(s))[0] for s in steps]
-    sig = torch.tensor([[t[i], t[i + 1]] for t, i in zip(tabs, idx)], dtype=torch.float32).cuda()
-    desc = torch.tensor([[r * n, n, 0, r * n] for r in range(R)], dtype=torch.int64).cuda()
+    sig = [(float(t[i]), float(t[i + 1])) for t, i in zip(tabs, idx)]
     out = torch.empty_like(x)
-    ops.cfg_scheduler_step(v, x, out, desc, sig, R, n, 1.0, False, 0)
-    assert torch.equal(out.float().cpu(), torch.from_numpy(z["bf16_prev"]))
+    ops.cfg_scheduler_step(v, _step_refs(ops, x, out, sig), tdt, 1.0, False, 0)
+    assert torch.equal(out.float().cpu(), torch.from_numpy(z[dt + "_prev"]))
 
 
-def test_euler_step_and_scale_match_reference_golden(cuda):
+@pytest.mark.parametrize("dt", ["bf16", "f32"])
+def test_euler_step_and_scale_match_reference_golden(cuda, dt):
     from oracle import schedulers as osch
     from sduss_b200 import ops
     z = np.load(os.path.join(G, "sched_euler.npz"))
+    tdt = torch.bfloat16 if dt == "bf16" else torch.float32
     for mode, pt in ((1, "epsilon"), (2, "v_prediction")):
-        tag = pt + "_bf16"
+        tag = f"{pt}_{dt}"
         steps, idx = z[tag + "_steps"], z[tag + "_idx"]
-        x = torch.from_numpy(z[tag + "_x"]).cuda().bfloat16()
-        e = torch.from_numpy(z[tag + "_eps"]).cuda().bfloat16()
+        x = torch.from_numpy(z[tag + "_x"]).cuda().to(tdt)
+        e = torch.from_numpy(z[tag + "_eps"]).cuda().to(tdt)
         R, n = x.shape[0], x[0].numel()
         tabs = [osch.euler_sigmas(int(s))[0] for s in steps]
-        sig = torch.tensor([[t[i], t[i + 1]] for t, i in zip(tabs, idx)], dtype=torch.float32).cuda()
-        desc = torch.tensor([[r * n, n, 0, r * n] for r in range(R)], dtype=torch.int64).cuda()
+        sig = [(float(t[i]), float(t[i + 1])) for t, i in zip(tabs, idx)]
         out = torch.empty_like(x)
-        ops.cfg_scheduler_step(e, x, out, desc, sig, R, n, 1.0, False, mode)
+        ops.cfg_scheduler_step(e, _step_refs(ops, x, out, sig), tdt, 1.0, False, mode)
         assert torch.equal(out.float().cpu(), torch.from_numpy(z[tag + "_prev"])), pt
-        # scale_model_input on the CFG-duplicated batch [x, x]
-        xin = torch.cat([x, x]).contiguous()
-        d2 = torch.tensor([[l * n, n] for l in range(2 * R)], dtype=torch.int64).cuda()
-        s2 = torch.cat([sig[:, 0], sig[:, 0]]).contiguous()
-        y = torch.empty_like(xin)
-        ops.euler_scale_input(xin, y, d2, s2, 2 * R, n)
-        assert torch.equal(y.float().cpu(), torch.from_numpy(z[tag + "_scaled"])), pt
+        # scale_model_input on the CFG-duplicated batch [x, x]: one gather with a CFG duplicate.
+        # The kernel's output is the model's bf16 input; the reference result is in the sample
+        # dtype, so for fp32 samples the comparison is against its bf16 rounding.
+        y = torch.empty((2 * R, n), device="cuda", dtype=torch.bfloat16)
+        xs = x.element_size()
+        refs = ops.latent_refs((x.data_ptr() + r * n * xs, 0, n, r * n, (R + r) * n, sig[r][0], 0.0)
+                               for r in range(R))
+        ops.gather_latents(refs, tdt, y.view(-1), scale_input=True)
+        want = torch.from_numpy(z[tag + "_scaled"]).reshape(2 * R, n).to(torch.bfloat16)
+        assert torch.equal(y.cpu(), want), pt
+
+
+def test_scheduler_mixins_match_reference_golden(cuda):
+    """The drop-in scheduler methods (same names / arguments / side effects as the reference's
+    batch_step and batch_scale_model_input) on the same fixtures, through the public classes."""
+    from types import SimpleNamespace
+    from oracle import schedulers as osch
+    from sduss_b200.schedulers import (B200EulerDiscreteScheduler, B200FlowMatchEulerDiscreteScheduler,
+                                       SchedulerStates)
+    z = np.load(os.path.join(G, "sched_euler.npz"))
+    for pt in ("epsilon", "v_prediction"):
+        for dt, tdt in (("bf16", torch.bfloat16), ("f32", torch.float32)):
+            tag = f"{pt}_{dt}"
+            sch = B200EulerDiscreteScheduler(prediction_type=pt)
+            reqs = []
+            for n_steps, i in zip(z[tag + "_steps"], z[tag + "_idx"]):
+                sig, ts, _ = osch.euler_sigmas(int(n_steps))
+                st = SchedulerStates(sig, int(n_steps), ts)
+                st._step_index = st.timestep_idx = int(i)
+                reqs.append(SimpleNamespace(scheduler_states=st))
+            x = torch.from_numpy(z[tag + "_x"]).cuda().to(tdt)
+            e = torch.from_numpy(z[tag + "_eps"]).cuda().to(tdt)
+            scaled = sch.batch_scale_model_input(reqs, torch.cat([x, x]), None)
+            assert scaled.dtype == tdt
+            assert torch.equal(scaled.to(torch.bfloat16).cpu(),
+                               torch.from_numpy(z[tag + "_scaled"]).to(torch.bfloat16))
+            prev = sch.batch_step(reqs, e, None, x, return_dict=False)
+            assert prev.dtype == tdt and torch.equal(prev.float().cpu(), torch.from_numpy(z[tag + "_prev"]))
+            assert [r.scheduler_states._step_index for r in reqs] == [int(i) + 1 for i in z[tag + "_idx"]]
+            with pytest.raises(NotImplementedError):
+                sch.batch_step(reqs, e, None, x, s_churn=0.1)
+    z = np.load(os.path.join(G, "sched_flow_match.npz"))
+    sch = B200FlowMatchEulerDiscreteScheduler()
+    for dt, tdt in (("bf16", torch.bfloat16), ("f32", torch.float32)):
+        reqs = []
+        for n_steps, i in zip(z[dt + "_steps"], z[dt + "_idx"]):
+            sig, ts = osch.flow_match_sigmas(int(n_steps))
+            st = SchedulerStates(sig, int(n_steps), ts)
+            st._step_index = int(i)
+            reqs.append(SimpleNamespace(scheduler_states=st))
+        x = torch.from_numpy(z[dt + "_x"]).cuda().to(tdt)
+        v = torch.from_numpy(z[dt + "_v"]).cuda().to(tdt)
+        prev = sch.batch_step(reqs, v, x, None, return_dict=False)
+        assert torch.equal(prev.float().cpu(), torch.from_numpy(z[dt + "_prev"]))
 
 
 def test_cfg_combine_matches_torch_bf16(cuda):
@@ -172,10 +226,51 @@ def test_cfg_combine_matches_torch_bf16(cuda):
     R, n = 3, 16 * 64 * 64
     eps = torch.randn(2 * R, n, generator=g).cuda().bfloat16()
     x = torch.randn(R, n, generator=g).cuda().bfloat16()
-    sig = torch.tensor([[1.0, 0.9], [0.5, 0.45], [0.1, 0.0]], dtype=torch.float32).cuda()
-    desc = torch.tensor([[r * n, n, r * n, (R + r) * n] for r in range(R)], dtype=torch.int64).cuda()
+    sig = [(1.0, 0.9), (0.5, 0.45), (0.1, 0.0)]
     out = torch.empty_like(x)
-    ops.cfg_scheduler_step(eps, x, out, desc, sig, R, n, 7.0, True, 0)
+    refs = _step_refs(ops, x, out, sig, eps_rows=[(r, R + r) for r in range(R)])
+    ops.cfg_scheduler_step(eps, refs, torch.bfloat16, 7.0, True, 0)
     comb = osch.cfg_combine(eps.cpu(), 7.0)  # bf16 tensor ops, as the reference pipeline does
-    ref = osch.flow_match_batch_step(comb, x.cpu(), sig[:, 0].cpu(), sig[:, 1].cpu())
+    s = torch.tensor(sig)
+    ref = osch.flow_match_batch_step(comb, x.cpu(), s[:, 0], s[:, 1])
     assert torch.equal(out.cpu(), ref)
+
+
+@pytest.mark.parametrize("ldt", [torch.float32, torch.float16])
+def test_step_keeps_the_latent_dtype(cuda, ldt):
+    """fp32 / fp16 latents with a bf16 model: the update runs in fp32 on the upcast sample exactly
+    as the reference does and the result stays in the LATENT's dtype (the reference would cast it to
+    the model dtype; keeping it loses nothing between steps). 40 requests: two launches of 32."""
+    from sduss_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    R, n = 40, 1000
+    eps = torch.randn(2 * R, n, generator=g).cuda().bfloat16()
+    x = torch.randn(R, n, generator=g).cuda().to(ldt)
+    sig = [(1.0 - 0.01 * r, 0.98 - 0.01 * r) for r in range(R)]
+    out = torch.empty_like(x)
+    refs = _step_refs(ops, x, out, sig, eps_rows=[(r, R + r) for r in range(R)])
+    ops.cfg_scheduler_step(eps, refs, ldt, 5.0, True, 1)
+    u, c = eps[:R], eps[R:]
+    comb = (u + 5.0 * (c - u)).float()
+    s = torch.tensor(sig, device="cuda")
+    xf = x.float()
+    x0 = xf - s[:, :1] * comb
+    d = (xf - x0) / s[:, :1]
+    want = (xf + d * (s[:, 1:] - s[:, :1])).to(ldt)
+    assert out.dtype == ldt and torch.equal(out, want)
+
+
+def test_write_f32_and_gather_rows(cuda):
+    from sduss_b200 import ops
+    vals = [float(i) * 0.37 - 3 for i in range(300)]  # > 256: two launches
+    dst = torch.zeros(320, device="cuda")
+    ops.write_f32(dst, vals)
+    assert torch.equal(dst[:300].cpu(), torch.tensor(vals, dtype=torch.float32))
+    assert dst[300:].abs().sum().item() == 0
+    g = torch.Generator().manual_seed(1)
+    for cols, dtype in ((1536 * 5, torch.bfloat16), (6, torch.float32), (130, torch.bfloat16)):
+        srcs = [torch.randn(cols, generator=g).to(dtype).cuda() for _ in range(70)]  # > 64
+        out = torch.zeros((70, cols + 8), device="cuda", dtype=dtype)
+        ops.gather_rows(out, srcs)  # row stride > row bytes
+        assert torch.equal(out[:, :cols], torch.stack(srcs))
+        assert out[:, cols:].abs().sum().item() == 0

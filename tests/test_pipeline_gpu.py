@@ -20,40 +20,109 @@ def _sd3(seed=0):
     return cfg, sd, model, sched, B200StableDiffusion3Pipeline(model, sched)
 
 
-def _oracle_sd3_step(sd, cfg, r, x, sig, ts, k, cfg_on, g):
-    from oracle import schedulers as osch
-    from oracle import sd3_mmdit as o3
-    f = lambda t: t.float().cpu()
-    if cfg_on:
-        ehs = torch.cat([f(r.sampling_params.negative_prompt_embeds), f(r.sampling_params.prompt_embeds)])
-        pooled = torch.cat([f(r.prepare_output.negative_pooled_prompt_embeds), f(r.prepare_output.pooled_prompt_embeds)])
-        out = o3.sd3_forward(sd, cfg, {"x": torch.cat([x, x])}, ehs, pooled, ts[k:k + 1].repeat(2))["x"]
-        eps = osch.cfg_combine(out, g)
-    else:
-        eps = o3.sd3_forward(sd, cfg, {"x": x}, f(r.sampling_params.prompt_embeds),
-                             f(r.prepare_output.pooled_prompt_embeds), ts[k:k + 1])["x"]
-    return osch.flow_match_batch_step(eps, x, sig[k:k + 1], sig[k + 1:k + 2])
-
-
 @pytest.mark.parametrize("cfg_on", [True, False])
 def test_sd3_three_step_rollout(cuda, cfg_on):
+    """Three steps of a mixed batch; after EVERY step the prediction the step applied,
+    (x' - x) / (sigma' - sigma), is compared per request with the oracle's (CFG-combined)
+    prediction at the same latent and timestep: cosine and max-abs (tests/_parity.py)."""
+    import _parity as P
     from oracle import schedulers as osch
     from sduss_b200.synthetic import make_sd3_requests
     cfg, sd, model, sched, pipe = _sd3()
-    reqs = make_sd3_requests(cfg, {"256": 2, "512": 1}, 28, sched, cuda, ctx_len=cfg.context_len, seed=3)
-    flat = [r for rs in reqs.values() for r in rs]
-    ref = [r.sampling_params.latents.float().cpu() for r in flat]
+    reqs = make_sd3_requests(cfg, {"256": 2, "512": 1}, 28, sched, cuda, ctx_len=cfg.context_len, seed=3,
+                             latent_dtype=torch.float32)
     sig, ts = osch.flow_match_sigmas(28)
     for k in range(3):
+        before = P.snapshot(reqs)
         pipe.denoising_step(reqs, cfg_on, 7.0, True, 256)
-        ref = [_oracle_sd3_step(sd, cfg, r, x, sig, ts, k, cfg_on, 7.0) for r, x in zip(flat, ref)]
+        torch.cuda.synchronize()
+        P.check_step(reqs, before, lambda r: sig,
+                     lambda r, x, kk: P.oracle_sd3_prediction(sd, cfg, r, x, ts[kk], cfg_on, 7.0),
+                     label=f"sd3 step {k}")
+    for rs in reqs.values():
+        for r in rs:
+            assert r.sampling_params.latents.dtype == torch.float32  # the latent keeps its dtype
+            assert r.scheduler_states._step_index == 3 and r.scheduler_states.timestep_idx == 3
+
+
+def test_parity_check_catches_a_blind_model(cuda, monkeypatch):
+    """Negative controls for the step-level parity check: a step whose model output is zeroed, or
+    replaced by noise, or whose CFG branches are swapped must FAIL it -- while the updated latents
+    themselves still look fine (cosine > 0.999 against the oracle's x'), which is why comparing
+    latents is not a parity test."""
+    import _parity as P
+    from oracle import schedulers as osch
+    from sduss_b200 import ops
+    from sduss_b200.synthetic import make_sd3_requests
+    cfg, sd, model, sched, pipe = _sd3()
+    sig, ts = osch.flow_match_sigmas(28)
+    real_run = ops.run_plan
+
+    def sabotage(kind):
+        def run(model_, plan, prologue=None):
+            real_run(model_, plan, prologue)
+            if kind == "zero":
+                plan.flat_out.zero_()
+            elif kind == "noise":
+                plan.flat_out.copy_(torch.randn_like(plan.flat_out, dtype=torch.float32))
+            elif kind == "swap":  # uncond <-> cond predictions of every resolution
+                for res, n, _, _ in plan.comp:
+                    o = plan.stage_out[res]
+                    o.copy_(torch.cat([o[n // 2:], o[:n // 2]]).clone())
+        return run
+
+    for kind in ("zero", "noise", "swap"):
+        reqs = make_sd3_requests(cfg, {"256": 1, "512": 1}, 28, sched, cuda, ctx_len=cfg.context_len, seed=9,
+                                 latent_dtype=torch.float32)
+        before = P.snapshot(reqs)
+        monkeypatch.setattr(ops, "run_plan", sabotage(kind))
+        pipe.denoising_step(reqs, True, 7.0, True, 256)
+        torch.cuda.synchronize()
+        monkeypatch.setattr(ops, "run_plan", real_run)
+        rows = []
+        P.check_step(reqs, before, lambda r: sig,
+                     lambda r, x, kk: P.oracle_sd3_prediction(sd, cfg, r, x, ts[kk], True, 7.0), report=rows)
+        assert rows and not any(P.ok(c, e, sc) for _, c, e, sc in rows), (kind, rows)
+        # ... and the latent-level comparison the round-1 tests used does not notice:
+        for rs in reqs.values():
+            for r in rs:
+                x, k = before[r.request_id]
+                ref = x + (sig[k + 1] - sig[k]) * P.oracle_sd3_prediction(sd, cfg, r, x, ts[k], True, 7.0)
+                got = r.sampling_params.latents.float().cpu()
+                cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
+                assert cos > 0.99, (kind, cos)
+    # the unsabotaged step passes on the same requests
+    reqs = make_sd3_requests(cfg, {"256": 1, "512": 1}, 28, sched, cuda, ctx_len=cfg.context_len, seed=9,
+                             latent_dtype=torch.float32)
+    before = P.snapshot(reqs)
+    pipe.denoising_step(reqs, True, 7.0, True, 256)
     torch.cuda.synchronize()
-    for r, x in zip(flat, ref):
-        got = r.sampling_params.latents.float().cpu()
-        assert got.shape == x.shape and r.sampling_params.latents.dtype == torch.bfloat16
-        cos = torch.nn.functional.cosine_similarity(got.flatten(), x.flatten(), dim=0).item()
-        assert cos > 0.998, cos  # three bf16 steps vs fp32 oracle
-        assert r.scheduler_states._step_index == 3 and r.scheduler_states.timestep_idx == 3
+    P.check_step(reqs, before, lambda r: sig,
+                 lambda r, x, kk: P.oracle_sd3_prediction(sd, cfg, r, x, ts[kk], True, 7.0))
+
+
+def test_bf16_latents_follow_the_reference_rounding(cuda):
+    """With bf16 request latents (the model dtype) the step is, bit for bit, the reference's
+    arithmetic on the B200 model output: bf16 CFG combine, fp32 update, bf16 result."""
+    from oracle import schedulers as osch
+    from sduss_b200.synthetic import make_sd3_requests
+    cfg, sd, model, sched, pipe = _sd3()
+    reqs = make_sd3_requests(cfg, {"256": 1, "512": 2}, 28, sched, cuda, ctx_len=cfg.context_len, seed=4)
+    flat = [r for res in sorted(reqs, key=int) for r in reqs[res]]
+    x0 = [r.sampling_params.latents.clone() for r in flat]
+    pipe.denoising_step(reqs, True, 7.0, True, 256)
+    torch.cuda.synchronize()
+    plan = next(iter(model._plans.values()))
+    sig, _ = osch.flow_match_sigmas(28)
+    i = 0
+    for res in sorted(reqs, key=int):
+        out = plan.stage_out[res]
+        eps = osch.cfg_combine(out.cpu(), 7.0)          # bf16 tensor ops
+        for j, r in enumerate(reqs[res]):
+            want = osch.flow_match_batch_step(eps[j:j + 1], x0[i].cpu(), sig[:1], sig[1:2])
+            assert r.sampling_params.latents.dtype == torch.bfloat16
+            assert torch.equal(r.sampling_params.latents.cpu(), want)
+            i += 1
 
 
 def test_changing_batch_composition_reuses_plans(cuda):
@@ -82,7 +151,9 @@ def test_changing_batch_composition_reuses_plans(cuda):
             assert a[res][0].scheduler_states._step_index == 3
 
 
-def test_sdxl_three_step_rollout_cfg_off(cuda):
+@pytest.mark.parametrize("cfg_on", [False, True])
+def test_sdxl_three_step_rollout(cuda, cfg_on):
+    import _parity as P
     from dataclasses import asdict
     from oracle import schedulers as osch
     from oracle import sdxl_unet as ox
@@ -96,26 +167,15 @@ def test_sdxl_three_step_rollout_cfg_off(cuda):
     model = B200UNet(sd, UNetConfig(**d), device="cuda")
     sched = B200EulerDiscreteScheduler()
     pipe = B200StableDiffusionXLPipeline(model, sched)
-    reqs = make_sdxl_requests(oc, {"256": 1, "768": 1}, 50, sched, cuda, seed=2)
-    flat = [r for rs in reqs.values() for r in rs]
-    ref = [r.sampling_params.latents.float().cpu() for r in flat]
+    reqs = make_sdxl_requests(oc, {"256": 1, "768": 1}, 50, sched, cuda, seed=2, latent_dtype=torch.float32)
     sig, ts, _ = osch.euler_sigmas(50)
-    f = lambda t: t.float().cpu()
     for k in range(3):
-        pipe.denoising_step(reqs, False, 0.0, 5.0, None, {}, None, None, None, True, 256)
-        nxt = []
-        for r, x in zip(flat, ref):
-            xin = osch.batch_scale_model_input(x.to(torch.bfloat16), [sig[k]]).float()
-            out = ox.unet_forward(sd, oc, {"x": xin}, ts[k:k + 1], f(r.sampling_params.prompt_embeds),
-                                  f(r.prepare_output.pooled_prompt_embeds), f(r.prepare_output.add_time_ids))["x"]
-            nxt.append(osch.euler_batch_step(out, x, [sig[k]], [sig[k + 1]]))
-        ref = nxt
-    torch.cuda.synchronize()
-    for r, x in zip(flat, ref):
-        got = f(r.sampling_params.latents)
-        cos = torch.nn.functional.cosine_similarity(got.flatten(), x.flatten(), dim=0).item()
-        assert cos > 0.998, cos
-        assert r.scheduler_states._step_index == 3
+        before = P.snapshot(reqs)
+        pipe.denoising_step(reqs, cfg_on, 0.0, 5.0, None, {}, None, None, None, True, 256)
+        torch.cuda.synchronize()
+        P.check_step(reqs, before, lambda r: sig,
+                     lambda r, x, kk: P.oracle_sdxl_prediction(sd, oc, r, x, sig[kk], ts[kk], cfg_on, 5.0),
+                     label=f"sdxl step {k}")
 
 
 def test_unsupported_arguments_raise(cuda):

@@ -10,6 +10,16 @@ exist on the GPU box, which is why the outputs are committed as small fixtures.
                    FlowMatchEulerDiscreteScheduler.batch_step
                    (diffusers/schedulers/*.py), imported with a stub `diffusers` base class
                    (the methods under test only read self.config.prediction_type).
+  step_sd3.npz   : ESyMReDStableDiffusion3Pipeline.denoising_step
+  step_sdxl.npz    (pipeline_stable_diffusion_3_esymred.py:232-388) and
+                   ESyMReDStableDiffusionXLPipeline.denoising_step
+                   (pipeline_stable_diffusion_xl_esymred.py:260-403): the reference's OWN step
+                   orchestration -- gather order, CFG duplication, conditioning order, per-request
+                   timesteps / sigmas, CFG combine, scheduler update, state side effects -- extracted
+                   with `ast` (the modules import diffusers) and executed with the reference's own
+                   scheduler + scheduler-state classes; the one substitution is the model:
+                   `self.transformer` / `self.unet` is the fp32 oracle forward (oracle/) on a tiny
+                   config, because the real model arithmetic lives in diffusers.
 """
 import ast
 import importlib.util
@@ -188,9 +198,139 @@ def gen_sched():
     np.savez_compressed(os.path.join(OUT, "sched_flow_match.npz"), **cases)
 
 
+def load_denoising_step(path, cls_name):
+    """The `denoising_step` method of the reference pipeline class, compiled from its own source."""
+    import typing
+    src = open(path).read()
+    for node in ast.walk(ast.parse(src)):
+        if isinstance(node, ast.ClassDef) and node.name == cls_name:
+            for item in node.body:
+                if isinstance(item, ast.FunctionDef) and item.name == "denoising_step":
+                    ns = {"torch": torch, "PipelineImageInput": typing.Any, "rescale_noise_cfg": None}
+                    ns.update({k: getattr(typing, k) for k in ("Optional", "List", "Tuple", "Union", "Dict", "Any",
+                                                               "Callable", "Type")})
+                    exec(compile(ast.Module(body=[item], type_ignores=[]), path, "exec"), ns)
+                    return ns["denoising_step"]
+    raise RuntimeError(f"{cls_name}.denoising_step not found in {path}")
+
+
+def _weights_checksum(sd):
+    return float(sum(v.double().abs().sum().item() for v in sd.values()))
+
+
+def gen_step():
+    """Two consecutive denoising steps of a mixed-resolution batch whose requests sit at DIFFERENT
+    step indices (what continuous batching produces), CFG on and off."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from oracle import schedulers as osch
+    from oracle import sd3_mmdit as o3
+    from oracle import sdxl_unet as ox
+    mods = load_ref_schedulers()
+    q = lambda t: t.to(torch.bfloat16).float()   # inputs / weights exactly representable in bf16
+
+    def make_reqs(States, tables, spec, start_idx, C, ctx, ctx_dim, pooled_dim, g, with_ids, scale=1.0):
+        reqs, rid = {}, 0
+        for res, n in spec.items():
+            side, reqs[res] = int(res) // 8, []
+            for _ in range(n):
+                sig, ts = tables
+                st = States(sigmas=sig.clone(), num_inference_steps=len(ts), timesteps=ts.clone())
+                st._step_index = st.timestep_idx = start_idx[rid]
+                po = types.SimpleNamespace(pooled_prompt_embeds=q(torch.randn(1, pooled_dim, generator=g)),
+                                           negative_pooled_prompt_embeds=q(torch.randn(1, pooled_dim, generator=g)))
+                if with_ids:
+                    po.add_time_ids = torch.tensor([[1024., 1024., 0., 0., 1024., 1024.]])
+                    po.negative_add_time_ids = po.add_time_ids.clone()
+                sp = types.SimpleNamespace(latents=q(torch.randn(1, C, side, side, generator=g) * scale),
+                                           prompt_embeds=q(torch.randn(1, ctx, ctx_dim, generator=g)),
+                                           negative_prompt_embeds=q(torch.randn(1, ctx, ctx_dim, generator=g)))
+                reqs[res].append(types.SimpleNamespace(request_id=rid, sampling_params=sp, prepare_output=po,
+                                                       scheduler_states=st))
+                rid += 1
+        return reqs
+
+    def record(cases, tag, reqs, step):
+        for rs in reqs.values():
+            for r in rs:
+                cases[f"{tag}_x{step}_{r.request_id}"] = r.sampling_params.latents.float().numpy()
+                cases[f"{tag}_idx{step}_{r.request_id}"] = np.asarray(
+                    [r.scheduler_states._step_index, r.scheduler_states.timestep_idx])
+
+    def record_inputs(cases, tag, reqs, with_ids):
+        for res, rs in reqs.items():
+            for r in rs:
+                i = r.request_id
+                cases[f"{tag}_res_{i}"] = np.asarray(int(res))
+                cases[f"{tag}_pe_{i}"] = r.sampling_params.prompt_embeds.numpy()
+                cases[f"{tag}_npe_{i}"] = r.sampling_params.negative_prompt_embeds.numpy()
+                cases[f"{tag}_pp_{i}"] = r.prepare_output.pooled_prompt_embeds.numpy()
+                cases[f"{tag}_npp_{i}"] = r.prepare_output.negative_pooled_prompt_embeds.numpy()
+                if with_ids:
+                    cases[f"{tag}_ids_{i}"] = r.prepare_output.add_time_ids.numpy()
+
+    # ---------------- SD3 (flow match, guidance 7.0)
+    step3 = load_denoising_step(f"{REF}/diffusers/pipelines/stable_diffusion_3/pipeline_stable_diffusion_3_esymred.py",
+                                "ESyMReDStableDiffusion3Pipeline")
+    cfg = o3.sd3_tiny_config()
+    sd = {k: q(v) for k, v in o3.init_sd3_weights(cfg, 0).items()}
+    calls = []
+
+    def transformer(hidden_states, timestep, encoder_hidden_states, pooled_projections, **kw):
+        calls.append({k: kw[k] for k in ("is_sliced", "patch_size", "input_indices")})
+        assert kw["joint_attention_kwargs"] is None and kw["return_dict"] is False
+        return (o3.sd3_forward(sd, cfg, hidden_states, encoder_hidden_states, pooled_projections, timestep),)
+
+    Fm = mods["scheduling_flow_match_euler_discrete"]
+    pipe = types.SimpleNamespace(transformer=transformer, scheduler=Fm.FlowMatchEulerDiscreteScheduler(),
+                                 joint_attention_kwargs=None)
+    cases = {"weights_checksum": np.asarray(_weights_checksum(sd)), "guidance": np.asarray(7.0),
+             "num_inference_steps": np.asarray(28)}
+    g = torch.Generator().manual_seed(11)
+    for tag, cfg_on in (("cfg", True), ("nocfg", False)):
+        reqs = make_reqs(Fm.FlowMatchEulerDiscreteSchedulerStates, osch.flow_match_sigmas(28),
+                         {"256": 2, "512": 1}, [0, 5, 12], cfg.in_channels, cfg.context_len,
+                         cfg.joint_attention_dim, cfg.pooled_projection_dim, g, False)
+        record_inputs(cases, tag, reqs, False)
+        record(cases, tag, reqs, 0)
+        for k in (1, 2):
+            step3(pipe, reqs, cfg_on, 7.0, True, 256)
+            record(cases, tag, reqs, k)
+    assert calls[0]["input_indices"]["256"] == ["0", "1", "0-1", "1-1"]
+    np.savez_compressed(os.path.join(OUT, "step_sd3.npz"), **cases)
+
+    # ---------------- SDXL (Euler epsilon, guidance 5.0)
+    stepx = load_denoising_step(f"{REF}/diffusers/pipelines/stable_diffusion_xl/pipeline_stable_diffusion_xl_esymred.py",
+                                "ESyMReDStableDiffusionXLPipeline")
+    oc = ox.sdxl_tiny_config()
+    sdx = {k: q(v) for k, v in ox.init_unet_weights(oc, 0).items()}
+
+    def unet(sample, t, encoder_hidden_states, added_cond_kwargs, **kw):
+        assert kw["timestep_cond"] is None and kw["cross_attention_kwargs"] is None
+        return (ox.unet_forward(sdx, oc, sample, t, encoder_hidden_states, added_cond_kwargs["text_embeds"],
+                                added_cond_kwargs["time_ids"]),)
+
+    Eu = mods["scheduling_euler_discrete"]
+    pipe = types.SimpleNamespace(unet=unet, scheduler=Eu.EulerDiscreteScheduler(prediction_type="epsilon"))
+    sig, ts, init_sigma = osch.euler_sigmas(50)
+    cases = {"weights_checksum": np.asarray(_weights_checksum(sdx)), "guidance": np.asarray(5.0),
+             "num_inference_steps": np.asarray(50)}
+    for tag, cfg_on in (("cfg", True), ("nocfg", False)):
+        reqs = make_reqs(Eu.EulerDiscreteSchedulerStates, (sig, ts), {"256": 1, "768": 1}, [0, 17],
+                         oc.in_channels, oc.context_len, oc.cross_attention_dim, oc.pooled_dim, g, True,
+                         scale=init_sigma)
+        record_inputs(cases, tag, reqs, True)
+        record(cases, tag, reqs, 0)
+        for k in (1, 2):
+            stepx(pipe, reqs, cfg_on, 0.0, 5.0, None, {}, None, None, None, True, 256)
+            record(cases, tag, reqs, k)
+    np.savez_compressed(os.path.join(OUT, "step_sdxl.npz"), **cases)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_pack()
     gen_sched()
+    gen_step()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
