@@ -364,3 +364,93 @@ def test_vae_decoder_host_relayout_matches_oracle_semantics():
     assert torch.count_nonzero(m.w[a + ".qkv.bias"][2 * C:]) == 0
     assert torch.equal(m.w[a + ".v.bias"].float(), sd[a + ".to_v.bias"].bfloat16().float())
     assert m.w["decoder.conv_in.weight"].shape == (C, 64)      # K = 4 * 9 = 36 padded to 64
+
+
+def test_dispatch_board_is_the_live_greedy_rule():
+    """DispatchBoard (shared memory between the bench's rank processes) = GreedyDispath
+    (dispatcher/policy/greedy.py:16-36) on outstanding pixels; with nothing finished it reproduces
+    greedy_assign, and finished requests free their rank."""
+    import os
+    from sduss_b200.dp import DispatchBoard, greedy_assign
+    res = [512, 1024, 768, 768, 512, 1024, 512, 512, 768, 1024, 1024, 512]
+    name = f"sduss_b200_test_{os.getpid()}"
+    owner = DispatchBoard(name, len(res), 3, create=True)
+    other = DispatchBoard(name, len(res), 3, create=False)   # what another rank's process attaches to
+    try:
+        for i, r in enumerate(res):
+            owner.dispatch(i, r)
+        want = greedy_assign(res, 3)
+        got = [[i for i in range(len(res)) if other.assign[i] == k] for k in range(3)]
+        assert got == want
+        # rank 2 finishes everything it has: the next request must go there
+        for i in got[2]:
+            other.report_finished(2, res[i])
+        assert int(owner.dispatched[2] - owner.finished[2]) == 0
+        fresh = DispatchBoard(name + "b", 1, 3, create=True)
+        fresh.dispatched[:] = owner.dispatched
+        fresh.finished[:] = owner.finished
+        assert fresh.dispatch(0, 512) == 2
+        fresh.close()
+    finally:
+        other.close()
+        owner.close()
+
+
+_SERVE_WORKER = r"""
+import os, sys, time, json, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from types import SimpleNamespace
+from tools import serve_replay as sr
+
+class FakeWorker:
+    # stands in for the GPU worker: a step advances every request's scheduler state and takes 2 ms
+    dev = torch.device("cpu")
+    def __init__(self): self.plans = set(); self.posted = []
+    def new_request(self, rid, res):
+        return SimpleNamespace(request_id=rid, scheduler_states=SimpleNamespace(_step_index=0))
+    def call(self, batch):
+        self.plans.add(tuple(sorted((k, len(v)) for k, v in batch.items())))
+        assert sum(len(v) for v in batch.values()) <= sr.MAX_BATCH
+        time.sleep(0.002)
+        for rs in batch.values():
+            for r in rs: r.scheduler_states._step_index += 1
+    def throttle(self): pass
+    def sync(self): pass
+    def n_plans(self): return len(self.plans)
+    def post(self, fin): self.posted += [r.request_id for rs in fin.values() for r in rs]
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+sr.STEPS["sd3"] = 5
+w = FakeWorker()
+trace = sr.load_trace("sd3", 40, 200.0)
+rec = sr.serve_run("sd3", w, trace, rank, world, dist, "cputest")
+posted = [None] * world
+dist.all_gather_object(posted, w.posted)
+if rank == 0:
+    rec["posted"] = posted
+    print("RESULT " + json.dumps(rec))
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_serving_replay(tmp_path):
+    """bench.py --serve's host logic on 2 CPU ranks (gloo): the reference trace fixture is
+    dispatched live by the greedy rule, every request is served exactly once by exactly one rank,
+    batches never exceed max_batchsize, both ranks get work, and the record carries the serving keys."""
+    import json
+    script = tmp_path / "serve_worker.py"
+    script.write_text(_SERVE_WORKER.format(root=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29631")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29631", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")][0]
+    rec = json.loads(line[len("RESULT "):])
+    served = sorted(i for p in rec["posted"] for i in p)
+    assert served == list(range(40))
+    assert sum(rec["served_per_rank"]) == 40 and min(rec["served_per_rank"]) >= 10
+    assert rec["requests"] == 40 and rec["steps_per_request"] == 5 and rec["req_s"] > 0
+    assert rec["latency_s"]["p99"] >= rec["latency_s"]["p50"] > 0
+    assert len(rec["runner_cpu_utilisation_per_rank"]) == 2 and "host_cpu_percent" in rec

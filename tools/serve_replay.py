@@ -1,0 +1,246 @@
+"""Serving replay on N data-parallel B200 workers: BASELINE configs[2] (SDXL-base, 50 steps) and
+configs[3] (SD3.5-medium, 28 steps), `bench.py --serve` and the `serve` sub-records of the default
+bench line.
+
+What is replayed (reference: tests/server/esymred_test.py:195-215 drives the server with
+exp/<model>/qps_<q>.csv rows = arrival ms, resolution, steps):
+  * arrivals  : the first rows of the reference's own trace exp/<model>/qps_8.0.csv (committed as
+                tests/fixtures/traces/<model>_qps_8.0.csv), arrival times rescaled to the offered
+                rate (a Poisson process stays Poisson under time scaling);
+  * dispatch  : the reference's GreedyDispath rule (dispatcher/policy/greedy.py:16-36), live: a
+                dispatcher thread in rank 0 places each request, at its arrival time, on the rank
+                with the fewest outstanding pixels (sduss_b200.dp.DispatchBoard, shared memory);
+  * batching  : per rank, `fcfs_mixed`-style continuous batching (worker/scheduler/policy/
+                FCFS_Mixed.py): every dispatched request joins the running mixed-resolution batch
+                at the next step boundary, up to max_batchsize 12 (scripts/paper/e2e.sh:73);
+  * per step  : this repo's drop-in `denoising_step` over the whole mixed batch;
+  * post stage: every request that finished at a step goes through the B200 VAE decoder
+                (post_inference, row f-4) before it counts as served.
+Not simulated: the prepare stage (text encoders; requests arrive with random embeddings), HTTP,
+PIL conversion. One process per GPU, no collective on the data path; torch.distributed only
+synchronises the start and gathers the per-rank results.
+"""
+import json
+import os
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STEPS = {"sd3": 28, "sdxl": 50}
+MAX_BATCH = 12
+
+
+def load_trace(kind, n, qps):
+    """(arrival seconds, resolution) x n from the committed reference trace, rescaled to `qps`."""
+    rows = np.loadtxt(os.path.join(ROOT, "tests", "fixtures", "traces", f"{kind}_qps_8.0.csv"),
+                      delimiter=",", skiprows=1)
+    assert n <= rows.shape[0], f"trace fixture holds {rows.shape[0]} rows"
+    t = rows[:n, 0] / 1000.0 * (8.0 / qps)
+    return [(float(a), str(int(r))) for a, r in zip(t, rows[:n, 1])]
+
+
+class _Worker:
+    def __init__(self, kind, dev, seed):
+        import bench
+        from sduss_b200 import synthetic
+        from sduss_b200.vae import B200VAEDecoder, VAEDecoderConfig
+        self.kind, self.dev = kind, dev
+        self.cfg, sd, self.pipe, self.make, self.call = bench.build_pipeline(kind, dev)
+        del sd
+        vcfg = VAEDecoderConfig() if kind == "sdxl" else VAEDecoderConfig(
+            latent_channels=16, scaling_factor=1.5305, shift_factor=0.0609, use_post_quant_conv=False)
+        self.pipe.vae = B200VAEDecoder(synthetic.random_vae_state_dict(vcfg, dev), vcfg, device=dev)
+        # a small pool of synthetic conditioning per resolution (stands in for the prepare stage)
+        self.pool = {res: [self.make({res: 1}, STEPS[kind], seed + 17 * j)[res][0] for j in range(4)]
+                     for res in ("512", "768", "1024")}
+        self.seed = seed
+
+    def new_request(self, rid, res):
+        """A fresh request object with its own latents and scheduler state; conditioning tensors are
+        cloned so the step's per-request conditioning cache sees a new prompt (as in serving)."""
+        import copy
+        proto = self.pool[res][rid % 4]
+        r = copy.copy(proto)
+        r.request_id = rid
+        r.sampling_params = copy.copy(proto.sampling_params)
+        r.sampling_params.latents = torch.randn_like(proto.sampling_params.latents)
+        r.sampling_params.prompt_embeds = proto.sampling_params.prompt_embeds.clone()
+        r.sampling_params.negative_prompt_embeds = proto.sampling_params.negative_prompt_embeds.clone()
+        r.scheduler_states = copy.deepcopy(proto.scheduler_states)
+        return r
+
+    def sync(self):
+        torch.cuda.synchronize()
+
+    def throttle(self, depth=2):
+        """The steps are asynchronous; let the host run at most `depth` steps ahead of the GPU so
+        that a request that arrives now joins the batch at (nearly) the GPU's next step boundary."""
+        q = self.__dict__.setdefault("_inflight", [])
+        ev = torch.cuda.Event()
+        ev.record()
+        q.append(ev)
+        if len(q) > depth:
+            q.pop(0).synchronize()
+
+    def n_plans(self):
+        return len(self.pipe.model._plans)
+
+    def post(self, finished):
+        self.pipe.post_inference(finished, "pt")
+
+    def warm(self):
+        """Touch the kernels / allocator once per resolution so the replay does not time lazy init."""
+        for res in ("512", "768", "1024"):
+            r = self.new_request(-1, res)
+            for _ in range(2):
+                self.call({res: [r]})
+            self.pipe.post_inference({res: [r]}, "pt")
+        torch.cuda.synchronize()
+
+
+def serve_run(kind, worker, trace, rank, world, dist, tag):
+    """One replay. Returns the result record on rank 0 (None elsewhere)."""
+    from sduss_b200.dp import DispatchBoard
+    n_req, steps = len(trace), STEPS[kind]
+    board_name = f"sduss_b200_{tag}_{os.environ.get('MASTER_PORT', '0')}_{kind}"
+    board = DispatchBoard(board_name, n_req, world, create=True) if rank == 0 else None
+    if dist is not None:
+        dist.barrier()
+    if board is None:
+        board = DispatchBoard(board_name, n_req, world, create=False)
+    # common start time
+    t0 = [time.time() + 0.5]
+    if dist is not None:
+        dist.broadcast_object_list(t0, src=0, **({"device": worker.dev} if worker.dev.type == "cuda" else {}))
+    t0 = t0[0]
+    stop = threading.Event()
+
+    def dispatcher():
+        for i, (ta, res) in enumerate(trace):
+            while not stop.is_set():
+                dt = t0 + ta - time.time()
+                if dt <= 0:
+                    break
+                time.sleep(min(dt, 0.005))
+            board.dispatch(i, int(res))
+
+    th = None
+    if rank == 0:
+        th = threading.Thread(target=dispatcher, daemon=True)
+        th.start()
+    import psutil
+    psutil.cpu_percent(None)
+    proc = psutil.Process()
+    cpu0 = proc.cpu_times()
+    plans0, n_steps, batch_sizes = worker.n_plans(), 0, []
+    running, lat, scanned, mine_done, finish_t = [], [], 0, 0, t0
+    waiting = []
+    while True:
+        # newly dispatched requests, in arrival order
+        while scanned < n_req and board.assign[scanned] >= 0:
+            if board.assign[scanned] == rank:
+                waiting.append(scanned)
+            scanned += 1
+        while waiting and len(running) < MAX_BATCH:
+            i = waiting.pop(0)
+            running.append((i, worker.new_request(i, trace[i][1])))
+        if not running:
+            if scanned >= n_req:
+                break
+            time.sleep(0.001)
+            continue
+        batch = {}
+        for i, r in running:
+            batch.setdefault(trace[i][1], []).append(r)
+        worker.call(batch)
+        worker.throttle()
+        n_steps += 1
+        batch_sizes.append(len(running))
+        keep, fin = [], {}
+        for i, r in running:
+            if r.scheduler_states._step_index >= steps:
+                fin.setdefault(trace[i][1], []).append((i, r))
+            else:
+                keep.append((i, r))
+        if fin:
+            worker.post({res: [r for _, r in v] for res, v in fin.items()})
+            worker.sync()
+            now = time.time()
+            for res, v in fin.items():
+                for i, _ in v:
+                    lat.append(now - (t0 + trace[i][0]))
+                    board.report_finished(rank, int(res))
+                    mine_done += 1
+            finish_t = now
+        running = keep
+    worker.sync()
+    stop.set()
+    cpu1 = proc.cpu_times()
+    wall_rank = finish_t - t0
+    host_cpu = psutil.cpu_percent(None)
+    rec = {"rank": rank, "served": mine_done, "wall_s": wall_rank, "lat": lat, "steps": n_steps,
+           "mean_batch": float(np.mean(batch_sizes)) if batch_sizes else 0.0,
+           "new_plans": worker.n_plans() - plans0,
+           "proc_cpu_s": (cpu1.user + cpu1.system) - (cpu0.user + cpu0.system), "host_cpu_percent": host_cpu}
+    allrec = [rec]
+    if dist is not None:
+        allrec = [None] * world
+        dist.all_gather_object(allrec, rec)
+    if th is not None:
+        th.join(timeout=1.0)
+    if dist is not None:
+        dist.barrier()
+    board.close()
+    if rank != 0:
+        return None
+    wall = max(r["wall_s"] for r in allrec)
+    lats = np.asarray([x for r in allrec for x in r["lat"]])
+    offered = n_req / trace[-1][0]
+    return {"req_s": n_req / wall, "offered_req_s": offered, "requests": n_req, "steps_per_request": steps,
+            "wall_s": wall, "latency_s": {"mean": float(lats.mean()), "p50": float(np.percentile(lats, 50)),
+                                          "p99": float(np.percentile(lats, 99))},
+            "batch_steps_per_s": sum(r["steps"] for r in allrec) / wall,
+            "request_steps_per_s": n_req * steps / wall,
+            "mean_batch": float(np.mean([r["mean_batch"] for r in allrec])),
+            "served_per_rank": [r["served"] for r in allrec],
+            "new_compositions_per_rank": [r["new_plans"] for r in allrec],
+            "runner_cpu_utilisation_per_rank": [round(r["proc_cpu_s"] / max(r["wall_s"], 1e-9), 3) for r in allrec],
+            "host_cpu_percent": allrec[0]["host_cpu_percent"], "host_cores": os.cpu_count(),
+            "max_batchsize": MAX_BATCH, "policy": "greedy dispatch + fcfs_mixed continuous batching",
+            "stages": "denoising steps + VAE decode (post_inference); prepare stage not simulated",
+            "trace": f"reference exp/{kind}/qps_8.0.csv rows 0..{n_req - 1}, arrivals rescaled to {offered:.2f} req/s"}
+
+
+def serve_main(args, rank, world, local_rank):
+    """bench.py --serve [--model sd3|sdxl|both] [--qps Q per GPU] [--requests R per GPU]."""
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    kinds = ["sd3", "sdxl"] if args.model == "both" else [args.model]
+    out = {}
+    for kind in kinds:
+        w = _Worker(kind, dev, seed=1000 * rank)
+        w.warm()
+        per_gpu_q = args.qps if args.qps > 0 else 4.0
+        n = (args.requests if args.requests > 0 else 48) * world
+        rec = serve_run(kind, w, load_trace(kind, n, per_gpu_q * world), rank, world, dist, "serve")
+        if rank == 0:
+            out[kind] = rec
+        del w
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+    if rank == 0:
+        k0 = kinds[0]
+        line = {"metric": f"served requests/s ({'+'.join(kinds)}; denoise + VAE decode, reference arrival trace)",
+                "value": out[k0]["req_s"], "unit": "req/s", "n_gpus": world, "higher_is_better": True,
+                "scaling": "weak", "data": "synthetic", "dtype": "bf16", "serve": out}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
