@@ -67,6 +67,9 @@ typedef struct B200EpilogueDesc {
   int32_t rms_k_cols;   /* columns [q_cols, q_cols + k_cols) are k heads                  */
   float rms_eps;
   float q_scale;        /* folded into normalised q (softmax scale * log2(e))             */
+  int32_t act;          /* activation of B200_EPI_GELU_TANH / gate of B200_EPI_GEGLU:     */
+                        /* 0 = the mode's default (tanh-GELU / erf-GELU), 1 tanh-GELU,    */
+                        /* 2 erf-GELU, 3 quick-GELU x*sigmoid(1.702x) (text encoders)     */
 } B200EpilogueDesc;
 
 /* A: [M, lda] bf16, W: [N, ldw] bf16 (K contiguous in both). N, K, lda, ldw, ldc multiples
@@ -114,6 +117,23 @@ int b200_attn_build_schedule(const int32_t* seq_table, int n_seq, int n_heads,
 int b200_attn_varlen_bf16(const B200AttnSource* src_a, const B200AttnSource* src_b,
                           const int32_t* seq_table, const int32_t* work_units, int n_units,
                           int32_t* sched_state, int max_ctas, float softmax_scale, void* stream);
+
+/* The same kernel with the two variants the PREPARE stage's text encoders need (SURVEY.md row f-4;
+ * transformers CLIPAttention / T5Attention reached from encode_prompt,
+ * pipeline_stable_diffusion_3_esymred.py:119-141): a causal mask (CLIP: key position <= query
+ * position inside the sequence) and an additive relative position bias (T5):
+ * logits[q, k] += rel_bias[head * rel_ld + (k - q) + rel_len - 1], fp32, pre-divided by softmax_scale,
+ * valid for sequences of up to rel_len tokens (rel_ld >= 2 rel_len - 1). extra == NULL: plain. */
+typedef struct B200AttnExtra {
+  int32_t causal;
+  int32_t rel_len;
+  const float* rel_bias;
+  int32_t rel_ld;
+} B200AttnExtra;
+int b200_attn_varlen_ex(const B200AttnSource* src_a, const B200AttnSource* src_b,
+                        const int32_t* seq_table, const int32_t* work_units, int n_units,
+                        int32_t* sched_state, int max_ctas, float softmax_scale,
+                        const B200AttnExtra* extra, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * HBM-bound kernels (coalesced 16-byte vectors, warp-shuffle reductions).
@@ -259,6 +279,17 @@ int b200_split_patches(const uint64_t* lat_ptr, const int32_t* ldesc, const int3
                        int n_patches, int C, int ps, void* out, void* stream);
 int b200_concat_patches(const void* patches, const int32_t* ldesc, const int32_t* pdesc,
                         int n_patches, int C, int ps, const uint64_t* out_ptr, void* stream);
+
+/* ---- Prepare stage (text encoders behind encode_prompt,
+ * pipeline_stable_diffusion_3_esymred.py:119-141, pipeline_stable_diffusion_xl_esymred.py:120-160).
+ * Linear layers, CLIP's LayerNorm and the attention run on the kernels above; these two are added. */
+/* out[i, :] = table[ids[i], :] (+ pos[i % seq_len, :] when pos != NULL): CLIPTextEmbeddings
+ * (token + learned position embedding) / T5 embed_tokens. ids: DEVICE int32 [n]. D % 8 == 0. */
+int b200_embed_rows_bf16(const int32_t* ids, int n, const void* table, int vocab, int D,
+                         const void* pos, int seq_len, void* out, int ldo, void* stream);
+/* y = weight * bf16(x * rsqrt(mean(x^2) + eps)): T5LayerNorm (no mean subtraction, no bias). */
+int b200_rmsnorm_bf16(const void* x, int ldx, int T, int D, float eps, const void* weight, void* y,
+                      int ldy, void* stream);
 
 /* ---- VAE decode stage (post_inference, pipeline_stable_diffusion_xl_esymred.py:
  * 406-462 and pipeline_stable_diffusion_3_esymred.py:391-415). The decoder's convolutions, GroupNorms,

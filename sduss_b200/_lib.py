@@ -33,7 +33,17 @@ class EpilogueDesc(ctypes.Structure):
         ("rms_wq", c_void_p), ("rms_wk", c_void_p),
         ("rms_q_cols", ctypes.c_int32), ("rms_k_cols", ctypes.c_int32),
         ("rms_eps", c_float), ("q_scale", c_float),
+        ("act", ctypes.c_int32),
     ]
+
+
+ACT_DEFAULT, ACT_GELU_TANH, ACT_GELU_ERF, ACT_QUICK_GELU = 0, 1, 2, 3
+
+
+class AttnExtra(ctypes.Structure):
+    """Mirror of B200AttnExtra: causal mask / relative position bias of the text encoders."""
+    _fields_ = [("causal", ctypes.c_int32), ("rel_len", ctypes.c_int32), ("rel_bias", c_void_p),
+                ("rel_ld", ctypes.c_int32)]
 
 
 class AttnSource(ctypes.Structure):
@@ -83,6 +93,12 @@ SIGNATURES = {
     "b200_attn_build_schedule": [c_void_p, c_int, c_int, c_void_p, ctypes.POINTER(c_int)],
     "b200_attn_varlen_bf16": [ctypes.POINTER(AttnSource), ctypes.POINTER(AttnSource), c_void_p,
                               c_void_p, c_int, c_void_p, c_int, c_float, c_void_p],
+    "b200_attn_varlen_ex": [ctypes.POINTER(AttnSource), ctypes.POINTER(AttnSource), c_void_p,
+                            c_void_p, c_int, c_void_p, c_int, c_float, ctypes.POINTER(AttnExtra),
+                            c_void_p],
+    "b200_embed_rows_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
+                             c_void_p],
+    "b200_rmsnorm_bf16": [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p],
     "b200_layernorm_mod_bf16": [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                 c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
                                 c_int, c_void_p, c_int, c_void_p],

@@ -90,6 +90,10 @@ struct AttnArgs {
   int ldo[2];
   int o_col[2];
   float scale_log2;                  // softmax scale * log2(e)
+  // prepare-stage variants (text encoders; uniform per launch, off on the denoising path):
+  int causal;                        // CLIP: key position <= query position
+  const float* rel_bias;             // T5: logits += rel_bias[head][k_pos - q_pos + rel_len - 1]
+  int rel_len, rel_ld;               //     (already divided by the softmax scale)
   long long* dbg;                    // optional phase cycle counters (ATT_TIMING builds)
 };
 
@@ -104,7 +108,7 @@ struct AttnArgs {
 // One work unit, decoded from the tables (written once per plan, not by the preceding kernel:
 // safe to read before pdl_wait()).
 struct AttnUnit {
-  int q_seg, q_row0, q_rows, nq, head;
+  int q_seg, q_row0, q_rows, nq, head, q_pos0;
   int ka_row, ka_len, kb_row, kb_len, nA, n_tiles;
 };
 
@@ -117,6 +121,7 @@ __device__ __forceinline__ AttnUnit load_unit(const AttnArgs& a, int u) {
   w.head = item.w;
   const int seg_row = w.q_seg == 0 ? q.x : q.z, seg_len = w.q_seg == 0 ? q.y : q.w;
   w.q_row0 = seg_row + item.z;
+  w.q_pos0 = (w.q_seg == 0 ? 0 : q.y) + item.z;     // position of the unit's first query in its sequence
   w.q_rows = min(ATT_NQ * ATT_BM, seg_len - item.z);  // valid query rows of this unit
   w.nq = (w.q_rows + ATT_BM - 1) / ATT_BM;            // active query tiles
   w.ka_row = k.x; w.ka_len = k.y; w.kb_row = k.z; w.kb_len = k.w;
@@ -415,6 +420,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
           for (int i = 0; i < ATT_BN; ++i)
             if (i >= n_valid) s[i] = -INFINITY;
         }
+        if (a.causal != 0 || a.rel_bias != nullptr) {
+          // text-encoder variants: T5 relative position bias and / or CLIP's causal mask
+          const int qpos = w.q_pos0 + t * ATT_BM + r;
+          const int kpos0 = inA ? j * ATT_BN : w.ka_len + (j - w.nA) * ATT_BN;
+          if (a.rel_bias != nullptr && t * ATT_BM + r < w.q_rows) {
+            const float* bh = a.rel_bias + size_t(w.head) * a.rel_ld + (kpos0 - qpos + a.rel_len - 1);
+#pragma unroll
+            for (int i = 0; i < ATT_BN; ++i)
+              if (i < n_valid) s[i] += __ldg(bh + i);
+          }
+          if (a.causal != 0) {
+#pragma unroll
+            for (int i = 0; i < ATT_BN; ++i)
+              if (kpos0 + i > qpos) s[i] = -INFINITY;
+          }
+        }
         // 8 independent chains (one long fmax chain would expose its full latency)
         float mx8[8];
 #pragma unroll
@@ -612,7 +633,17 @@ extern "C" int b200_attn_varlen_bf16(const B200AttnSource* src_a, const B200Attn
                                      const int32_t* seq_table, const int32_t* work_units,
                                      int n_units, int32_t* sched_state, int max_ctas,
                                      float softmax_scale, void* stream_) {
+  return b200_attn_varlen_ex(src_a, src_b, seq_table, work_units, n_units, sched_state, max_ctas,
+                             softmax_scale, nullptr, stream_);
+}
+
+extern "C" int b200_attn_varlen_ex(const B200AttnSource* src_a, const B200AttnSource* src_b,
+                                   const int32_t* seq_table, const int32_t* work_units,
+                                   int n_units, int32_t* sched_state, int max_ctas,
+                                   float softmax_scale, const B200AttnExtra* extra, void* stream_) {
   if (!src_a || !seq_table || !work_units || !sched_state || n_units <= 0 || max_ctas < 0)
+    return B200_ERR_INVALID;
+  if (extra && extra->rel_bias && (extra->rel_len <= 0 || extra->rel_ld < 2 * extra->rel_len - 1))
     return B200_ERR_INVALID;
   const int n_ctas = std::min(n_units, max_ctas > 0 ? max_ctas : device_sm_count());
   const B200AttnSource* srcs[2] = {src_a, src_b ? src_b : src_a};
@@ -650,6 +681,10 @@ extern "C" int b200_attn_varlen_bf16(const B200AttnSource* src_a, const B200Attn
   a.sched = sched_state;
   a.n_units = n_units;
   a.scale_log2 = softmax_scale * 1.4426950408889634f;
+  a.causal = extra ? extra->causal : 0;
+  a.rel_bias = extra ? extra->rel_bias : nullptr;
+  a.rel_len = extra ? extra->rel_len : 0;
+  a.rel_ld = extra ? extra->rel_ld : 0;
   a.dbg = nullptr;
 #ifdef ATT_TIMING
   {

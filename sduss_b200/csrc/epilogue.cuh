@@ -33,6 +33,8 @@ struct EpiArgs {
   int rms_k_cols;              // columns [q_cols, q_cols + k_cols) are k heads
   float rms_eps;
   float q_scale;               // multiplied into normalised q (softmax scale * log2 e)
+  int act;                     // activation of EPI_GELU_TANH / gate of EPI_GEGLU: 0 = the mode's
+                               // default (tanh-GELU / erf-GELU), 1 tanh-GELU, 2 erf-GELU, 3 quick-GELU
 };
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
@@ -44,6 +46,28 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 }
 __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.f + erff(x * 0.7071067811865476f));
+}
+
+__device__ __forceinline__ float quick_gelu_f(float x) {  // x * sigmoid(1.702 x)   (CLIP-L)
+  return x / (1.f + __expf(-1.702f * x));
+}
+// Runtime-selected activation (uniform per launch): the text encoders of the prepare stage use
+// erf-GELU (CLIP-G), quick-GELU (CLIP-L) and a tanh-GELU gate (T5 v1.1) on the same templates.
+// The selector is tested ONCE per chunk, outside the element loops: the hot epilogues (SD3 FF1: tanh,
+// SDXL GEGLU: erf) keep a single straight-line activation loop.
+template <int N>
+__device__ __forceinline__ void act_inplace(float* v, int act, int dflt) {
+  const int a = act == 0 ? dflt : act;
+  if (a == 1) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = gelu_tanh_f(v[j]);
+  } else if (a == 2) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = gelu_erf_f(v[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = quick_gelu_f(v[j]);
+  }
 }
 
 __device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float* out) {
@@ -73,8 +97,7 @@ __device__ __forceinline__ void epilogue_chunk64(const EpiArgs& e, float* acc, i
     }
   }
   if constexpr (EPI == EPI_GELU_TANH) {
-#pragma unroll
-    for (int j = 0; j < 64; ++j) acc[j] = gelu_tanh_f(acc[j]);
+    act_inplace<64>(acc, e.act, 1);
   }
   if constexpr (EPI == EPI_ROWVEC) {
     const int g = e.row_group[row];
@@ -138,8 +161,9 @@ __device__ __forceinline__ void epilogue_chunk64(const EpiArgs& e, float* acc, i
   }
   if constexpr (EPI == EPI_GEGLU) {
     // chunk = [32 hidden | 32 gate] -> 32 output columns at n0/2
+    act_inplace<32>(acc + 32, e.act, 2);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = acc[j] * gelu_erf_f(acc[32 + j]);
+    for (int j = 0; j < 32; ++j) acc[j] = acc[j] * acc[32 + j];
     __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(e.C) + size_t(row) * e.ldc + (n0 >> 1);
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
@@ -207,8 +231,7 @@ __device__ __forceinline__ void epilogue_math64(const EpiArgs& e, float* acc, in
     }
   }
   if constexpr (EPI == EPI_GELU_TANH) {
-#pragma unroll
-    for (int j = 0; j < 64; ++j) acc[j] = gelu_tanh_f(acc[j]);
+    act_inplace<64>(acc, e.act, 1);
   }
   if constexpr (EPI == EPI_ROWVEC) {
     const int g = row_ok ? e.row_group[row] : 0;
@@ -267,8 +290,9 @@ __device__ __forceinline__ void epilogue_math64(const EpiArgs& e, float* acc, in
     }
   }
   if constexpr (EPI == EPI_GEGLU) {
+    act_inplace<32>(acc + 32, e.act, 2);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = acc[j] * gelu_erf_f(acc[32 + j]);
+    for (int j = 0; j < 32; ++j) acc[j] = acc[j] * acc[32 + j];
   }
 }
 

@@ -374,6 +374,7 @@ extern "C" int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
   e.rms_k_cols = ep->rms_k_cols;
   e.rms_eps = ep->rms_eps;
   e.q_scale = ep->q_scale;
+  e.act = ep->act;
   GemmShape s{M, N, K};
   // output / residual tensor maps of the staged epilogue (bf16 outputs only)
   CUtensorMap tmC = tmA, tmR = tmA;

@@ -276,7 +276,7 @@ def _req(t, dtype=torch.bfloat16):
 
 def gemm(a, w, out=None, *, epi=EPI_BIAS, bias=None, resid=None, gate=None, row_group=None,
          rowvec=None, rms_wq=None, rms_wk=None, rms_q_cols=0, rms_k_cols=0, rms_eps=1e-6,
-         q_scale=1.0, out_fp32=False):
+         q_scale=1.0, out_fp32=False, act=0):
     """out = epilogue(a @ w.T). a: [M, K] bf16 (row stride may exceed K), w: [N, K] bf16."""
     _req(a), _req(w)
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
@@ -297,7 +297,7 @@ def gemm(a, w, out=None, *, epi=EPI_BIAS, bias=None, resid=None, gate=None, row_
     d.rowvec, d.ldv = _ptr(rowvec), (rowvec.stride(0) if rowvec is not None else 0)
     d.rms_wq, d.rms_wk = _ptr(rms_wq), _ptr(rms_wk)
     d.rms_q_cols, d.rms_k_cols = rms_q_cols, rms_k_cols
-    d.rms_eps, d.q_scale = rms_eps, q_scale
+    d.rms_eps, d.q_scale, d.act = rms_eps, q_scale, act
     _ev = _count("b200_gemm_bf16", (M, N, K, epi))
     check(lib.b200_gemm_bf16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), M, N, K, epi,
                              ctypes.byref(d), _stream()), "b200_gemm_bf16")
@@ -353,15 +353,50 @@ def build_attn_plan(seqs, device, n_heads, max_ctas=None):
             attn_max_ctas() if max_ctas is None else max_ctas)
 
 
-def attn_varlen(src_a, src_b, seq_table, work_units, n_units, sched_state, max_ctas, scale):
+def attn_varlen(src_a, src_b, seq_table, work_units, n_units, sched_state, max_ctas, scale,
+                causal=False, rel_bias=None, rel_len=0):
+    """rel_bias: fp32 [heads, >= 2 rel_len - 1], bias of key offset (k - q) at column k - q + rel_len - 1,
+    already divided by `scale` (T5); causal: CLIP's mask. Both off on the denoising path."""
     _ev = _count("b200_attn_varlen_bf16")
-    check(lib.b200_attn_varlen_bf16(ctypes.byref(src_a),
-                                    ctypes.byref(src_b) if src_b is not None else None,
-                                    _ptr(seq_table), _ptr(work_units), n_units, _ptr(sched_state),
-                                    max_ctas, ctypes.c_float(scale), _stream()),
-          "b200_attn_varlen_bf16")
+    extra = None
+    if causal or rel_bias is not None:
+        extra = _lib.AttnExtra()
+        extra.causal = int(causal)
+        if rel_bias is not None:
+            _req(rel_bias, torch.float32)
+            assert rel_bias.dim() == 2 and rel_bias.stride(1) == 1
+            extra.rel_bias, extra.rel_len, extra.rel_ld = _ptr(rel_bias), rel_len, rel_bias.stride(0)
+    check(lib.b200_attn_varlen_ex(ctypes.byref(src_a),
+                                  ctypes.byref(src_b) if src_b is not None else None,
+                                  _ptr(seq_table), _ptr(work_units), n_units, _ptr(sched_state),
+                                  max_ctas, ctypes.c_float(scale),
+                                  ctypes.byref(extra) if extra is not None else None, _stream()),
+          "b200_attn_varlen_ex")
     if _ev is not None:
         _ev.record()
+
+
+def embed_rows(ids, table, out, pos=None, seq_len=0):
+    """out[i] = table[ids[i]] (+ pos[i % seq_len]); ids int32 on the device."""
+    _req(ids, torch.int32), _req(table), _req(out)
+    n, D = ids.numel(), table.shape[1]
+    _ev = _count("b200_embed_rows_bf16")
+    check(lib.b200_embed_rows_bf16(_ptr(ids), n, _ptr(table), table.shape[0], D, _ptr(pos), seq_len,
+                                   _ptr(out), out.stride(0), _stream()), "b200_embed_rows_bf16")
+    if _ev is not None:
+        _ev.record()
+    return out
+
+
+def rmsnorm(x, weight, y, eps):
+    _req(x), _req(weight), _req(y)
+    T, D = x.shape
+    _ev = _count("b200_rmsnorm_bf16")
+    check(lib.b200_rmsnorm_bf16(_ptr(x), x.stride(0), T, D, ctypes.c_float(eps), _ptr(weight), _ptr(y),
+                                y.stride(0), _stream()), "b200_rmsnorm_bf16")
+    if _ev is not None:
+        _ev.record()
+    return y
 
 
 # ------------------------------------------------------------------ HBM-bound kernels

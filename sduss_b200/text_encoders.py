@@ -1,0 +1,278 @@
+"""The PREPARE stage's text encoders on the B200 kernels (second half).
+
+The reference's `prepare_inference` (pipeline_stable_diffusion_3_esymred.py:49-230,
+pipeline_stable_diffusion_xl_esymred.py:56-258) calls diffusers' `encode_prompt`, i.e. transformers'
+CLIPTextModel(WithProjection) x2 and, for SD3, the T5-XXL encoder, once per arriving batch of
+requests. With a 43 ms denoising step and a 15 ms VAE decode this is the largest stage left on
+stock kernels (T5-XXL alone is 4.8 TFLOP per request with its negative prompt: one denoising step).
+
+Everything runs on the denoising path's kernels: tcgen05 GEMMs with fused bias / activation /
+residual epilogues (activation selected at run time: quick-GELU for CLIP-L, erf-GELU for CLIP-G,
+tanh-GELU gate for T5), the packed varlen attention kernel (head_dim 64 in all three encoders) with
+its causal (CLIP) and relative-position-bias (T5) variants, the LayerNorm kernel, plus
+b200_embed_rows_bf16 and b200_rmsnorm_bf16. One plan (workspaces + CUDA graph) per batch size.
+
+Inputs are TOKEN IDS (the tokenizers are host-side Python in the reference as well); outputs are
+what `encode_prompt` returns: the penultimate CLIP hidden states, the projected EOS embedding, the
+T5 encoder output, assembled into `prompt_embeds` / `pooled_prompt_embeds`.
+"""
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import ACT_GELU_ERF, ACT_GELU_TANH, ACT_QUICK_GELU
+
+
+def _cfg(cfg, name, default=None):
+    if isinstance(cfg, dict):
+        return cfg.get(name, default)
+    return getattr(cfg, name, default)
+
+
+class _Plan:
+    """Workspaces of one batch size: every buffer is rewritten by each forward before it is read."""
+
+    def __init__(self, device):
+        self.device, self.bufs, self.graph, self.graph_launches = device, {}, None, 0
+        self.attn = {}
+
+    def buf(self, name, shape, dtype=torch.bfloat16):
+        t = self.bufs.get(name)
+        if t is None:
+            t = self.bufs[name] = torch.empty(shape, device=self.device, dtype=dtype)
+        assert tuple(t.shape) == tuple(shape), (name, t.shape, shape)
+        return t
+
+
+class _EncoderBase(torch.nn.Module):
+    def __init__(self, device):
+        super().__init__()
+        self.device = torch.device(device)
+        self.dtype = torch.bfloat16
+        self.use_graphs = ops.graphs_enabled()
+        self._plans: Dict[tuple, _Plan] = {}
+
+    def _w(self, t):
+        return t.to(device=self.device, dtype=torch.bfloat16).contiguous()
+
+    def _plan(self, B, S):
+        pl = self._plans.get((B, S))
+        if pl is None:
+            pl = self._plans[(B, S)] = _Plan(self.device)
+            pl.B, pl.S = B, S
+            pl.ids = torch.empty((B * S,), device=self.device, dtype=torch.int32)
+            seqs = [(b * S, S, 0, 0, b * S, S, 0, 0) for b in range(B)]
+            pl.attn_plan = ops.build_attn_plan(seqs, self.device, self.heads)
+        return pl
+
+    def _load_ids(self, pl, ids):
+        ids = torch.as_tensor(ids)
+        assert ids.shape == (pl.B, pl.S), (ids.shape, pl.B, pl.S)
+        pl.ids.copy_(ids.reshape(-1).to(torch.int32), non_blocking=False)
+
+
+class B200CLIPTextEncoder(_EncoderBase):
+    """transformers CLIPTextModel / CLIPTextModelWithProjection (pre-LN transformer, causal mask,
+    learned positions). forward(ids [B, S]) -> dict(hidden_states_penultimate [B, S, D],
+    last_hidden_state [B, S, D] (after final_layer_norm), pooled [B, D], text_embeds [B, P] | None)."""
+
+    def __init__(self, state_dict, config, device="cuda"):
+        super().__init__(device)
+        sd, p = state_dict, "text_model."
+        self.D = _cfg(config, "hidden_size")
+        self.heads = _cfg(config, "num_attention_heads")
+        self.layers = _cfg(config, "num_hidden_layers")
+        self.eps = _cfg(config, "layer_norm_eps", 1e-5)
+        self.eos_id = _cfg(config, "eos_token_id", 2)
+        assert self.D // self.heads == 64, "attention kernel is specialised for head_dim 64"
+        act = _cfg(config, "hidden_act", "quick_gelu")
+        self.act = {"quick_gelu": ACT_QUICK_GELU, "gelu": ACT_GELU_ERF, "gelu_new": ACT_GELU_TANH,
+                    "gelu_pytorch_tanh": ACT_GELU_TANH}[act]
+        self.tok = self._w(sd[p + "embeddings.token_embedding.weight"])
+        self.pos = self._w(sd[p + "embeddings.position_embedding.weight"])
+        self.blocks = []
+        for i in range(self.layers):
+            b = f"{p}encoder.layers.{i}."
+            self.blocks.append({
+                "ln1_w": self._w(sd[b + "layer_norm1.weight"]), "ln1_b": self._w(sd[b + "layer_norm1.bias"]),
+                "qkv_w": self._w(torch.cat([sd[f"{b}self_attn.{n}_proj.weight"] for n in "qkv"], 0)),
+                "qkv_b": self._w(torch.cat([sd[f"{b}self_attn.{n}_proj.bias"] for n in "qkv"], 0)),
+                "o_w": self._w(sd[b + "self_attn.out_proj.weight"]), "o_b": self._w(sd[b + "self_attn.out_proj.bias"]),
+                "ln2_w": self._w(sd[b + "layer_norm2.weight"]), "ln2_b": self._w(sd[b + "layer_norm2.bias"]),
+                "fc1_w": self._w(sd[b + "mlp.fc1.weight"]), "fc1_b": self._w(sd[b + "mlp.fc1.bias"]),
+                "fc2_w": self._w(sd[b + "mlp.fc2.weight"]), "fc2_b": self._w(sd[b + "mlp.fc2.bias"])})
+        self.fln_w, self.fln_b = self._w(sd[p + "final_layer_norm.weight"]), self._w(sd[p + "final_layer_norm.bias"])
+        self.proj = self._w(sd["text_projection.weight"]) if "text_projection.weight" in sd else None
+
+    @classmethod
+    def from_transformers(cls, model, device="cuda"):
+        return cls(model.state_dict(), model.config, device=device)
+
+    def _run(self, pl):
+        G, D, T = ops.gemm, self.D, pl.B * pl.S
+        F = self.blocks[0]["fc1_w"].shape[0]
+        x = ops.embed_rows(pl.ids, self.tok, pl.buf("x", (T, D)), pos=self.pos, seq_len=pl.S)
+        h, qkv, att, ff = pl.buf("h", (T, D)), pl.buf("qkv", (T, 3 * D)), pl.buf("att", (T, D)), pl.buf("ff", (T, F))
+        last = pl.buf("x_last", (T, D))
+        if "self" not in pl.attn:
+            pl.attn["self"] = ops.attn_source(q=qkv, q_col=0, k=qkv, k_col=D, v=qkv, v_col=2 * D, out=att)
+        for i, blk in enumerate(self.blocks):
+            out = last if i == self.layers - 1 else x   # hidden_states[-2] = input of the last layer
+            ops.layernorm_mod(x, h, eps=self.eps, gamma=blk["ln1_w"], beta=blk["ln1_b"])
+            G(h, blk["qkv_w"], qkv, bias=blk["qkv_b"])
+            ops.attn_varlen(pl.attn["self"], None, *pl.attn_plan, 0.125, causal=True)
+            G(att, blk["o_w"], out, bias=blk["o_b"], epi=ops.EPI_GATE_RESID, resid=x)
+            ops.layernorm_mod(out, h, eps=self.eps, gamma=blk["ln2_w"], beta=blk["ln2_b"])
+            G(h, blk["fc1_w"], ff, bias=blk["fc1_b"], epi=ops.EPI_GELU_TANH, act=self.act)
+            G(ff, blk["fc2_w"], out, bias=blk["fc2_b"], epi=ops.EPI_GATE_RESID, resid=out)
+        ops.layernorm_mod(last, pl.buf("final", (T, D)), eps=self.eps, gamma=self.fln_w, beta=self.fln_b)
+
+    @torch.no_grad()
+    def forward(self, ids):
+        ids = torch.as_tensor(ids)
+        B, S = ids.shape
+        pl = self._plan(B, S)
+        ops.run_plan(self, pl, lambda p: self._load_ids(p, ids))
+        final = pl.bufs["final"].view(B, S, self.D)
+        # pooled = final-LN hidden state at the EOS token (CLIPTextTransformer.forward)
+        host = ids.cpu()
+        pos = host.argmax(-1) if self.eos_id == 2 else (host == self.eos_id).int().argmax(-1)
+        pooled = pl.buf("pooled", (B, self.D))
+        ops.gather_rows(pooled, [final[b, int(pos[b])] for b in range(B)])
+        emb = ops.gemm(pooled, self.proj, pl.buf("emb", (B, self.proj.shape[0]))) if self.proj is not None else None
+        return {"hidden_states_penultimate": pl.bufs["x"].view(B, S, self.D), "last_hidden_state": final,
+                "pooled": pooled, "text_embeds": emb}
+
+
+class B200T5Encoder(_EncoderBase):
+    """transformers T5EncoderModel (v1.1: RMS norms, no biases, un-scaled attention + relative
+    position bias of layer 0, gated tanh-GELU feed-forward). forward(ids [B, S]) -> [B, S, d_model].
+    No attention mask: diffusers' SD3 `_get_t5_prompt_embeds` passes none."""
+
+    def __init__(self, state_dict, config, device="cuda", max_len=512):
+        super().__init__(device)
+        sd = state_dict
+        self.D = _cfg(config, "d_model")
+        self.heads = _cfg(config, "num_heads")
+        self.dk = _cfg(config, "d_kv")
+        self.layers = _cfg(config, "num_layers")
+        self.eps = _cfg(config, "layer_norm_epsilon", 1e-6)
+        assert self.dk == 64, "attention kernel is specialised for head_dim 64"
+        ffp = _cfg(config, "feed_forward_proj", "gated-gelu")
+        assert ffp == "gated-gelu", "T5 v1.1 (gated tanh-GELU) feed-forward only"
+        emb = sd.get("encoder.embed_tokens.weight", sd.get("shared.weight"))
+        self.tok = self._w(emb)
+        inner = self.heads * self.dk
+        self.blocks = []
+        for i in range(self.layers):
+            b = f"encoder.block.{i}.layer."
+            w_hidden, w_gate = sd[b + "1.DenseReluDense.wi_1.weight"], sd[b + "1.DenseReluDense.wi_0.weight"]
+            Fh = w_hidden.shape[0]
+            assert Fh % 32 == 0
+            # GEGLU epilogue layout: [32 hidden | 32 gate] row blocks share a tile; out = hidden * act(gate)
+            idx = torch.arange(2 * Fh).view(2, Fh // 32, 32).permute(1, 0, 2).reshape(-1)
+            self.blocks.append({
+                "ln1": self._w(sd[b + "0.layer_norm.weight"]),
+                "qkv_w": self._w(torch.cat([sd[f"{b}0.SelfAttention.{n}.weight"] for n in "qkv"], 0)),
+                "o_w": self._w(sd[b + "0.SelfAttention.o.weight"]),
+                "ln2": self._w(sd[b + "1.layer_norm.weight"]),
+                "wi": self._w(torch.cat([w_hidden, w_gate], 0)[idx]),
+                "wo": self._w(sd[b + "1.DenseReluDense.wo.weight"])})
+        self.final_ln = self._w(sd["encoder.final_layer_norm.weight"])
+        self.inner, self.d_ff = inner, Fh
+        # relative position bias as a function of (k - q): [heads, 2 max_len - 1] fp32; the softmax
+        # scale is 1 (T5 does not scale the logits), so no pre-division is needed
+        table = sd["encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"].float()  # [buckets, H]
+        rel = torch.arange(-(max_len - 1), max_len)
+        buckets = self._bucket(rel, _cfg(config, "relative_attention_num_buckets", 32),
+                               _cfg(config, "relative_attention_max_distance", 128))
+        ld = (2 * max_len - 1 + 3) // 4 * 4
+        bias = torch.zeros((self.heads, ld), dtype=torch.float32)
+        bias[:, :2 * max_len - 1] = table[buckets].t()
+        self.rel_bias, self.max_len = bias.to(self.device).contiguous(), max_len
+
+    @staticmethod
+    def _bucket(rel, num_buckets, max_distance):
+        """T5Attention._relative_position_bucket (bidirectional) for rel = key_pos - query_pos."""
+        nb = num_buckets // 2
+        out = (rel > 0).long() * nb
+        rel = rel.abs()
+        max_exact = nb // 2
+        large = max_exact + (torch.log(rel.float().clamp(min=1) / max_exact) / math.log(max_distance / max_exact)
+                             * (nb - max_exact)).long()
+        large = torch.min(large, torch.full_like(large, nb - 1))
+        return out + torch.where(rel < max_exact, rel, large)
+
+    @classmethod
+    def from_transformers(cls, model, device="cuda", max_len=512):
+        return cls(model.state_dict(), model.config, device=device, max_len=max_len)
+
+    def _run(self, pl):
+        G, D, T = ops.gemm, self.D, pl.B * pl.S
+        I = self.inner
+        x = ops.embed_rows(pl.ids, self.tok, pl.buf("x", (T, D)))
+        h, qkv, att, ff = pl.buf("h", (T, D)), pl.buf("qkv", (T, 3 * I)), pl.buf("att", (T, I)), pl.buf("ff", (T, self.d_ff))
+        if "self" not in pl.attn:
+            pl.attn["self"] = ops.attn_source(q=qkv, q_col=0, k=qkv, k_col=I, v=qkv, v_col=2 * I, out=att)
+        for blk in self.blocks:
+            ops.rmsnorm(x, blk["ln1"], h, self.eps)
+            G(h, blk["qkv_w"], qkv)
+            ops.attn_varlen(pl.attn["self"], None, *pl.attn_plan, 1.0, rel_bias=self.rel_bias, rel_len=self.max_len)
+            G(att, blk["o_w"], x, epi=ops.EPI_GATE_RESID, resid=x)
+            ops.rmsnorm(x, blk["ln2"], h, self.eps)
+            G(h, blk["wi"], ff, epi=ops.EPI_GEGLU, act=ACT_GELU_TANH)
+            G(ff, blk["wo"], x, epi=ops.EPI_GATE_RESID, resid=x)
+        ops.rmsnorm(x, self.final_ln, pl.buf("out", (T, D)), self.eps)
+
+    @torch.no_grad()
+    def forward(self, ids):
+        ids = torch.as_tensor(ids)
+        B, S = ids.shape
+        assert S <= self.max_len
+        pl = self._plan(B, S)
+        ops.run_plan(self, pl, lambda p: self._load_ids(p, ids))
+        return pl.bufs["out"].view(B, S, self.D)
+
+
+class B200PromptEncoder:
+    """diffusers `encode_prompt` for one branch (positive or negative prompts), from token ids.
+    kind "sd3": CLIP-L + CLIP-G + T5 -> (prompt_embeds [B, 77 + S_t5, joint_dim], pooled [B, D_l' + D_g'])
+    kind "sdxl": CLIP-L + CLIP-G     -> (prompt_embeds [B, 77, D_l + D_g], pooled [B, proj_g])
+    (StableDiffusion3Pipeline.encode_prompt / StableDiffusionXLPipeline.encode_prompt, clip_skip=None:
+    penultimate hidden states; pooled = projected EOS embeddings)."""
+
+    def __init__(self, kind, clip_l: B200CLIPTextEncoder, clip_g: B200CLIPTextEncoder,
+                 t5: Optional[B200T5Encoder] = None, joint_dim: int = 4096):
+        assert kind in ("sd3", "sdxl")
+        assert kind == "sdxl" or t5 is not None
+        self.kind, self.clip_l, self.clip_g, self.t5, self.joint_dim = kind, clip_l, clip_g, t5, joint_dim
+        self.device = clip_l.device
+
+    @torch.no_grad()
+    def encode(self, ids_l, ids_g, ids_t5=None):
+        ol, og = self.clip_l(ids_l), self.clip_g(ids_g)
+        hl, hg = ol["hidden_states_penultimate"], og["hidden_states_penultimate"]
+        B, S, Dl = hl.shape
+        Dg = hg.shape[-1]
+        dev = self.device
+        if self.kind == "sdxl":
+            out = torch.empty((B * S, Dl + Dg), device=dev, dtype=torch.bfloat16)
+            ops.copy_cols(hl.reshape(B * S, Dl), out, Dl)
+            ops.copy_cols(hg.reshape(B * S, Dg), out[:, Dl:], Dg)
+            return out.view(B, S, Dl + Dg), og["text_embeds"].clone()
+        t5 = self.t5(ids_t5)
+        St, J = t5.shape[1], self.joint_dim
+        out = torch.zeros((B, S + St, J), device=dev, dtype=torch.bfloat16)  # clip part zero-padded to J
+        for b in range(B):
+            rows = out[b].view(S + St, J)
+            ops.copy_cols(hl[b], rows[:S], Dl)
+            ops.copy_cols(hg[b], rows[:S, Dl:], Dg)
+            ops.copy_cols(t5[b], rows[S:], J)
+        el, eg = ol["text_embeds"], og["text_embeds"]
+        pooled = torch.empty((B, el.shape[1] + eg.shape[1]), device=dev, dtype=torch.bfloat16)
+        ops.copy_cols(el, pooled, el.shape[1])
+        ops.copy_cols(eg, pooled[:, el.shape[1]:], eg.shape[1])
+        return out, pooled
