@@ -77,6 +77,13 @@ class _CondEntry:
     __slots__ = ("refs", "versions", "ctx", "pooled", "ids")
 
 
+def _version(t):
+    try:
+        return t._version
+    except RuntimeError:   # inference tensors (made under torch.inference_mode) carry no version counter
+        return -1
+
+
 class _CondCache:
     """Per-(request, CFG branch) conditioning that does not change over the request's steps: the
     projected text context, the pooled embedding as bf16, SDXL's time ids as fp32. An entry is valid
@@ -91,7 +98,7 @@ class _CondCache:
     def lookup(self, key, sources):
         e = self.entries.get(key)
         if e is not None and all(r() is s for r, s in zip(e.refs, sources)) and \
-                e.versions == tuple(s._version for s in sources):
+                e.versions == tuple(_version(s) for s in sources):
             self.entries.move_to_end(key)
             self.hits += 1
             return e
@@ -101,7 +108,7 @@ class _CondCache:
     def store(self, key, sources, ctx, pooled, ids):
         e = _CondEntry()
         e.refs = tuple(weakref.ref(s) for s in sources)
-        e.versions = tuple(s._version for s in sources)
+        e.versions = tuple(_version(s) for s in sources)
         e.ctx, e.pooled, e.ids = ctx, pooled, ids
         self.entries[key] = e
         self.entries.move_to_end(key)
@@ -132,6 +139,61 @@ class B200DenoisingPipelineBase:
         self.vae = vae  # optional sduss_b200.vae.B200VAEDecoder (post_inference, row f-4)
         self._tables = _HostTables()
         self._cond = _CondCache()
+
+    # -- prepare stage -----------------------------------------------------------------
+    def attach_text_encoders(self, prompt_encoder, tokenizers):
+        """prompt_encoder: sduss_b200.text_encoders.B200PromptEncoder; tokenizers: the pipeline's
+        tokenizer, tokenizer_2[, tokenizer_3] (callables with the transformers tokenizer call
+        signature returning an object / dict with `input_ids`)."""
+        self.prompt_encoder, self.tokenizers = prompt_encoder, list(tokenizers)
+
+    @staticmethod
+    def _ids(tok, prompts, max_length):
+        out = tok(prompts, padding="max_length", max_length=max_length, truncation=True, return_tensors="pt")
+        return out["input_ids"] if isinstance(out, dict) else out.input_ids
+
+    def _encode(self, prompts, max_sequence_length):
+        """prompts: one list of strings per tokenizer -> (prompt_embeds, pooled)."""
+        lens = [77, 77, max_sequence_length]
+        ids = [self._ids(t, p, n) for t, p, n in zip(self.tokenizers, prompts, lens)]
+        return self.prompt_encoder.encode(*ids)
+
+    @torch.inference_mode()
+    def _prepare(self, reqs: Dict[str, List], second_prompts, cfg: bool, generator, max_sequence_length,
+                 latent_channels, init_noise_sigma_of, force_zero_negative=False, extra=None) -> None:
+        """Shared body of prepare_inference: text encoders for the positive (and, under CFG, negative)
+        prompts of all requests in ONE pass each, initial latents, per-request scheduler tables, and
+        the per-request hand-over the reference does at the end of prepare_inference
+        (pipeline_stable_diffusion_3_esymred.py:219-229, ..._xl_esymred.py:244-258)."""
+        from types import SimpleNamespace
+        if getattr(self, "prompt_encoder", None) is None:
+            raise RuntimeError("prepare_inference needs text encoders (attach_text_encoders)")
+        res_list = sorted(r for r in reqs if len(reqs[r]) > 0)     # the reference sorts the keys as strings
+        flat = [r for res in res_list for r in reqs[res]]
+        pick = lambda sp, names: next((getattr(sp, n) for n in names if getattr(sp, n, None) is not None), "")
+        pos = [[pick(r.sampling_params, names) for r in flat] for names in second_prompts["pos"]]
+        emb, pooled = self._encode(pos, max_sequence_length)
+        if cfg:
+            if force_zero_negative:
+                nemb, npooled = torch.zeros_like(emb), torch.zeros_like(pooled)
+            else:
+                neg = [[pick(r.sampling_params, names) for r in flat] for names in second_prompts["neg"]]
+                nemb, npooled = self._encode(neg, max_sequence_length)
+        dev = self.model.device
+        self.scheduler.batch_set_timesteps(flat, device=dev)
+        for i, r in enumerate(flat):
+            sp = r.sampling_params
+            if getattr(sp, "latents", None) is None:
+                h, w = sp.height // 8, sp.width // 8
+                lat = torch.randn((1, latent_channels, h, w), generator=generator, device=dev, dtype=torch.float32)
+                sp.latents = (lat * init_noise_sigma_of(r)).to(emb.dtype)
+            elif not sp.latents.is_cuda:
+                sp.latents = sp.latents.to(dev)
+            sp.prompt_embeds = emb[i:i + 1]
+            sp.negative_prompt_embeds = nemb[i:i + 1] if cfg else None
+            r.prepare_output = SimpleNamespace(
+                pooled_prompt_embeds=pooled[i:i + 1],
+                negative_pooled_prompt_embeds=npooled[i:i + 1] if cfg else None, **(extra or {}))
 
     # -- post stage --------------------------------------------------------------------
     @torch.inference_mode()
@@ -283,6 +345,22 @@ class B200StableDiffusion3Pipeline(B200DenoisingPipelineBase):
     def _pooled_buffer(pl):
         return pl.pooled
 
+    def prepare_inference(self, runner_reqs: Dict[str, List] = None, guidance_scale: float = 7.0,
+                          generator=None, pooled_prompt_embeds=None, negative_pooled_prompt_embeds=None,
+                          joint_attention_kwargs=None, clip_skip=None, max_sequence_length: int = 256,
+                          skip_layer_guidance_scale: float = 2.8) -> None:
+        """ESyMReDStableDiffusion3Pipeline.prepare_inference
+        (pipeline_stable_diffusion_3_esymred.py:49-230): CLIP-L / CLIP-G / T5 prompt encoding
+        (prompt_2 / prompt_3 default to prompt, negatives to ""), N(0, 1) latents, per-request
+        flow-match tables."""
+        assert clip_skip is None and not joint_attention_kwargs, "clip_skip / LoRA scale are not supported"
+        cfg = guidance_scale > 1.0   # diffusers' do_classifier_free_guidance
+        names = {"pos": [("prompt",), ("prompt_2", "prompt"), ("prompt_3", "prompt")],
+                 "neg": [("negative_prompt",), ("negative_prompt_2", "negative_prompt"),
+                         ("negative_prompt_3", "negative_prompt")]}
+        self._prepare(runner_reqs, names, cfg, generator, max_sequence_length, self.model.cfg.in_channels,
+                      lambda r: 1.0)
+
     @torch.inference_mode()
     def denoising_step(self, runner_reqs: Dict[str, List], do_classifier_free_guidance: bool = True,
                        guidance_scale: float = 7.0, is_sliced: bool = True, patch_size: int = 256) -> None:
@@ -306,6 +384,38 @@ class B200StableDiffusionXLPipeline(B200DenoisingPipelineBase):
     @staticmethod
     def _pooled_buffer(pl):
         return pl.text_embeds
+
+    def prepare_inference(self, worker_reqs: Dict[str, List] = None, denoising_end=None,
+                          guidance_scale: float = 5.0, eta: float = 0.0, generator=None,
+                          pooled_prompt_embeds=None, negative_pooled_prompt_embeds=None, ip_adapter_image=None,
+                          ip_adapter_image_embeds=None, output_type="pil", return_dict=True,
+                          cross_attention_kwargs=None, guidance_rescale: float = 0.0,
+                          crops_coords_top_left=(0, 0), negative_original_size=None,
+                          negative_crops_coords_top_left=(0, 0), negative_target_size=None, clip_skip=None,
+                          force_zeros_for_empty_prompt: bool = True) -> None:
+        """ESyMReDStableDiffusionXLPipeline.prepare_inference
+        (pipeline_stable_diffusion_xl_esymred.py:56-258): CLIP-L / CLIP-G prompt encoding (the reference
+        passes no negative prompt: zeros under SDXL-base's force_zeros_for_empty_prompt), initial
+        latents scaled by init_noise_sigma, per-request Euler tables, add_time_ids built for
+        original / target size (1024, 1024) whatever the request resolution (deviation D3)."""
+        assert clip_skip is None and not cross_attention_kwargs and denoising_end is None
+        assert ip_adapter_image is None and ip_adapter_image_embeds is None
+        cfg = guidance_scale > 1.0
+        # the reference calls encode_prompt(prompt=prompt, prompt_2=None, negative_prompt=None, ...):
+        # prompt_2 and the requests' negative prompts are NOT used (xl_esymred.py:118-133)
+        names = {"pos": [("prompt",), ("prompt",)], "neg": [(), ()]}
+        dev = self.model.device
+        ids = torch.tensor([[1024., 1024., float(crops_coords_top_left[0]), float(crops_coords_top_left[1]),
+                             1024., 1024.]], device=dev, dtype=torch.bfloat16)
+        if negative_original_size is not None and negative_target_size is not None:
+            nids = torch.tensor([[float(v) for v in (*negative_original_size, *negative_crops_coords_top_left,
+                                                     *negative_target_size)]], device=dev, dtype=torch.bfloat16)
+        else:
+            nids = ids
+        self._prepare(worker_reqs, names, cfg, generator, 77, self.model.cfg.in_channels,
+                      lambda r: self.scheduler.init_noise_sigma, force_zero_negative=force_zeros_for_empty_prompt,
+                      extra={"add_time_ids": ids, "negative_add_time_ids": nids, "timestep_cond": None,
+                             "extra_step_kwargs": {}})
 
     @torch.inference_mode()
     def denoising_step(self, worker_reqs: Dict[str, List], do_classifier_free_guidance: bool = True,

@@ -16,7 +16,9 @@ post_inference (VAE), class attributes -- is inherited untouched, so `_ModelRunn
 (sduss/worker/runner/_model_runner.py:109-114,238-264) cannot tell the difference.
 With `b200_vae=True` the `vae` sub-module is additionally wrapped in `B200VAEProxy`: the inherited
 post_inference is still the reference's code, but its `self.vae.decode(...)` runs on the B200
-kernels.
+kernels. With `b200_text_encoders=True` the text encoders are wrapped in
+`B200CLIPProxy` / `B200T5Proxy` the same way: the inherited prepare_inference -> encode_prompt is
+unchanged and its encoder calls run on the B200 kernels.
 """
 from typing import Type
 
@@ -27,7 +29,8 @@ _KINDS = {
 }
 
 
-def make_b200_pipeline(reference_cls: Type, kind: str, device: str = "cuda", b200_vae: bool = False) -> Type:
+def make_b200_pipeline(reference_cls: Type, kind: str, device: str = "cuda", b200_vae: bool = False,
+                       b200_text_encoders: bool = False) -> Type:
     if kind not in _KINDS:
         raise ValueError(f"kind must be one of {sorted(_KINDS)}, got {kind!r}")
     module_key, mod_name, model_name, step_name = _KINDS[kind]
@@ -48,6 +51,15 @@ def make_b200_pipeline(reference_cls: Type, kind: str, device: str = "cuda", b20
                 # now runs on the B200 kernels (sduss_b200.vae.B200VAEProxy)
                 from .vae import B200VAEProxy
                 sub_modules["vae"] = B200VAEProxy(sub_modules["vae"], device=device)
+            if b200_text_encoders:
+                # row f-4, prepare half: the inherited prepare_inference -> encode_prompt keeps calling
+                # self.text_encoder*(ids, output_hidden_states=True); those now run on the B200 kernels
+                from .text_encoders import B200CLIPProxy, B200T5Proxy
+                for key in ("text_encoder", "text_encoder_2"):
+                    if sub_modules.get(key) is not None:
+                        sub_modules[key] = B200CLIPProxy(sub_modules[key], device=device)
+                if sub_modules.get("text_encoder_3") is not None:
+                    sub_modules["text_encoder_3"] = B200T5Proxy(sub_modules["text_encoder_3"], device=device)
             return cls(**sub_modules)
 
         def _b200_step(self):

@@ -276,3 +276,67 @@ class B200PromptEncoder:
         ops.copy_cols(el, pooled, el.shape[1])
         ops.copy_cols(eg, pooled[:, el.shape[1]:], eg.shape[1])
         return out, pooled
+
+
+# ---------------------------------------------------------------------------------------------
+# Registry-level drop-in: stand-ins for `self.text_encoder*` so that the reference's inherited
+# prepare_inference -> diffusers encode_prompt runs unmodified on the B200 kernels.
+# ---------------------------------------------------------------------------------------------
+class _PenultimateOnly:
+    """`.hidden_states` of the proxy output: encode_prompt reads hidden_states[-2] (clip_skip=None);
+    any other layer is not computed."""
+
+    def __init__(self, penultimate):
+        self._p = penultimate
+
+    def __getitem__(self, i):
+        if i != -2:
+            raise NotImplementedError("only hidden_states[-2] (clip_skip=None) is produced by the B200 encoder")
+        return self._p
+
+
+class _ClipOutput:
+    def __init__(self, first, penultimate, last):
+        self.text_embeds = self.pooler_output = first
+        self.last_hidden_state = last
+        self.hidden_states = _PenultimateOnly(penultimate)
+
+    def __getitem__(self, i):
+        if i != 0:
+            raise IndexError(i)
+        return self.text_embeds
+
+
+class B200CLIPProxy:
+    """Wraps a transformers CLIPTextModel / CLIPTextModelWithProjection: same call as diffusers'
+    `_get_clip_prompt_embeds` makes, `enc(input_ids, output_hidden_states=True)`, result supports
+    `[0]` (projected EOS embedding, or the pooled EOS state without a projection) and
+    `.hidden_states[-2]`. Unknown attributes (config, dtype, device ...) forward to the wrapped module."""
+
+    def __init__(self, module, device="cuda"):
+        self._module = module
+        self._enc = B200CLIPTextEncoder.from_transformers(module, device=device)
+
+    def __getattr__(self, name):
+        return getattr(self._module, name)
+
+    def __call__(self, input_ids, attention_mask=None, output_hidden_states=True, **kw):
+        assert attention_mask is None, "encode_prompt passes no attention mask to the CLIP encoders"
+        o = self._enc(input_ids)
+        first = o["text_embeds"] if o["text_embeds"] is not None else o["pooled"]
+        return _ClipOutput(first.clone(), o["hidden_states_penultimate"].clone(), o["last_hidden_state"].clone())
+
+
+class B200T5Proxy:
+    """Wraps a transformers T5EncoderModel: `enc(input_ids)[0]` as `_get_t5_prompt_embeds` calls it."""
+
+    def __init__(self, module, device="cuda", max_len=512):
+        self._module = module
+        self._enc = B200T5Encoder.from_transformers(module, device=device, max_len=max_len)
+
+    def __getattr__(self, name):
+        return getattr(self._module, name)
+
+    def __call__(self, input_ids, attention_mask=None, **kw):
+        assert attention_mask is None, "_get_t5_prompt_embeds passes no attention mask"
+        return (self._enc(input_ids).clone(),)
