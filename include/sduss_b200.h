@@ -70,6 +70,9 @@ typedef struct B200EpilogueDesc {
   int32_t act;          /* activation of B200_EPI_GELU_TANH / gate of B200_EPI_GEGLU:     */
                         /* 0 = the mode's default (tanh-GELU / erf-GELU), 1 tanh-GELU,    */
                         /* 2 erf-GELU, 3 quick-GELU x*sigmoid(1.702x) (text encoders)     */
+  const int32_t* row_mask; /* patch cache, may be NULL: device int32 per chunk   */
+  int32_t row_mask_shift;  /* of 2^shift rows (shift >= 8); M tiles of a chunk whose entry is 0   */
+                           /* are skipped: no loads, no MMA, their rows of C stay as they are     */
 } B200EpilogueDesc;
 
 /* A: [M, lda] bf16, W: [N, ldw] bf16 (K contiguous in both). N, K, lda, ldw, ldc multiples
@@ -129,6 +132,9 @@ typedef struct B200AttnExtra {
   int32_t rel_len;
   const float* rel_bias;
   int32_t rel_ld;
+  int32_t q_mask_shift;    /* patch cache: q_mask[row >> shift] (shift >= 7) == 0 */
+  const int32_t* q_mask;   /* marks segment-A query rows to skip (output rows stay untouched);     */
+                           /* keys / values of skipped rows are still read. NULL = all computed.   */
 } B200AttnExtra;
 int b200_attn_varlen_ex(const B200AttnSource* src_a, const B200AttnSource* src_b,
                         const int32_t* seq_table, const int32_t* work_units, int n_units,
@@ -143,11 +149,14 @@ int b200_attn_varlen_ex(const B200AttnSource* src_a, const B200AttnSource* src_b
  * (g = 0 when row_group is NULL); optional second output y2 with (scale2_col, shift2_col).
  * Covers diffusers LayerNorm, AdaLayerNormZero, SD35AdaLayerNormZeroX and
  * AdaLayerNormContinuous as called from sduss modules/transformer.py:185-279,317-386 and
- * modules/SD3Transformer.py:238. x, y: [T, ld] bf16; D <= 2048, D % 8 == 0; mod: [G, ldm] bf16. */
+ * modules/SD3Transformer.py:238. x, y: [T, ld] bf16; D <= 2048, D % 8 == 0; mod: [G, ldm] bf16.
+ * row_mask (patch cache, may be NULL): device int32 per chunk of 2^row_mask_shift rows; rows of a
+ * chunk whose entry is 0 are left untouched in y / y2. */
 int b200_layernorm_mod_bf16(const void* x, int ldx, int T, int D, float eps, const void* gamma,
                             const void* beta, const void* mod, int ldm, const int32_t* row_group,
                             int shift_col, int scale_col, void* y, int ldy, int shift2_col,
-                            int scale2_col, void* y2, int ldy2, void* stream);
+                            int scale2_col, void* y2, int ldy2, const int32_t* row_mask,
+                            int row_mask_shift, void* stream);
 
 /* y = x * sigmoid(x), n % 8 == 0 elements of bf16. */
 int b200_silu_bf16(const void* x, void* y, long long n, void* stream);
@@ -279,6 +288,31 @@ int b200_split_patches(const uint64_t* lat_ptr, const int32_t* ldesc, const int3
                        int n_patches, int C, int ps, void* out, void* stream);
 int b200_concat_patches(const void* patches, const int32_t* ldesc, const int32_t* pdesc,
                         int n_patches, int C, int ps, const uint64_t* out_ptr, void* stream);
+
+/* ---- Patch cache ("block skip"; CacheManager.get_sd3_mask,
+ * sduss/model_executor/modules/cache_manager.py:161-191). One launch per transformer block decides,
+ * on the device and inside the captured graph, which 256-token patches are recomputed: it streams the
+ * block input x once -- per-patch MSE against `prev` (the block input at the previous step), which
+ * it refreshes in the same pass -- evaluates the flattened RandomForest on [block_index, timestep,
+ * MSE] and applies the refresh rule. mask[p] = 1: recompute. The mask is what the row_mask /
+ * q_mask arguments of the GEMM, LayerNorm and attention entry points take.
+ * A patch of a latent with latent_valid == 0 (its kept copies belong to another request or an older
+ * step) has MSE = float(sys.maxsize) as in the reference and is always recomputed. */
+typedef struct B200Forest {      /* all arrays in DEVICE memory                                   */
+  const int32_t* feature;        /* [nodes] feature index (0 block, 1 timestep, 2 MSE); < 0 = leaf */
+  const float* threshold;        /* [nodes] go left when x[feature] <= threshold (sklearn)         */
+  const int32_t* left;           /* [nodes]                                                        */
+  const int32_t* right;          /* [nodes]                                                        */
+  const float* value;            /* [nodes] leaf: probability of class 1 (= recompute)             */
+  const int32_t* roots;          /* [n_trees] root node of each tree                               */
+  int32_t n_trees;
+} B200Forest;
+long long b200_patch_mask_workspace_bytes(int n_patches);  /* zero it once; the kernel leaves it zeroed */
+int b200_patch_mask_bf16(const void* x, int ldx, void* prev, int ldp, int n_patches,
+                         int rows_per_patch, int D, const int32_t* patch_latent,
+                         const float* latent_t, const float* latent_valid, int32_t* skipped,
+                         int32_t* mask, float* mse, const B200Forest* forest, int block_index,
+                         int refresh, void* workspace, void* stream);
 
 /* ---- Prepare stage (text encoders behind encode_prompt,
  * pipeline_stable_diffusion_3_esymred.py:119-141, pipeline_stable_diffusion_xl_esymred.py:120-160).

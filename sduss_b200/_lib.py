@@ -34,6 +34,7 @@ class EpilogueDesc(ctypes.Structure):
         ("rms_q_cols", ctypes.c_int32), ("rms_k_cols", ctypes.c_int32),
         ("rms_eps", c_float), ("q_scale", c_float),
         ("act", ctypes.c_int32),
+        ("row_mask", c_void_p), ("row_mask_shift", ctypes.c_int32),
     ]
 
 
@@ -43,7 +44,13 @@ ACT_DEFAULT, ACT_GELU_TANH, ACT_GELU_ERF, ACT_QUICK_GELU = 0, 1, 2, 3
 class AttnExtra(ctypes.Structure):
     """Mirror of B200AttnExtra: causal mask / relative position bias of the text encoders."""
     _fields_ = [("causal", ctypes.c_int32), ("rel_len", ctypes.c_int32), ("rel_bias", c_void_p),
-                ("rel_ld", ctypes.c_int32)]
+                ("rel_ld", ctypes.c_int32), ("q_mask_shift", ctypes.c_int32), ("q_mask", c_void_p)]
+
+
+class Forest(ctypes.Structure):
+    """Mirror of B200Forest: a flattened RandomForest in device memory (patch cache, row f-3)."""
+    _fields_ = [("feature", c_void_p), ("threshold", c_void_p), ("left", c_void_p), ("right", c_void_p),
+                ("value", c_void_p), ("roots", c_void_p), ("n_trees", ctypes.c_int32)]
 
 
 class AttnSource(ctypes.Structure):
@@ -101,7 +108,10 @@ SIGNATURES = {
     "b200_rmsnorm_bf16": [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p],
     "b200_layernorm_mod_bf16": [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                 c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
-                                c_int, c_void_p, c_int, c_void_p],
+                                c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
+    "b200_patch_mask_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(Forest), c_int, c_int,
+                             c_void_p, c_void_p],
     "b200_silu_bf16": [c_void_p, c_void_p, ctypes.c_longlong, c_void_p],
     "b200_timestep_embedding": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
     "b200_sd3_patchify": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
@@ -142,6 +152,8 @@ def _bind():
         fn.restype = c_int
     lib.b200_groupnorm_workspace_bytes.argtypes = [ctypes.c_longlong, c_int]
     lib.b200_groupnorm_workspace_bytes.restype = ctypes.c_longlong
+    lib.b200_patch_mask_workspace_bytes.argtypes = [c_int]
+    lib.b200_patch_mask_workspace_bytes.restype = ctypes.c_longlong
 
 
 _bind()

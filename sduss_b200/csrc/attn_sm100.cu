@@ -76,6 +76,15 @@ constexpr float ATT_RESCALE_THRESHOLD = 8.f;  // lazy rescale: keep a stale max 
 #ifndef ATT_F32X2
 #define ATT_F32X2 1  // packed fp32 pairs (FFMA2 / FADD2) in the softmax
 #endif
+#ifndef ATT_EXTRAS
+#define ATT_EXTRAS 1  // causal mask / relative bias / q-tile skip compiled in (0: A/B build without them)
+#endif
+#ifndef ATT_POLY_MOD
+#define ATT_POLY_MOD 0  // > 0: every ATT_POLY_MOD-th element pair takes exp2 on the FMA pipe (below)
+#endif
+#ifndef ATT_POLY_DEG
+#define ATT_POLY_DEG 3
+#endif
 #ifndef ATT_SKEW
 #define ATT_SKEW 0  // one-time start offset (cycles) between the softmax groups of a CTA (A/B knob)
 #endif
@@ -94,6 +103,9 @@ struct AttnArgs {
   int causal;                        // CLIP: key position <= query position
   const float* rel_bias;             // T5: logits += rel_bias[head][k_pos - q_pos + rel_len - 1]
   int rel_len, rel_ld;               //     (already divided by the softmax scale)
+  // patch cache: query tiles of segment A whose chunk (row >> shift) has mask 0 are
+  // skipped (their output rows stay as they are); keys / values are read whatever their mask
+  const int* q_mask; int q_mask_shift;
   long long* dbg;                    // optional phase cycle counters (ATT_TIMING builds)
 };
 
@@ -109,6 +121,7 @@ struct AttnArgs {
 // safe to read before pdl_wait()).
 struct AttnUnit {
   int q_seg, q_row0, q_rows, nq, head, q_pos0;
+  int active;  // bit t: query tile t of the unit is computed
   int ka_row, ka_len, kb_row, kb_len, nA, n_tiles;
 };
 
@@ -123,12 +136,45 @@ __device__ __forceinline__ AttnUnit load_unit(const AttnArgs& a, int u) {
   w.q_row0 = seg_row + item.z;
   w.q_pos0 = (w.q_seg == 0 ? 0 : q.y) + item.z;     // position of the unit's first query in its sequence
   w.q_rows = min(ATT_NQ * ATT_BM, seg_len - item.z);  // valid query rows of this unit
-  w.nq = (w.q_rows + ATT_BM - 1) / ATT_BM;            // active query tiles
+  w.nq = (w.q_rows + ATT_BM - 1) / ATT_BM;            // query tiles with rows
+  w.active = 0;
+  for (int t = 0; t < w.nq; ++t)
+    if (!ATT_EXTRAS || w.q_seg != 0 || a.q_mask == nullptr ||
+        a.q_mask[(w.q_row0 + t * ATT_BM) >> a.q_mask_shift] != 0)
+      w.active |= 1 << t;
   w.ka_row = k.x; w.ka_len = k.y; w.kb_row = k.z; w.kb_len = k.w;
   w.nA = (w.ka_len + ATT_BN - 1) / ATT_BN;
   w.n_tiles = w.nA + (w.kb_len + ATT_BN - 1) / ATT_BN;
   return w;
 }
+
+#if ATT_POLY_MOD > 0
+// exp2 of a pair on the FMA + ALU pipes instead of MUFU (the kernel's bound, see the header):
+// Cody-Waite split x = n + r with the 1.5 * 2^23 magic add (n lands in the low mantissa bits of t),
+// packed degree-2/3 minimax of 2^r on [-0.5, 0.5] (relative error 1.7e-3 / 7.5e-5: below the bf16
+// rounding of P), exponent inserted with a shift + integer add. 3-4 FFMA2/FADD2 issue slots + 6
+// ALU ops per pair against two 8-cycle MUFU slots.
+__device__ __forceinline__ float2 poly_exp2_pair(float2 x) {
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f);
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 fl = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 r = __fadd2_rn(x, make_float2(-fl.x, -fl.y));
+#if ATT_POLY_DEG == 2
+  float2 p = __ffma2_rn(make_float2(0.238428926f, 0.238428926f), r, make_float2(0.703448005f, 0.703448005f));
+  p = __ffma2_rn(p, r, make_float2(1.00044314f, 1.00044314f));
+#else
+  float2 p = __ffma2_rn(make_float2(0.0551716677f, 0.0551716677f), r, make_float2(0.242611122f, 0.242611122f));
+  p = __ffma2_rn(p, r, make_float2(0.693260986f, 0.693260986f));
+  p = __ffma2_rn(p, r, make_float2(0.999928074f, 0.999928074f));
+#endif
+  float2 out;
+  out.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  out.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return out;
+}
+#endif
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant__ CUtensorMap tmQB,
@@ -226,6 +272,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
     int ks = 0, vs = 0;
     uint32_t kph = 0, vph = 0;
     int u = blockIdx.x;  // grid <= n_units
+    uint32_t qi = 0;     // units with at least one computed tile (they own a Q buffer set)
     for (uint32_t it = 0;; ++it) {
       // draw the unit after this one now; the result is only needed at the end of the iteration
       int drawn = 0;
@@ -238,9 +285,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
       }
       if (u < 0) break;
       const AttnUnit w = load_unit(a, u);
-      const uint32_t qb = it % ATT_QBUF;
-      mbar_wait(&q_empty[qb], ((it / ATT_QBUF) & 1) ^ 1);  // unit it - QBUF no longer reads this set
-      if (lane == 0) {
+      const int n_steps_u = w.active != 0 ? w.n_tiles : 0;  // a unit of clean patches loads nothing
+      const uint32_t qb = qi % ATT_QBUF;
+      if (w.active != 0) mbar_wait(&q_empty[qb], ((qi / ATT_QBUF) & 1) ^ 1);  // unit qi - QBUF no longer reads this set
+      if (lane == 0 && w.active != 0) {
         const CUtensorMap* qm = w.q_seg == 0 ? &tmQA : &tmQB;
         const int boxes = (w.q_rows + ATT_BOX_ROWS - 1) / ATT_BOX_ROWS;
         mbar_expect_tx(&q_full[qb], boxes * ATT_BOX_BYTES);
@@ -248,7 +296,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
           tma_load_2d(sQ + qb * (ATT_NQ * ATT_Q_BYTES) + b * ATT_BOX_BYTES, qm, &q_full[qb],
                       a.q_col[w.q_seg] + w.head * ATT_D, w.q_row0 + b * ATT_BOX_ROWS);
       }
-      for (int j = 0; j < w.n_tiles; ++j) {
+      if (w.active != 0) ++qi;
+      for (int j = 0; j < n_steps_u; ++j) {
         const bool inA = j < w.nA;
         const int row = inA ? w.ka_row + j * ATT_BN : w.kb_row + (j - w.nA) * ATT_BN;
         mbar_wait(&k_empty[ks], kph ^ 1);
@@ -282,6 +331,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
     int ks = 0, vs = 0;
     uint32_t kph = 0, vph = 0;
     uint32_t g = 0;  // key steps tile t has run in earlier units (phase of its s/p/o barriers)
+    uint32_t qi = 0; // units with at least one computed tile (Q buffer sets, as in the producer)
     uint64_t dq = 0;
     auto issue_qk = [&](uint32_t k_addr) {  // S_t = Q_t K^T
       if (lane == 0) {
@@ -310,12 +360,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
       const int u = take_unit(it);
       if (u < 0) break;
       const AttnUnit w = load_unit(a, u);
-      const uint32_t qb = it % ATT_QBUF;
+      if (w.active == 0) continue;  // every query tile of the unit belongs to a clean patch
+      const uint32_t qb = qi % ATT_QBUF;
       uint64_t* q_empty_u = &q_empty[qb];
       dq = make_sdesc_sw128(smem_u32(sQ + (qb * ATT_NQ + t) * ATT_Q_BYTES));
-      mbar_wait(&q_full[qb], (it / ATT_QBUF) & 1);
+      mbar_wait(&q_full[qb], (qi / ATT_QBUF) & 1);
+      ++qi;
       tc_fence_after();
-      if (t >= w.nq) {
+      if (((w.active >> t) & 1) == 0) {
         // idle tile of a short unit: release Q and every ring stage unread
         if (lane == 0) mbar_arrive(q_empty_u);
         for (int j = 0; j < w.n_tiles; ++j) {
@@ -385,7 +437,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
       const int u = take_unit(it);
       if (u < 0) break;
       const AttnUnit w = load_unit(a, u);
-      if (t >= w.nq) continue;
+      if (((w.active >> t) & 1) == 0) continue;
       float m_run = -INFINITY, l_run = 0.f;
 
       for (int j = 0; j < w.n_tiles; ++j) {
@@ -420,7 +472,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
           for (int i = 0; i < ATT_BN; ++i)
             if (i >= n_valid) s[i] = -INFINITY;
         }
-        if (a.causal != 0 || a.rel_bias != nullptr) {
+        if (ATT_EXTRAS && (a.causal != 0 || a.rel_bias != nullptr)) {
           // text-encoder variants: T5 relative position bias and / or CLIP's causal mask
           const int qpos = w.q_pos0 + t * ATT_BM + r;
           const int kpos0 = inA ? j * ATT_BN : w.ka_len + (j - w.nA) * ATT_BN;
@@ -463,6 +515,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < ATT_BN / 2; ++i) {
           const float2 x = __ffma2_rn(s2[i], sc2, nm2);
+#if ATT_POLY_MOD > 0
+          if (i % ATT_POLY_MOD == 0) { s2[i] = poly_exp2_pair(x); continue; }
+#endif
           s2[i] = make_float2(fast_exp2(x.x), fast_exp2(x.y));
         }
         float2 acc2[4];
@@ -685,6 +740,9 @@ extern "C" int b200_attn_varlen_ex(const B200AttnSource* src_a, const B200AttnSo
   a.rel_bias = extra ? extra->rel_bias : nullptr;
   a.rel_len = extra ? extra->rel_len : 0;
   a.rel_ld = extra ? extra->rel_ld : 0;
+  a.q_mask = extra ? extra->q_mask : nullptr;
+  a.q_mask_shift = extra ? extra->q_mask_shift : 0;
+  if (a.q_mask && a.q_mask_shift < 7) return B200_ERR_INVALID;  // a query tile is 128 rows
   a.dbg = nullptr;
 #ifdef ATT_TIMING
   {

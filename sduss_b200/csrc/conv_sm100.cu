@@ -362,7 +362,7 @@ extern "C" int b200_conv3x3_bf16(const void* in_maps_dev, const void* out_maps_d
   e.row_group = ep->row_group;
   e.rowvec = static_cast<const __nv_bfloat16*>(ep->rowvec); e.ldv = ep->ldv;
   e.rms_wq = nullptr; e.rms_wk = nullptr; e.rms_q_cols = 0; e.rms_k_cols = 0;
-  e.rms_eps = 0.f; e.q_scale = 1.f; e.act = 0;
+  e.rms_eps = 0.f; e.q_scale = 1.f; e.act = 0; e.row_mask = nullptr; e.row_mask_shift = 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   if (bn256) return dispatch_conv<256, 1>(epi_mode, tmW, a, e, M_total, sms, st);
   // 128-wide tiles with several rounds of tile pairs: two M tiles per CTA share each weight tile

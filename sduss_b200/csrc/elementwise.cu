@@ -46,6 +46,7 @@ struct LnArgs {
   __nv_bfloat16* y; int ldy;
   int shift2_col, scale2_col;
   __nv_bfloat16* y2; int ldy2;
+  const int* row_mask; int row_mask_shift;  // patch cache: rows of chunk (row >> shift) with mask 0 are skipped
 };
 
 constexpr int LN_MAXIT = 8;   // 8 iterations * 32 lanes * 8 elements = 2048 columns
@@ -220,6 +221,7 @@ ln_mod_kernel(const __grid_constant__ LnArgs a, int rows_per_block) {
 #pragma unroll
       for (int i = 0; i < NIT; ++i) nx[p][i] = nx[p + 1][i];
     load_row(nx[PF - 1], row + (PF + 1) * LN_WARPS);
+    if (a.row_mask != nullptr && a.row_mask[row >> a.row_mask_shift] == 0) continue;  // clean patch: keep y
     const int g = grouped ? a.row_group[row] : 0;
     const int slot = g == g0 ? 0 : (g == g1 ? 1 : -1);
     if (has_params && slot < 0) {  // warp-uniform
@@ -360,7 +362,8 @@ extern "C" int b200_layernorm_mod_bf16(const void* x, int ldx, int T, int D, flo
                                        const void* gamma, const void* beta, const void* mod,
                                        int ldm, const int32_t* row_group, int shift_col,
                                        int scale_col, void* y, int ldy, int shift2_col,
-                                       int scale2_col, void* y2, int ldy2, void* stream) {
+                                       int scale2_col, void* y2, int ldy2, const int32_t* row_mask,
+                                       int row_mask_shift, void* stream) {
   if (!x || !y || T <= 0 || D <= 0 || (D & 7) || D > LN_MAXIT * 256 || (ldx & 7) || (ldy & 7))
     return B200_ERR_INVALID;
   if ((gamma == nullptr) != (beta == nullptr)) return B200_ERR_INVALID;
@@ -369,7 +372,7 @@ extern "C" int b200_layernorm_mod_bf16(const void* x, int ldx, int T, int D, flo
   LnArgs a{static_cast<const bf16*>(x), ldx, T, D, eps, static_cast<const bf16*>(gamma),
            static_cast<const bf16*>(beta), static_cast<const bf16*>(mod), ldm, row_group,
            shift_col, scale_col, static_cast<bf16*>(y), ldy, shift2_col, scale2_col,
-           static_cast<bf16*>(y2), ldy2};
+           static_cast<bf16*>(y2), ldy2, row_mask, row_mask_shift};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch ((D + 255) / 256) {
     case 1: return launch_ln<1>(a, st);

@@ -35,7 +35,14 @@ struct EpiArgs {
   float q_scale;               // multiplied into normalised q (softmax scale * log2 e)
   int act;                     // activation of EPI_GELU_TANH / gate of EPI_GEGLU: 0 = the mode's
                                // default (tanh-GELU / erf-GELU), 1 tanh-GELU, 2 erf-GELU, 3 quick-GELU
+  const int* row_mask;         // patch cache: M tiles of chunk (m0 >> row_mask_shift) with mask 0 are
+  int row_mask_shift;          // skipped entirely (no loads, no MMA, C untouched); null = all tiles
 };
+
+// true when the M tile starting at row m0 belongs to a clean patch (kept as it is)
+__device__ __forceinline__ bool tile_skipped(const EpiArgs& e, int m0, int M) {
+  return e.row_mask != nullptr && m0 < M && e.row_mask[m0 >> e.row_mask_shift] == 0;
+}
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;

@@ -107,6 +107,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int t = first_tile; t < num_tiles; t += tile_step) {
       const int m0 = ((t / tiles_n) * MC + int(rank)) * BM;
       const int n0 = (t % tiles_n) * BN;
+      if (tile_skipped(e, m0 - int(rank) * BM, s.M)) continue;  // clean patch (same answer in both CTAs of a pair)
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (lane == 0) {
@@ -133,7 +134,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = first_tile; t < num_tiles; t += tile_step, ++it) {
+    for (int t = first_tile; t < num_tiles; t += tile_step) {
+      if (tile_skipped(e, (t / tiles_n) * MC * BM, s.M)) continue;
       const int acc = it & 1;
       mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -160,6 +162,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           phase ^= 1;
         }
       }
+      ++it;  // accumulator stages count the tiles actually computed
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
@@ -179,10 +182,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tma_prefetch_desc(&tmC);
       if (has_resid) tma_prefetch_desc(&tmR);
     }
-    for (int t = first_tile; t < num_tiles; t += tile_step, ++it) {
+    for (int t = first_tile; t < num_tiles; t += tile_step) {
       const int acc = it & 1;
       const int m0 = ((t / tiles_n) * MC + int(rank)) * BM;
       const int n0 = (t % tiles_n) * BN;
+      if (tile_skipped(e, m0 - int(rank) * BM, s.M)) continue;
       if (has_resid && leader) {  // residual chunks 0 and 1 fly while the main loop finishes
         tma_store_wait_read<0>();   // both staging tiles have left for HBM (previous tile)
 #pragma unroll
@@ -243,6 +247,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
+      ++it;
     }
     if (leader) tma_store_wait<0>();
   }
@@ -375,6 +380,9 @@ extern "C" int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
   e.rms_eps = ep->rms_eps;
   e.q_scale = ep->q_scale;
   e.act = ep->act;
+  e.row_mask = ep->row_mask;
+  e.row_mask_shift = ep->row_mask_shift;
+  if (ep->row_mask && ep->row_mask_shift < 8) return B200_ERR_INVALID;  // a CTA pair covers 256 rows
   GemmShape s{M, N, K};
   // output / residual tensor maps of the staged epilogue (bf16 outputs only)
   CUtensorMap tmC = tmA, tmR = tmA;

@@ -45,22 +45,25 @@ def capture_after():
     return int(os.environ.get("SDUSS_B200_CAPTURE_AFTER", "2"))
 
 
-def run_plan(model, plan, prologue=None):
+def run_plan(model, plan, prologue=None, run=None, state=None):
     """Runs prologue(plan) (per-step inputs: by-value kernel arguments that change every step, never
-    captured) and then model._run(plan). All shapes and pointers of a plan are static, so the
-    forward -- a few hundred to a few thousand launches -- is captured into a CUDA graph on the
-    plan's second use and replayed from then on; per-launch profiling (ops.profile) forces the
-    eager path."""
+    captured) and then run(plan) (default model._run). All shapes and pointers of a plan are static,
+    so the forward -- a few hundred to a few thousand launches -- is captured into a CUDA graph on
+    the plan's second use and replayed from then on; per-launch profiling (ops.profile) forces the
+    eager path. `state` holds graph / use counters (default: the plan itself; a plan that is run in
+    more than one way, e.g. with and without the patch cache, passes one state object per way)."""
     global launch_count
+    run = model._run if run is None else run
+    st = plan if state is None else state
     if not getattr(model, "use_graphs", False) or profile is not None:
-        _run_eager(model, plan, prologue)
+        _run_eager(model, plan, prologue, run)
         return
-    plan.uses = getattr(plan, "uses", 0) + 1
-    if plan.graph is None:
-        if plan.uses < capture_after() or not getattr(plan, "warm", False):
-            _run_eager(model, plan, prologue)  # eager: allocates workspaces, encodes tensor maps
-            plan.warm = True
-            if plan.uses < capture_after():
+    st.uses = getattr(st, "uses", 0) + 1
+    if getattr(st, "graph", None) is None:
+        if st.uses < capture_after() or not getattr(st, "warm", False):
+            _run_eager(model, plan, prologue, run)  # eager: allocates workspaces, encodes tensor maps
+            st.warm = True
+            if st.uses < capture_after():
                 return
             torch.cuda.current_stream().synchronize()
             eager_done = True
@@ -69,21 +72,21 @@ def run_plan(model, plan, prologue=None):
             if prologue is not None:
                 prologue(plan)
         n0 = launch_count
-        plan.graph = _capture(model, plan)
-        plan.graph_launches = launch_count - n0
+        st.graph = _capture(model, plan, run)
+        st.graph_launches = launch_count - n0
         launch_count = n0
         if eager_done:
             return                            # the eager run already produced this call's result
-        plan.graph.replay()
-        launch_count += plan.graph_launches
+        st.graph.replay()
+        launch_count += st.graph_launches
         return
     if prologue is not None:
         prologue(plan)
-    plan.graph.replay()
-    launch_count += plan.graph_launches
+    st.graph.replay()
+    launch_count += st.graph_launches
 
 
-def _capture(model, plan):
+def _capture(model, plan, run=None):
     """Stream capture of model._run(plan) without torch.cuda.graph()'s entry cost (it runs
     gc.collect(), a device-wide synchronize and empty_cache() on every capture: tens of ms, and the
     emptied allocator cache is paid again by the next steps). A warm plan allocates nothing while
@@ -98,7 +101,7 @@ def _capture(model, plan):
     with torch.cuda.stream(side):
         g.capture_begin(capture_error_mode="thread_local")
         try:
-            model._run(plan)
+            (run or model._run)(plan)
         finally:
             g.capture_end()
     cur.wait_stream(side)
@@ -111,7 +114,7 @@ class ArenaOverflow(RuntimeError):
         self.need = need
 
 
-def _run_eager(model, plan, prologue=None):
+def _run_eager(model, plan, prologue=None, run=None):
     """prologue(plan); model._run(plan). Plans that bump-allocate their workspaces from the model's
     Arena restart on a larger block when it overflows (a handful of times per process: the block
     doubles); the prologue is re-run because it fills buffers of the block."""
@@ -119,7 +122,7 @@ def _run_eager(model, plan, prologue=None):
         try:
             if prologue is not None:
                 prologue(plan)
-            return model._run(plan)
+            return (run or model._run)(plan)
         except ArenaOverflow as e:
             if torch.cuda.is_available():  # kernels of the partial run still use the old views
                 torch.cuda.current_stream().synchronize()
@@ -276,7 +279,7 @@ def _req(t, dtype=torch.bfloat16):
 
 def gemm(a, w, out=None, *, epi=EPI_BIAS, bias=None, resid=None, gate=None, row_group=None,
          rowvec=None, rms_wq=None, rms_wk=None, rms_q_cols=0, rms_k_cols=0, rms_eps=1e-6,
-         q_scale=1.0, out_fp32=False, act=0):
+         q_scale=1.0, out_fp32=False, act=0, row_mask=None, row_mask_shift=8):
     """out = epilogue(a @ w.T). a: [M, K] bf16 (row stride may exceed K), w: [N, K] bf16."""
     _req(a), _req(w)
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
@@ -298,6 +301,9 @@ def gemm(a, w, out=None, *, epi=EPI_BIAS, bias=None, resid=None, gate=None, row_
     d.rms_wq, d.rms_wk = _ptr(rms_wq), _ptr(rms_wk)
     d.rms_q_cols, d.rms_k_cols = rms_q_cols, rms_k_cols
     d.rms_eps, d.q_scale, d.act = rms_eps, q_scale, act
+    if row_mask is not None:  # patch cache: M tiles of clean patches are skipped, their rows of out kept
+        _req(row_mask, torch.int32)
+        d.row_mask, d.row_mask_shift = _ptr(row_mask), row_mask_shift
     _ev = _count("b200_gemm_bf16", (M, N, K, epi))
     check(lib.b200_gemm_bf16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), M, N, K, epi,
                              ctypes.byref(d), _stream()), "b200_gemm_bf16")
@@ -354,14 +360,17 @@ def build_attn_plan(seqs, device, n_heads, max_ctas=None):
 
 
 def attn_varlen(src_a, src_b, seq_table, work_units, n_units, sched_state, max_ctas, scale,
-                causal=False, rel_bias=None, rel_len=0):
+                causal=False, rel_bias=None, rel_len=0, q_mask=None, q_mask_shift=8):
     """rel_bias: fp32 [heads, >= 2 rel_len - 1], bias of key offset (k - q) at column k - q + rel_len - 1,
     already divided by `scale` (T5); causal: CLIP's mask. Both off on the denoising path."""
     _ev = _count("b200_attn_varlen_bf16")
     extra = None
-    if causal or rel_bias is not None:
+    if causal or rel_bias is not None or q_mask is not None:
         extra = _lib.AttnExtra()
         extra.causal = int(causal)
+        if q_mask is not None:  # patch cache: query tiles of clean patches (segment A) are skipped
+            _req(q_mask, torch.int32)
+            extra.q_mask, extra.q_mask_shift = _ptr(q_mask), q_mask_shift
         if rel_bias is not None:
             _req(rel_bias, torch.float32)
             assert rel_bias.dim() == 2 and rel_bias.stride(1) == 1
@@ -374,6 +383,61 @@ def attn_varlen(src_a, src_b, seq_table, work_units, n_units, sched_state, max_c
           "b200_attn_varlen_ex")
     if _ev is not None:
         _ev.record()
+
+
+class DeviceForest:
+    """A RandomForest flattened into device arrays for b200_patch_mask_bf16. Build it from a fitted
+    sklearn RandomForestClassifier (`from_sklearn`) or from explicit arrays; `threshold_rule(tau)` is
+    the one-node forest "recompute iff MSE > tau"."""
+
+    def __init__(self, feature, threshold, left, right, value, roots, device):
+        i32 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.int32).to(device)
+        f32 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32).to(device)
+        self.t = (i32(feature), f32(threshold), i32(left), i32(right), f32(value), i32(roots))
+        self.c = _lib.Forest()
+        (self.c.feature, self.c.threshold, self.c.left, self.c.right, self.c.value, self.c.roots) = \
+            [_ptr(t) for t in self.t]
+        self.c.n_trees = len(roots)
+
+    @classmethod
+    def from_sklearn(cls, rf, device):
+        feature, threshold, left, right, value, roots = [], [], [], [], [], []
+        one = list(rf.classes_).index(1) if 1 in list(rf.classes_) else None
+        for est in rf.estimators_:
+            t, base = est.tree_, len(feature)
+            roots.append(base)
+            for n in range(t.node_count):
+                leaf = t.children_left[n] < 0
+                feature.append(-1 if leaf else int(t.feature[n]))
+                threshold.append(0.0 if leaf else float(t.threshold[n]))
+                left.append(0 if leaf else base + int(t.children_left[n]))
+                right.append(0 if leaf else base + int(t.children_right[n]))
+                v = t.value[n][0]
+                value.append(float(v[one] / v.sum()) if one is not None else 0.0)
+        return cls(feature, threshold, left, right, value, roots, device)
+
+    @classmethod
+    def threshold_rule(cls, tau, device):
+        return cls([2, -1, -1], [tau, 0.0, 0.0], [1, 0, 0], [2, 0, 0], [0.0, 0.0, 1.0], [0], device)
+
+
+def patch_mask_workspace(n_patches, device):
+    return torch.zeros(lib.b200_patch_mask_workspace_bytes(n_patches), dtype=torch.uint8, device=device)
+
+
+def patch_mask(x, prev, patch_latent, latent_t, latent_valid, skipped, mask, forest, block_index,
+               refresh, workspace, rows_per_patch=256, mse=None):
+    """mask[p] = 1 where patch p (rows_per_patch rows of x) must be recomputed; prev <- x."""
+    _req(x), _req(prev)
+    n = mask.numel()
+    _ev = _count("b200_patch_mask_bf16")
+    check(lib.b200_patch_mask_bf16(_ptr(x), x.stride(0), _ptr(prev), prev.stride(0), n, rows_per_patch,
+                                   x.shape[1], _ptr(patch_latent), _ptr(latent_t), _ptr(latent_valid),
+                                   _ptr(skipped), _ptr(mask), _ptr(mse), ctypes.byref(forest.c), block_index,
+                                   refresh, _ptr(workspace), _stream()), "b200_patch_mask_bf16")
+    if _ev is not None:
+        _ev.record()
+    return mask
 
 
 def embed_rows(ids, table, out, pos=None, seq_len=0):
@@ -401,7 +465,7 @@ def rmsnorm(x, weight, y, eps):
 
 # ------------------------------------------------------------------ HBM-bound kernels
 def layernorm_mod(x, y, *, eps, gamma=None, beta=None, mod=None, row_group=None, shift_col=0,
-                  scale_col=0, y2=None, shift2_col=0, scale2_col=0):
+                  scale_col=0, y2=None, shift2_col=0, scale2_col=0, row_mask=None, row_mask_shift=8):
     """y = LN(x)[*gamma+beta][*(1+mod[g,scale_col:])+mod[g,shift_col:]]; optional y2."""
     _req(x), _req(y)
     T, D = x.shape
@@ -410,7 +474,8 @@ def layernorm_mod(x, y, *, eps, gamma=None, beta=None, mod=None, row_group=None,
         _ptr(x), x.stride(0), T, D, ctypes.c_float(eps), _ptr(gamma), _ptr(beta), _ptr(mod),
         (mod.stride(0) if mod is not None else 0), _ptr(row_group), shift_col, scale_col,
         _ptr(y), y.stride(0), shift2_col, scale2_col, _ptr(y2),
-        (y2.stride(0) if y2 is not None else 0), _stream()), "b200_layernorm_mod_bf16")
+        (y2.stride(0) if y2 is not None else 0), _ptr(row_mask), row_mask_shift, _stream()),
+        "b200_layernorm_mod_bf16")
     if _ev is not None:
         _ev.record()
     return y

@@ -319,7 +319,26 @@ class B200DenoisingPipelineBase:
             if self.has_time_ids:
                 ops.gather_rows(pl.ids32.view(pl.L, -1), id_ptrs, e0.ids.numel() * 4)
 
-        ops.run_plan(model, plan, prologue)
+        if getattr(model, "patch_cache_enabled", lambda: False)():
+            # Patch cache (row f-3): a latent's kept block outputs / keys / values are usable iff this
+            # plan slot served the same request, same CFG branch, at the step right before this one.
+            cb = model.cache_for(plan)
+            tags = []
+            for res in res_list:
+                rs = reqs[res]
+                for k in range(dup):
+                    tags += [(r.request_id, k, r.scheduler_states._step_index) for r in rs]
+            valid = [1.0 if cb.tags[l] == t else 0.0 for l, t in enumerate(tags)]
+            cb.tags = [(rid, k, step + 1) for rid, k, step in tags]
+            base_prologue = prologue
+
+            def prologue(pl):
+                base_prologue(pl)
+                ops.write_f32(cb.valid, valid)
+
+            ops.run_plan(model, plan, prologue, run=model._run_cached, state=plan.cached_state)
+        else:
+            ops.run_plan(model, plan, prologue)
         ops.cfg_scheduler_step(plan.flat_out, s_refs, dtype, guidance, cfg, self.step_mode)
         for r, off, n, shape in views:
             ss = r.scheduler_states

@@ -83,7 +83,8 @@ class _Plan:
         T, Tc = self.T, self.Tc
         b16, f32 = torch.bfloat16, torch.float32
         specs = [("flat_in", (sum(numel_in),), b16), ("flat_out", (sum(numel_out),), b16),
-                 ("tokens", (T, cfg.in_channels * p * p), b16), ("x", (T, D), b16), ("xn", (T, D), b16),
+                 ("tokens", (T, cfg.in_channels * p * p), b16), ("x", (T, D), b16), ("xa", (T, D), b16),
+                 ("xn", (T, D), b16),
                  ("xn2", (T, D), b16), ("c", (Tc, D), b16), ("cn", (Tc, D), b16), ("qkv", (T, 3 * D), b16),
                  ("qkv_c", (Tc, 3 * D), b16), ("att", (T, D), b16), ("att_c", (Tc, D), b16),
                  ("ff", (T, 4 * D), b16), ("ff_c", (Tc, 4 * D), b16),
@@ -133,6 +134,57 @@ class _Plan:
                                        v_col=2 * D, out=self.att_c)
         self.graph = None
         self.graph_launches = 0
+        self.cache = None          # _PatchCache, allocated when the plan first runs with the patch cache
+        self.cached_state = None   # graph / use counters of the cached way of running this plan
+        self.S = S
+
+
+class _CachedState:
+    graph = None
+    graph_launches = 0
+    uses = 0
+    warm = False
+
+
+class _PatchCache:
+    """What a plan keeps ACROSS steps when the patch cache is on: per block the
+    block output `xout`, the block input of the previous step `xprev` (MSE feature), the fused q|k|v
+    projections `qkv` (`qkv2` for the second attention of dual blocks) -- rows of clean patches are
+    simply not rewritten, so they still hold what the patch had when it was last computed -- plus
+    the per-patch skip counters, the masks and the per-latent validity flags the step fills in.
+    Everything is tied to the plan's row layout: a request keeps its cache while it stays in the same
+    slot of the same batch composition from one step to the next (tags), otherwise its patches are
+    recomputed once and the cache restarts (zero-copy; the reference keys Python dicts of tensors by
+    request id and patch and re-stacks them every block, cache_manager.py:58-99)."""
+
+    PATCH = 256
+
+    def __init__(self, model, pl):
+        dev, D = model.device, model.cfg.inner_dim
+        assert all(s % self.PATCH == 0 for s in pl.S), "patch cache needs latents of whole 256-token patches"
+        n = pl.T // self.PATCH
+        self.n_patches = n
+        self.patch_latent = torch.from_numpy(
+            np.repeat(np.arange(pl.L, dtype=np.int32), [s // self.PATCH for s in pl.S])).to(dev)
+        nb = len(model.blocks)
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        self.xout = [torch.empty((pl.T, D), **bf) for _ in range(nb)]
+        self.xprev = [torch.empty((pl.T, D), **bf) for _ in range(nb)]
+        self.qkv = [torch.zeros((pl.T, 3 * D), **bf) for _ in range(nb)]  # K / V rows must stay finite
+        self.qkv2 = [torch.zeros((pl.T, 3 * D), **bf) if b["dual"] else None for b in model.blocks]
+        self.skipped = torch.zeros((nb, n), device=dev, dtype=torch.int32)
+        self.mask = torch.ones((nb, n), device=dev, dtype=torch.int32)
+        self.mse = torch.zeros((nb, n), device=dev, dtype=torch.float32)
+        self.valid = torch.zeros((pl.L,), device=dev, dtype=torch.float32)
+        self.ws = ops.patch_mask_workspace(n, dev)
+        self.tags = [None] * pl.L     # (request id, CFG branch, step index the kept data is good for)
+        self.src = [ops.attn_source(q=q, q_col=0, k=q, k_col=D, v=q, v_col=2 * D, out=pl.att) for q in self.qkv]
+        self.src2 = [None if q is None else ops.attn_source(q=q, q_col=0, k=q, k_col=D, v=q, v_col=2 * D, out=pl.att)
+                     for q in self.qkv2]
+
+    def bytes(self):
+        return sum(t.numel() * t.element_size() for grp in (self.xout, self.xprev, self.qkv, self.qkv2)
+                   for t in grp if t is not None)
 
 
 class B200SD3Transformer2DModel(torch.nn.Module):
@@ -230,6 +282,36 @@ class B200SD3Transformer2DModel(torch.nn.Module):
     def plan_for(self, comp, ctx_len) -> _Plan:
         """comp: ((resolution key, latents, h, w), ...) in ascending resolution order."""
         return self._plans.get((comp, ctx_len), lambda: _Plan(self, comp, ctx_len))
+
+    # ---- patch cache (SURVEY.md row f-3)
+    def enable_patch_cache(self, forest, refresh: int = 2, max_cached_plans: int = 3):
+        """forest: ops.DeviceForest deciding, from [block, timestep, MSE of the block input against the
+        previous step], which 256-token patches a block recomputes (reference: the cuML RandomForest
+        of ESYMRED_TRANSFORMER_PATH, cache_manager.py:37-44,161-191; refresh = 2 forced recompute
+        after two skips, :183). Only `max_cached_plans` batch compositions keep their (multi-GB)
+        cache buffers at a time; pass forest=None to switch the cache off."""
+        import collections
+        self.patch_forest, self.patch_refresh = forest, refresh
+        self._cache_lru, self._cache_max = collections.OrderedDict(), max_cached_plans
+        if forest is None:
+            for pl in self._plans.values():
+                pl.cached_state = pl.cache = None
+
+    def patch_cache_enabled(self):
+        return getattr(self, "patch_forest", None) is not None
+
+    def cache_for(self, pl):
+        """The plan's cache buffers (allocated on first use; least recently used plans lose theirs)."""
+        key = id(pl)
+        if pl.cache is None:
+            while len(self._cache_lru) >= self._cache_max:
+                _, old = self._cache_lru.popitem(last=False)
+                old.cached_state = None   # its graph points into the buffers: drop it first
+                old.cache = None
+            pl.cache, pl.cached_state = _PatchCache(self, pl), _CachedState()
+        self._cache_lru[key] = pl
+        self._cache_lru.move_to_end(key)
+        return pl.cache
 
     # ---- per-request conditioning, computed once per request (sduss_b200.pipelines caches it)
     cond_kind = "sd3"
@@ -344,6 +426,95 @@ class B200SD3Transformer2DModel(torch.nn.Module):
         main.wait_event(ev_side)  # rejoin (the last block has no context output, but keep the graph closed)
         om = self.out_mod
         ops.layernorm_mod(pl.x, pl.xn, eps=1e-6, mod=mod, row_group=pl.row_group,
+                          shift_col=om + D, scale_col=om)
+        G(pl.xn, self.proj_w, pl.out_tok, bias=self.proj_b)
+        ops.sd3_unpatchify(pl.out_tok, pl.desc, pl.L, pl.max_tokens, cfg.out_channels, p, pl.out_ptr)
+
+    def _run_cached(self, pl: _Plan):
+        """The forward with the patch cache (policy in oracle/patch_cache.py).
+        Same launches as _run plus one decision kernel per block; every image-stream kernel takes the
+        block's patch mask and skips the tiles of clean patches, whose block output / keys / values
+        stay in the per-block buffers of pl.cache. The residual stream therefore moves through
+        per-block buffers (block i reads xout[i-1], writes xout[i]) instead of being updated in
+        place. The context stream (333 tokens per latent) is always recomputed."""
+        cfg, cb = self.cfg, pl.cache
+        D, H, p = cfg.inner_dim, cfg.num_attention_heads, cfg.patch_size
+        G = ops.gemm
+        te = self.te
+        scale = 1.0 / math.sqrt(cfg.attention_head_dim)
+        ops.timestep_embedding(pl.t32, 256, out=pl.tsin)
+        G(pl.tsin, te["timestep_embedder.linear_1.weight"], pl.e1, bias=te["timestep_embedder.linear_1.bias"])
+        ops.silu(pl.e1, pl.e1)
+        G(pl.e1, te["timestep_embedder.linear_2.weight"], pl.e2, bias=te["timestep_embedder.linear_2.bias"])
+        G(pl.pooled, te["text_embedder.linear_1.weight"], pl.e3, bias=te["text_embedder.linear_1.bias"])
+        ops.silu(pl.e3, pl.e3)
+        G(pl.e3, te["text_embedder.linear_2.weight"], pl.temb, bias=te["text_embedder.linear_2.bias"],
+          epi=ops.EPI_GATE_RESID, resid=pl.e2)
+        ops.silu(pl.temb, pl.e1)
+        G(pl.e1, self.mod_w, pl.mod, bias=self.mod_b)
+        ops.sd3_patchify(pl.in_ptr, pl.desc, pl.L, pl.max_tokens, cfg.in_channels, p, pl.tokens)
+        G(pl.tokens, self.pe_w, pl.x, bias=self.pe_b, epi=ops.EPI_GATE_RESID, resid=pl.pos_rows)
+        mod = pl.mod
+        main = torch.cuda.current_stream()
+        side = self._side_stream() if getattr(self, "two_streams", True) else main
+        ev_main, ev_side = torch.cuda.Event(), torch.cuda.Event()
+        ev_main.record(main)
+        side.wait_event(ev_main)
+        xin = pl.x
+        for i, blk in enumerate(self.blocks):
+            m, cm = blk["mod"], blk["cmod"]
+            dual, last = blk["dual"], blk["last"]
+            mk = cb.mask[i]
+            with torch.cuda.stream(side):
+                if last:
+                    ops.layernorm_mod(pl.c, pl.cn, eps=1e-6, mod=mod, row_group=pl.row_group_ctx,
+                                      shift_col=cm + D, scale_col=cm)
+                else:
+                    ops.layernorm_mod(pl.c, pl.cn, eps=1e-6, mod=mod, row_group=pl.row_group_ctx,
+                                      shift_col=cm, scale_col=cm + D)
+                G(pl.cn, blk["aqkv_w"], pl.qkv_c, bias=blk["aqkv_b"], epi=ops.EPI_QK_RMSNORM,
+                  rms_wq=blk["norm_added_q"], rms_wk=blk["norm_added_k"], rms_q_cols=D, rms_k_cols=D)
+                ev_side.record(side)
+            # the decision: MSE of the block input against the previous step, forest, refresh rule
+            ops.patch_mask(xin, cb.xprev[i], cb.patch_latent, pl.t32, cb.valid, cb.skipped[i], mk,
+                           self.patch_forest, i, self.patch_refresh, cb.ws, mse=cb.mse[i])
+            ops.layernorm_mod(xin, pl.xn, eps=1e-6, mod=mod, row_group=pl.row_group,
+                              shift_col=m, scale_col=m + D,
+                              y2=pl.xn2 if dual else None, shift2_col=m + 6 * D, scale2_col=m + 7 * D,
+                              row_mask=mk)
+            G(pl.xn, blk["qkv_w"], cb.qkv[i], bias=blk["qkv_b"], epi=ops.EPI_QK_RMSNORM,
+              rms_wq=blk["norm_q"], rms_wk=blk["norm_k"], rms_q_cols=D, rms_k_cols=D, row_mask=mk)
+            main.wait_event(ev_side)
+            ops.attn_varlen(cb.src[i], pl.src_ctx, *pl.joint_plan, scale, q_mask=mk)
+            ev_main.record(main)
+            if not last:
+                with torch.cuda.stream(side):
+                    side.wait_event(ev_main)
+                    G(pl.att_c, blk["aout_w"], pl.c, bias=blk["aout_b"], epi=ops.EPI_GATE_RESID,
+                      resid=pl.c, gate=mod[:, cm + 2 * D:cm + 3 * D], row_group=pl.row_group_ctx)
+                    ops.layernorm_mod(pl.c, pl.cn, eps=1e-6, mod=mod, row_group=pl.row_group_ctx,
+                                      shift_col=cm + 3 * D, scale_col=cm + 4 * D)
+                    G(pl.cn, blk["ffc1_w"], pl.ff_c, bias=blk["ffc1_b"], epi=ops.EPI_GELU_TANH)
+                    G(pl.ff_c, blk["ffc2_w"], pl.c, bias=blk["ffc2_b"], epi=ops.EPI_GATE_RESID,
+                      resid=pl.c, gate=mod[:, cm + 5 * D:cm + 6 * D], row_group=pl.row_group_ctx)
+            G(pl.att, blk["out_w"], pl.xa, bias=blk["out_b"], epi=ops.EPI_GATE_RESID, resid=xin,
+              gate=mod[:, m + 2 * D:m + 3 * D], row_group=pl.row_group, row_mask=mk)
+            if dual:
+                G(pl.xn2, blk["qkv2_w"], cb.qkv2[i], bias=blk["qkv2_b"], epi=ops.EPI_QK_RMSNORM,
+                  rms_wq=blk["norm_q2"], rms_wk=blk["norm_k2"], rms_q_cols=D, rms_k_cols=D, row_mask=mk)
+                ops.attn_varlen(cb.src2[i], None, *pl.self_plan, scale, q_mask=mk)
+                G(pl.att, blk["out2_w"], pl.xa, bias=blk["out2_b"], epi=ops.EPI_GATE_RESID,
+                  resid=pl.xa, gate=mod[:, m + 8 * D:m + 9 * D], row_group=pl.row_group, row_mask=mk)
+            ops.layernorm_mod(pl.xa, pl.xn, eps=1e-6, mod=mod, row_group=pl.row_group,
+                              shift_col=m + 3 * D, scale_col=m + 4 * D, row_mask=mk)
+            G(pl.xn, blk["ff1_w"], pl.ff, bias=blk["ff1_b"], epi=ops.EPI_GELU_TANH, row_mask=mk)
+            G(pl.ff, blk["ff2_w"], cb.xout[i], bias=blk["ff2_b"], epi=ops.EPI_GATE_RESID, resid=pl.xa,
+              gate=mod[:, m + 5 * D:m + 6 * D], row_group=pl.row_group, row_mask=mk)
+            xin = cb.xout[i]
+        ev_side.record(side)
+        main.wait_event(ev_side)
+        om = self.out_mod
+        ops.layernorm_mod(xin, pl.xn, eps=1e-6, mod=mod, row_group=pl.row_group,
                           shift_col=om + D, scale_col=om)
         G(pl.xn, self.proj_w, pl.out_tok, bias=self.proj_b)
         ops.sd3_unpatchify(pl.out_tok, pl.desc, pl.L, pl.max_tokens, cfg.out_channels, p, pl.out_ptr)

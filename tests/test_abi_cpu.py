@@ -26,14 +26,15 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_ctypes_signatures_cover_header():
     from sduss_b200 import _lib
     declared = set(_header_functions())
-    bound = set(_lib.SIGNATURES) | {"b200_groupnorm_workspace_bytes"}
+    bound = set(_lib.SIGNATURES) | {"b200_groupnorm_workspace_bytes", "b200_patch_mask_workspace_bytes"}
     assert declared == bound, declared ^ bound
 
 
 def test_struct_layouts_match_header():
     from sduss_b200 import _lib
     # B200EpilogueDesc: 8B ptr, 2x i32, 2 ptr, i32(+pad), ptr, i32(+pad), ptr, ptr, i32(+pad), 2 ptr, 2 i32, 2 f32
-    assert ctypes.sizeof(_lib.EpilogueDesc) == 120 and _lib.EpilogueDesc.act.offset == 112
+    assert ctypes.sizeof(_lib.EpilogueDesc) == 136 and _lib.EpilogueDesc.act.offset == 112
+    assert _lib.EpilogueDesc.row_mask.offset == 120 and ctypes.sizeof(_lib.AttnExtra) == 32
     assert _lib.EpilogueDesc.row_group.offset == 56 and _lib.EpilogueDesc.rms_eps.offset == 104
     assert ctypes.sizeof(_lib.AttnSource) == 80
     assert _lib.AttnSource.k.offset == 24 and _lib.AttnSource.out.offset == 64

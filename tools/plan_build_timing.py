@@ -27,12 +27,12 @@ acc = {}
 orig_capture, orig_eager = ops._capture, ops._run_eager
 
 
-def cap(m, p):
-    t = time.perf_counter(); g = orig_capture(m, p); acc["capture"] = (time.perf_counter() - t) * 1e3; return g
+def cap(m, p, run=None):
+    t = time.perf_counter(); g = orig_capture(m, p, run); acc["capture"] = (time.perf_counter() - t) * 1e3; return g
 
 
-def eag(m, p, pro=None):
-    torch.cuda.synchronize(); t = time.perf_counter(); orig_eager(m, p, pro); torch.cuda.synchronize()
+def eag(m, p, pro=None, run=None):
+    torch.cuda.synchronize(); t = time.perf_counter(); orig_eager(m, p, pro, run); torch.cuda.synchronize()
     acc["eager"] = (time.perf_counter() - t) * 1e3
 
 
