@@ -14,6 +14,10 @@
  *     (norm_silu_concat.cu:434-437); callers of this ABI must turn non-zero into an exception.
  *   - activations are bf16 row-major "packed" buffers: rows = tokens / pixels of all requests
  *     back to back, columns = channels. Integer descriptor tables are int32.
+ *   - scratch memory is always the caller's: the four entry points that need any come with a
+ *     *_bytes query (b200_attn_workspace_bytes, b200_conv3x3_maps_bytes,
+ *     b200_groupnorm_workspace_bytes, b200_patch_mask_workspace_bytes); every other entry point
+ *     needs none.
  */
 #ifndef SDUSS_B200_H_
 #define SDUSS_B200_H_
@@ -115,6 +119,7 @@ typedef struct B200AttnSource {
  * Every row of the K / V source buffers must hold finite values. src_b may be NULL.
  * NULL q / k / v pointers inside a source mean that side contributes no such segment. */
 int b200_attn_rows_per_item(void);
+long long b200_attn_workspace_bytes(void);  /* size of sched_state (device, zeroed once by the caller) */
 int b200_attn_build_schedule(const int32_t* seq_table, int n_seq, int n_heads,
                              int32_t* work_units, int* n_units_out);
 int b200_attn_varlen_bf16(const B200AttnSource* src_a, const B200AttnSource* src_b,
@@ -240,6 +245,7 @@ int b200_gather_rows(void* dst, long long dst_stride_bytes, const void* const* s
  * Step 1 (once per batch composition, host): encode one input tensor map per latent.
  *   in_desc_host: HOST int32 [n][4] = {input row offset, Hin, Win, 0}; maps_host: HOST buffer
  *   of n * 128 bytes, to be uploaded to a 64-byte-aligned device buffer. */
+long long b200_conv3x3_maps_bytes(int n_latents);  /* size of maps_host / its device copy */
 int b200_conv3x3_encode_maps(const void* x, int ldx, int Cin, const int32_t* in_desc_host,
                              int n_latents, int stride, void* maps_host);
 /* Step 2 (per call): tiles_dev int32 [n_mtiles][4] = {latent, y0, x0, 0}: 16x8 (rows x cols)

@@ -154,6 +154,10 @@ def _bind():
     lib.b200_groupnorm_workspace_bytes.restype = ctypes.c_longlong
     lib.b200_patch_mask_workspace_bytes.argtypes = [c_int]
     lib.b200_patch_mask_workspace_bytes.restype = ctypes.c_longlong
+    lib.b200_attn_workspace_bytes.argtypes = []
+    lib.b200_attn_workspace_bytes.restype = ctypes.c_longlong
+    lib.b200_conv3x3_maps_bytes.argtypes = [c_int]
+    lib.b200_conv3x3_maps_bytes.restype = ctypes.c_longlong
 
 
 _bind()

@@ -76,9 +76,6 @@ constexpr float ATT_RESCALE_THRESHOLD = 8.f;  // lazy rescale: keep a stale max 
 #ifndef ATT_F32X2
 #define ATT_F32X2 1  // packed fp32 pairs (FFMA2 / FADD2) in the softmax
 #endif
-#ifndef ATT_EXTRAS
-#define ATT_EXTRAS 1  // causal mask / relative bias / q-tile skip compiled in (0: A/B build without them)
-#endif
 #ifndef ATT_POLY_MOD
 #define ATT_POLY_MOD 0  // > 0: every ATT_POLY_MOD-th element pair takes exp2 on the FMA pipe (below)
 #endif
@@ -125,6 +122,11 @@ struct AttnUnit {
   int ka_row, ka_len, kb_row, kb_len, nA, n_tiles;
 };
 
+// EXTRAS: 0 = the denoising path; 1 = + query-tile skip (patch cache); 2 = + causal mask / relative
+// position bias (text encoders). Separate instantiations because at 126-128 registers per thread
+// the extra live values of the in-loop variants cost 6 % (685 vs 732 TFLOP/s on the config-2 joint
+// shapes, profiles/r02_attn_variants.txt), branch or no branch.
+template <int EXTRAS>
 __device__ __forceinline__ AttnUnit load_unit(const AttnArgs& a, int u) {
   const int4 item = __ldg(reinterpret_cast<const int4*>(a.work_units) + u);
   const int4* st = reinterpret_cast<const int4*>(a.seq_table + item.x * 8);
@@ -139,7 +141,7 @@ __device__ __forceinline__ AttnUnit load_unit(const AttnArgs& a, int u) {
   w.nq = (w.q_rows + ATT_BM - 1) / ATT_BM;            // query tiles with rows
   w.active = 0;
   for (int t = 0; t < w.nq; ++t)
-    if (!ATT_EXTRAS || w.q_seg != 0 || a.q_mask == nullptr ||
+    if (EXTRAS == 0 || w.q_seg != 0 || a.q_mask == nullptr ||
         a.q_mask[(w.q_row0 + t * ATT_BM) >> a.q_mask_shift] != 0)
       w.active |= 1 << t;
   w.ka_row = k.x; w.ka_len = k.y; w.kb_row = k.z; w.kb_len = k.w;
@@ -176,6 +178,7 @@ __device__ __forceinline__ float2 poly_exp2_pair(float2 x) {
 }
 #endif
 
+template <int EXTRAS>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant__ CUtensorMap tmQB,
                 const __grid_constant__ CUtensorMap tmKA, const __grid_constant__ CUtensorMap tmKB,
@@ -284,7 +287,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
         mbar_arrive(&u_full[slot]);
       }
       if (u < 0) break;
-      const AttnUnit w = load_unit(a, u);
+      const AttnUnit w = load_unit<EXTRAS>(a, u);
       const int n_steps_u = w.active != 0 ? w.n_tiles : 0;  // a unit of clean patches loads nothing
       const uint32_t qb = qi % ATT_QBUF;
       if (w.active != 0) mbar_wait(&q_empty[qb], ((qi / ATT_QBUF) & 1) ^ 1);  // unit qi - QBUF no longer reads this set
@@ -359,7 +362,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
     for (uint32_t it = 0;; ++it) {
       const int u = take_unit(it);
       if (u < 0) break;
-      const AttnUnit w = load_unit(a, u);
+      const AttnUnit w = load_unit<EXTRAS>(a, u);
       if (w.active == 0) continue;  // every query tile of the unit belongs to a clean patch
       const uint32_t qb = qi % ATT_QBUF;
       uint64_t* q_empty_u = &q_empty[qb];
@@ -436,7 +439,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
     for (uint32_t it = 0;; ++it) {
       const int u = take_unit(it);
       if (u < 0) break;
-      const AttnUnit w = load_unit(a, u);
+      const AttnUnit w = load_unit<EXTRAS>(a, u);
       if (((w.active >> t) & 1) == 0) continue;
       float m_run = -INFINITY, l_run = 0.f;
 
@@ -472,7 +475,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
           for (int i = 0; i < ATT_BN; ++i)
             if (i >= n_valid) s[i] = -INFINITY;
         }
-        if (ATT_EXTRAS && (a.causal != 0 || a.rel_bias != nullptr)) {
+        if (EXTRAS == 2 && (a.causal != 0 || a.rel_bias != nullptr)) {
           // text-encoder variants: T5 relative position bias and / or CLIP's causal mask
           const int qpos = w.q_pos0 + t * ATT_BM + r;
           const int kpos0 = inA ? j * ATT_BN : w.ka_len + (j - w.nA) * ATT_BN;
@@ -650,6 +653,7 @@ extern "C" long long* b200_attn_debug_buffer(void) { return g_att_dbg; }
 #endif
 
 extern "C" int b200_attn_rows_per_item(void) { return ATT_NQ * ATT_BM; }
+extern "C" long long b200_attn_workspace_bytes(void) { return 2 * sizeof(int32_t); }  // sched_state
 
 // Host-side work list of the persistent kernel. Units = (query block of ATT_NQ tiles, head),
 // sorted longest first by the softmax time the kernel is bound by: key steps x max(active tiles x
@@ -754,27 +758,20 @@ extern "C" int b200_attn_varlen_ex(const B200AttnSource* src_a, const B200AttnSo
     g_att_dbg = dbg_buf;
   }
 #endif
+  const int extras = (a.causal != 0 || a.rel_bias != nullptr) ? 2 : (a.q_mask != nullptr ? 1 : 0);
+  auto kern = extras == 2 ? attn_fwd_kernel<2> : (extras == 1 ? attn_fwd_kernel<1> : attn_fwd_kernel<0>);
   static bool configured = false;
   if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    cudaError_t err = cudaFuncSetAttribute(attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
     if (err != cudaSuccess) return static_cast<int>(err);
     configured = true;
   }
-#ifdef ATT_TIMING
-  {
-    cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, attn_fwd_kernel);
-    static bool once = false;
-    if (!once) {
-      once = true;
-      printf("attn attrs: maxThreadsPerBlock=%d numRegs=%d sharedStatic=%zu maxDyn=%d local=%zu\n",
-             fa.maxThreadsPerBlock, fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes,
-             fa.localSizeBytes);
-    }
-  }
-#endif
   dim3 grid(n_ctas);
-  return launch_pdl(attn_fwd_kernel, grid, dim3(ATT_THREADS), ATT_SMEM,
+  return launch_pdl(kern, grid, dim3(ATT_THREADS), ATT_SMEM,
                     reinterpret_cast<cudaStream_t>(stream_), tm[0][0], tm[1][0], tm[0][1], tm[1][1],
                     tm[0][2], tm[1][2], a);
 }

@@ -19,7 +19,7 @@
 
 namespace b200 {
 
-constexpr int PC_SPLIT = 4;      // CTAs per patch (each owns rows/4 of it)
+constexpr int PC_SPLIT = 16;     // CTAs per patch (each owns rows/16 of it): 16 x patches CTAs stream the tensor
 constexpr int PC_THREADS = 256;
 
 struct ForestDev {

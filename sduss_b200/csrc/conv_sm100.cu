@@ -300,6 +300,8 @@ using namespace b200;
 // Encodes one input tensor map per latent into `maps_host` (host memory, n_latents entries of
 // 128 bytes); the caller uploads them to a 64-byte-aligned device buffer once per batch
 // composition. in_desc: int32 [n][4] = {input row offset, Hin, Win, 0}.
+extern "C" long long b200_conv3x3_maps_bytes(int n_latents) { return (long long)n_latents * 128; }
+
 extern "C" int b200_conv3x3_encode_maps(const void* x, int ldx, int Cin, const int32_t* in_desc_host,
                                         int n_latents, int stride, void* maps_host) {
   if (!x || !in_desc_host || !maps_host || n_latents <= 0 || (Cin & 7) || (ldx & 7) ||

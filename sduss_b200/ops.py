@@ -355,7 +355,7 @@ def build_attn_plan(seqs, device, n_heads, max_ctas=None):
                                        units.ctypes.data, ctypes.byref(n_units)),
           "b200_attn_build_schedule")
     return (torch.from_numpy(table).to(device), torch.from_numpy(units).to(device), n_units.value,
-            torch.zeros(2, dtype=torch.int32, device=device),
+            torch.zeros(lib.b200_attn_workspace_bytes() // 4, dtype=torch.int32, device=device),
             attn_max_ctas() if max_ctas is None else max_ctas)
 
 
@@ -415,6 +415,12 @@ class DeviceForest:
                 v = t.value[n][0]
                 value.append(float(v[one] / v.sum()) if one is not None else 0.0)
         return cls(feature, threshold, left, right, value, roots, device)
+
+    @classmethod
+    def from_npz(cls, path, device):
+        """A forest stored flattened (tools/patch_cache_study.py writes sduss_b200/data/patch_cache_*.npz)."""
+        z = np.load(path)
+        return cls(z["feature"], z["threshold"], z["left"], z["right"], z["value"], z["roots"], device)
 
     @classmethod
     def threshold_rule(cls, tau, device):
@@ -612,7 +618,7 @@ def conv3x3_encode_maps(x, cin, in_desc_host, stride):
     buffer holding n CUtensorMaps (64-byte aligned)."""
     _req(x)
     n = in_desc_host.shape[0]
-    host = np.zeros(n * 128, dtype=np.uint8)
+    host = np.zeros(lib.b200_conv3x3_maps_bytes(n), dtype=np.uint8)
     desc = np.ascontiguousarray(in_desc_host, dtype=np.int32)
     check(lib.b200_conv3x3_encode_maps(_ptr(x), x.stride(0), cin,
                                        desc.ctypes.data_as(ctypes.c_void_p), n, stride,

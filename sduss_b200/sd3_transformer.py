@@ -293,9 +293,13 @@ class B200SD3Transformer2DModel(torch.nn.Module):
         import collections
         self.patch_forest, self.patch_refresh = forest, refresh
         self._cache_lru, self._cache_max = collections.OrderedDict(), max_cached_plans
-        if forest is None:
-            for pl in self._plans.values():
-                pl.cached_state = pl.cache = None
+        for pl in self._plans.values():
+            # captured graphs of the cached forward hold the previous forest's device pointers
+            pl.cached_state = _CachedState() if (forest is not None and pl.cache is not None) else None
+            if forest is None:
+                pl.cache = None
+            elif pl.cache is not None:
+                self._cache_lru[id(pl)] = pl
 
     def patch_cache_enabled(self):
         return getattr(self, "patch_forest", None) is not None

@@ -26,7 +26,8 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_ctypes_signatures_cover_header():
     from sduss_b200 import _lib
     declared = set(_header_functions())
-    bound = set(_lib.SIGNATURES) | {"b200_groupnorm_workspace_bytes", "b200_patch_mask_workspace_bytes"}
+    bound = set(_lib.SIGNATURES) | {"b200_groupnorm_workspace_bytes", "b200_patch_mask_workspace_bytes",
+                                    "b200_attn_workspace_bytes", "b200_conv3x3_maps_bytes"}
     assert declared == bound, declared ^ bound
 
 
@@ -46,6 +47,8 @@ def test_invalid_arguments_are_rejected_without_a_device():
     assert lib.b200_gemm_bf16(None, 0, None, 0, 0, 0, 0, 0, None, None) == _lib.ERR_INVALID
     assert lib.b200_silu_bf16(None, None, 8, None) == _lib.ERR_INVALID
     assert lib.b200_groupnorm_workspace_bytes(128, 2) == 2 * 32 * 2 * 4 + 2 * 32 * 2 * 4
+    assert lib.b200_attn_workspace_bytes() == 8 and lib.b200_conv3x3_maps_bytes(3) == 384
+    assert lib.b200_patch_mask_workspace_bytes(10) == 10 * (16 * 4 + 4)
 
 
 def test_product_never_imports_oracle():
