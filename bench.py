@@ -468,7 +468,7 @@ def main():
                     help="both = SD3.5-medium headline (BASELINE configs[1]) + `sdxl` sub-record (configs[0] shape)")
     ap.add_argument("--serve", action="store_true", help="serving replay instead of the step bench")
     ap.add_argument("--no-serve", action="store_true", help="skip the `serve` sub-records of the step bench")
-    ap.add_argument("--serve-requests", type=int, default=36, help="requests per GPU of the `serve` sub-records")
+    ap.add_argument("--serve-requests", type=int, default=48, help="requests per GPU of the `serve` sub-records")
     ap.add_argument("--qps", type=float, default=0.0, help="--serve: offered requests/s per GPU (default 4)")
     ap.add_argument("--requests", type=int, default=0, help="--serve: requests per GPU (default 48)")
     args = ap.parse_args()

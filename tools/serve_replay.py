@@ -136,7 +136,7 @@ def serve_run(kind, worker, trace, rank, world, dist, tag):
     proc = psutil.Process()
     cpu0 = proc.cpu_times()
     plans0, n_steps, batch_sizes = worker.n_plans(), 0, []
-    running, lat, scanned, mine_done, finish_t = [], [], 0, 0, t0
+    running, lat, done_at, scanned, mine_done, finish_t = [], [], [], 0, 0, t0
     waiting = []
     while True:
         # newly dispatched requests, in arrival order
@@ -172,6 +172,7 @@ def serve_run(kind, worker, trace, rank, world, dist, tag):
             for res, v in fin.items():
                 for i, _ in v:
                     lat.append(now - (t0 + trace[i][0]))
+                    done_at.append(now - t0)
                     board.report_finished(rank, int(res))
                     mine_done += 1
             finish_t = now
@@ -181,7 +182,7 @@ def serve_run(kind, worker, trace, rank, world, dist, tag):
     cpu1 = proc.cpu_times()
     wall_rank = finish_t - t0
     host_cpu = psutil.cpu_percent(None)
-    rec = {"rank": rank, "served": mine_done, "wall_s": wall_rank, "lat": lat, "steps": n_steps,
+    rec = {"rank": rank, "served": mine_done, "wall_s": wall_rank, "lat": lat, "done_at": done_at, "steps": n_steps,
            "mean_batch": float(np.mean(batch_sizes)) if batch_sizes else 0.0,
            "new_plans": worker.n_plans() - plans0,
            "proc_cpu_s": (cpu1.user + cpu1.system) - (cpu0.user + cpu0.system), "host_cpu_percent": host_cpu}
@@ -199,7 +200,11 @@ def serve_run(kind, worker, trace, rank, world, dist, tag):
     wall = max(r["wall_s"] for r in allrec)
     lats = np.asarray([x for r in allrec for x in r["lat"]])
     offered = n_req / trace[-1][0]
-    return {"req_s": n_req / wall, "offered_req_s": offered, "requests": n_req, "steps_per_request": steps,
+    # steady state: completions between the 20th and the 80th percentile (ramp-up and drain excluded)
+    done = np.sort(np.asarray([x for r in allrec for x in r["done_at"]]))
+    lo, hi = int(0.2 * len(done)), int(0.8 * len(done))
+    steady = (hi - lo) / (done[hi] - done[lo]) if hi > lo and done[hi] > done[lo] else n_req / wall
+    return {"req_s": n_req / wall, "steady_req_s": float(steady), "offered_req_s": offered, "requests": n_req, "steps_per_request": steps,
             "wall_s": wall, "latency_s": {"mean": float(lats.mean()), "p50": float(np.percentile(lats, 50)),
                                           "p99": float(np.percentile(lats, 99))},
             "batch_steps_per_s": sum(r["steps"] for r in allrec) / wall,
