@@ -77,6 +77,10 @@ typedef struct B200EpilogueDesc {
   const int32_t* row_mask; /* patch cache, may be NULL: device int32 per chunk   */
   int32_t row_mask_shift;  /* of 2^shift rows (shift >= 8); M tiles of a chunk whose entry is 0   */
                            /* are skipped: no loads, no MMA, their rows of C stay as they are     */
+  float* stats_out;        /* b200_conv3x3_bf16 only, may be NULL: [n_mtiles * 2][Cout][2] fp32,  */
+                           /* per (16x8 output tile, row half, channel) the (sum, sum of squares) */
+                           /* of the stored bf16 outputs: the statistics pass of the GroupNorm    */
+                           /* that follows (b200_groupnorm_from_conv_stats), fused                */
 } B200EpilogueDesc;
 
 /* A: [M, lda] bf16, W: [N, ldw] bf16 (K contiguous in both). N, K, lda, ldw, ldc multiples
@@ -269,6 +273,15 @@ int b200_groupnorm_nhwc_bf16(const void* x, int ldx, long long T, int C, int gro
                              const void* gamma, const void* beta, const int32_t* row_group,
                              const int32_t* lat_chunks, int n_latents, int silu, void* y, int ldy,
                              void* workspace, void* stream);
+
+/* The same GroupNorm when the tensor was written by b200_conv3x3_bf16 with ep->stats_out set: the
+ * per-tile partial sums replace the statistics pass, so x is read once (finalize + apply).
+ * lat_tiles: int32 [n][4] = {first tile of the latent in the conv's tile list, its tiles, its
+ * pixels, 0}. Same workspace as b200_groupnorm_nhwc_bf16. */
+int b200_groupnorm_from_conv_stats(const void* x, int ldx, long long T, int C, int groups, float eps,
+                                   const void* gamma, const void* beta, const int32_t* row_group,
+                                   const float* conv_stats, const int32_t* lat_tiles, int n_latents,
+                                   int silu, void* y, int ldy, void* workspace, void* stream);
 
 /* SDXL pack: NCHW latents -> im2col rows of the 3x3/pad-1 conv_in (K = 9*C padded to ldo with
  * zeros): out[row_i + y*W + x, c*9 + ky*3 + kx]. Replaces split_sample's haloed windows

@@ -35,6 +35,7 @@ class EpilogueDesc(ctypes.Structure):
         ("rms_eps", c_float), ("q_scale", c_float),
         ("act", ctypes.c_int32),
         ("row_mask", c_void_p), ("row_mask_shift", ctypes.c_int32),
+        ("stats_out", c_void_p),
     ]
 
 
@@ -130,6 +131,9 @@ SIGNATURES = {
     "b200_groupnorm_nhwc_bf16": [c_void_p, c_int, ctypes.c_longlong, c_int, c_int, c_float,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                  c_int, c_void_p, c_void_p],
+    "b200_groupnorm_from_conv_stats": [c_void_p, c_int, ctypes.c_longlong, c_int, c_int, c_float,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                       c_void_p, c_int, c_void_p, c_void_p],
     "b200_pack_im2col3x3": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
     "b200_scatter_nchw": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "b200_upsample2x_nhwc": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,

@@ -244,6 +244,32 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
             tma_store_3d(a.out_maps + tl.x, stageC + b * EPI_STAGE_BYTES, nc, tl.z, tl.y);
             tma_store_commit();
           }
+          if (e.stats_out != nullptr) {
+            // GroupNorm statistics of the tensor being written, produced here instead of by a second
+            // pass over it: thread (half, col) sums column col of the staged bf16 tile over its 64
+            // rows in a fixed order (rows outside the latent excluded). Partials go to fixed slots
+            // [(tile, half)][channel]; the finalize kernel reduces them in a fixed order, so the
+            // result depends on the latent alone (batch invariance, determinism).
+            const int tid = int(threadIdx.x) - 128;
+            const int col = tid & 63, half = tid >> 6;
+            if (nc + col < a.Cout) {
+              const uint8_t* st = stageC + b * EPI_STAGE_BYTES;
+              float sm = 0.f, sq = 0.f;
+#pragma unroll 8
+              for (int rr = half * 64; rr < half * 64 + 64; ++rr) {
+                if (tl.y + rr / CV_TW < ld.y && tl.z + rr % CV_TW < ld.z) {
+                  const float f = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(
+                      st + sw128_off(rr, col >> 3) + (col & 7) * 2));
+                  sm += f;
+                  sq = fmaf(f, f, sq);
+                }
+              }
+              e.stats_out[(size_t(m0 + mt) * 2 + half) * a.Cout + nc + col] = make_float2(sm, sq);
+            }
+            // the leader refills this staging tile with a residual chunk at the top of the next
+            // iteration: every column reader must be done first
+            if (has_resid) named_barrier<1, 128>();
+          }
         }
         {
           const int left = (a.Cout - n0 + 63) / 64;
@@ -365,6 +391,7 @@ extern "C" int b200_conv3x3_bf16(const void* in_maps_dev, const void* out_maps_d
   e.rowvec = static_cast<const __nv_bfloat16*>(ep->rowvec); e.ldv = ep->ldv;
   e.rms_wq = nullptr; e.rms_wk = nullptr; e.rms_q_cols = 0; e.rms_k_cols = 0;
   e.rms_eps = 0.f; e.q_scale = 1.f; e.act = 0; e.row_mask = nullptr; e.row_mask_shift = 0;
+  e.stats_out = reinterpret_cast<float2*>(ep->stats_out);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   if (bn256) return dispatch_conv<256, 1>(epi_mode, tmW, a, e, M_total, sms, st);
   // 128-wide tiles with several rounds of tile pairs: two M tiles per CTA share each weight tile

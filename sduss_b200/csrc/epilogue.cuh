@@ -37,6 +37,8 @@ struct EpiArgs {
                                // default (tanh-GELU / erf-GELU), 1 tanh-GELU, 2 erf-GELU, 3 quick-GELU
   const int* row_mask;         // patch cache: M tiles of chunk (m0 >> row_mask_shift) with mask 0 are
   int row_mask_shift;          // skipped entirely (no loads, no MMA, C untouched); null = all tiles
+  float2* stats_out;           // conv only: per (M tile, row half, channel) (sum, sum of squares) of the
+                               // STORED bf16 outputs, for the GroupNorm that follows; null = off
 };
 
 // true when the M tile starting at row m0 belongs to a clean patch (kept as it is)

@@ -382,6 +382,7 @@ extern "C" int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
   e.act = ep->act;
   e.row_mask = ep->row_mask;
   e.row_mask_shift = ep->row_mask_shift;
+  e.stats_out = nullptr;  // produced by the convolution kernel only
   if (ep->row_mask && ep->row_mask_shift < 8) return B200_ERR_INVALID;  // a CTA pair covers 256 rows
   GemmShape s{M, N, K};
   // output / residual tensor maps of the staged epilogue (bf16 outputs only)

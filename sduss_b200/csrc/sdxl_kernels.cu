@@ -168,6 +168,48 @@ __global__ void gn_finalize_kernel(const float* partial, const int4* lat, int L,
   }
 }
 
+// Finalize from the statistics the producing convolution left behind (conv_sm100.cu, stats_out):
+// part: [n_mtiles * 2][C] float2 per (16x8-pixel tile, row half, channel). One CTA per (latent,
+// group): thread t adds the entries t, t + 256, ... of the latent's tiles x halves x the group's
+// channels in fp64, then a fixed shared-memory tree. lat_tiles: [L][4] = {first tile, tiles, pixels, 0}.
+__global__ void __launch_bounds__(256) gn_finalize_tiles_kernel(const float2* part, const int4* lat_tiles,
+                                                                int G, int cpg, int C, float eps,
+                                                                float* stats) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int l = blockIdx.x / G, g = blockIdx.x % G;
+  const int4 d = lat_tiles[l];
+  const long n_entries = long(d.y) * 2 * cpg;
+  const float2* base = part + size_t(d.x) * 2 * C + g * cpg;
+  double s = 0.0, q = 0.0;
+  for (long i = threadIdx.x; i < n_entries; i += 256) {
+    const long slot = i / cpg;
+    const int ch = int(i - slot * cpg);
+    const float2 v = base[slot * C + ch];
+    s += double(v.x);
+    q += double(v.y);
+  }
+  __shared__ double rs[256], rq[256];
+  rs[threadIdx.x] = s;
+  rq[threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      rs[threadIdx.x] += rs[threadIdx.x + o];
+      rq[threadIdx.x] += rq[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double n = double(d.z) * cpg;
+    const double mean = rs[0] / n;
+    double var = rq[0] / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[(size_t(l) * G + g) * 2] = float(mean);
+    stats[(size_t(l) * G + g) * 2 + 1] = float(1.0 / sqrt(var + double(eps)));
+  }
+}
+
 // SiLU as h + h * tanh(h), h = v / 2: one MUFU op per element instead of ex2 + rcp (+ the Newton
 // steps of an IEEE division); tanh.approx is accurate to 2^-11, below the bf16 rounding of y.
 // Chunks are walked from the END of the tensor (CTA 0 takes the last one): the statistics pass
@@ -364,6 +406,33 @@ extern "C" int b200_groupnorm_nhwc_bf16(const void* x, int ldx, long long T, int
   rc = launch_pdl(gn_finalize_kernel, dim3((n_latents * groups + 3) / 4), dim3(128), 0, ST(stream),
                   static_cast<const float*>(partial), reinterpret_cast<const int4*>(lat_chunks),
                   n_latents, groups, cpg, chunks, eps, stats);
+  if (rc) return rc;
+  auto kern = silu ? gn_apply_kernel<true> : gn_apply_kernel<false>;
+  return launch_pdl(kern, dim3(chunks, m.S), dim3(m.threads), 0, ST(stream),
+                    static_cast<const bf16*>(x), ldx, m.W, m.RL, cpg, groups, chunks,
+                    static_cast<const float*>(stats), row_group, static_cast<const bf16*>(gamma),
+                    static_cast<const bf16*>(beta), static_cast<bf16*>(y), ldy);
+}
+
+// GroupNorm whose statistics the producing convolution already computed (b200_conv3x3_bf16 with
+// ep->stats_out): finalize over the latent's tile partials + the apply pass -- x is read ONCE.
+extern "C" int b200_groupnorm_from_conv_stats(const void* x, int ldx, long long T, int C, int groups,
+                                              float eps, const void* gamma, const void* beta,
+                                              const int32_t* row_group, const float* conv_stats,
+                                              const int32_t* lat_tiles, int n_latents, int silu,
+                                              void* y, int ldy, void* workspace, void* stream) {
+  if (!x || !y || !gamma || !beta || !row_group || !conv_stats || !lat_tiles || !workspace || T <= 0 ||
+      (T % GN_CHUNK) || groups <= 0 || groups > GN_MAXG || (C % groups) || (C & 7) || C > GN_MAXC ||
+      (ldx & 7) || (ldy & 7) || n_latents <= 0)
+    return B200_ERR_INVALID;
+  const int cpg = C / groups;
+  const int chunks = int(T / GN_CHUNK);
+  const GnMap m = gn_map(C, groups);
+  if (m.RL < 1) return B200_ERR_INVALID;
+  float* stats = static_cast<float*>(workspace) + size_t(chunks) * GN_MAXG * 2;  // same slot as the 3-launch path
+  int rc = launch_pdl(gn_finalize_tiles_kernel, dim3(n_latents * groups), dim3(256), 0, ST(stream),
+                      reinterpret_cast<const float2*>(conv_stats), reinterpret_cast<const int4*>(lat_tiles),
+                      groups, cpg, C, eps, stats);
   if (rc) return rc;
   auto kern = silu ? gn_apply_kernel<true> : gn_apply_kernel<false>;
   return launch_pdl(kern, dim3(chunks, m.S), dim3(m.threads), 0, ST(stream),

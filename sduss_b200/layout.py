@@ -26,10 +26,15 @@ class LevelLayout:
         assert all(r % 64 == 0 for r in rows), "GroupNorm chunks need pixel counts multiple of 64"
         chunks = np.asarray([(self.row_off[i] // 64, rows[i] // 64, 0, 0) for i in range(self.L)], np.int32)
         self.lat_chunks = torch.from_numpy(chunks).to(device)
-        tiles = []
+        tiles, lat_tiles = [], []
         for i, (h, w) in enumerate(sizes):
+            first = len(tiles)
             for y0 in range(0, h, 16):
                 for x0 in range(0, w, 8):
                     tiles.append((i, y0, x0, 0))
+            lat_tiles.append((first, len(tiles) - first, h * w, 0))
         self.n_tiles = len(tiles)
         self.tiles = torch.from_numpy(np.asarray(tiles, np.int32)).to(device)
+        # per latent: {first conv tile, tiles, pixels}: where the convolution epilogue leaves the
+        # per-tile GroupNorm partial sums of this latent (b200_groupnorm_from_conv_stats)
+        self.lat_tiles = torch.from_numpy(np.asarray(lat_tiles, np.int32)).to(device)

@@ -632,11 +632,14 @@ def conv3x3_encode_maps(x, cin, in_desc_host, stride):
 
 
 def conv3x3(maps_dev, tiles, n_mtiles, out_lat, cin, cout, stride, weight, out, *, out_maps,
-            resid_maps=None, epi=EPI_BIAS, bias=None, rowvec=None, row_group=None):
+            resid_maps=None, epi=EPI_BIAS, bias=None, rowvec=None, row_group=None, stats_out=None):
     """out[M_total, cout] = conv3x3(x) through the implicit-GEMM kernel (see conv_sm100.cu).
     out_maps / resid_maps: conv3x3_encode_maps(out or resid buffer, cout, out_desc_host, 1)."""
     _req(weight), _req(out)
     d = _epi_desc(out, bias=bias, rowvec=rowvec, row_group=row_group)
+    if stats_out is not None:  # per (tile, half, channel) sums for the GroupNorm that follows
+        assert stats_out.dtype == torch.float32 and stats_out.numel() >= n_mtiles * 2 * cout * 2
+        d.stats_out = _ptr(stats_out)
     _ev = _count("b200_conv3x3_bf16", (out.shape[0], cout, 9 * cin, stride))
     check(lib.b200_conv3x3_bf16(_ptr(maps_dev), _ptr(out_maps), _ptr(resid_maps), _ptr(tiles),
                                 n_mtiles, _ptr(out_lat), cin, cout,
@@ -662,6 +665,42 @@ def groupnorm_nhwc(x, y, gamma, beta, row_group, lat_chunks, n_latents, workspac
                                        _ptr(gamma), _ptr(beta), _ptr(row_group), _ptr(lat_chunks),
                                        n_latents, int(silu), _ptr(y), y.stride(0),
                                        _ptr(workspace), _stream()), "b200_groupnorm_nhwc_bf16")
+    if _ev is not None:
+        _ev.record()
+    return y
+
+
+def conv_stats_buffer(pl, out, level, n_tiles, cout):
+    """The fp32 buffer [n_tiles * 2, cout, 2] a convolution writing `out` leaves its per-tile GroupNorm
+    partial sums in (one per (level, cout) of the plan, from its arena), tagged so that a GroupNorm
+    reading `out` next can tell the statistics are those of `out`'s current contents."""
+    name = f"convstats{level}_{cout}"
+    t = pl.bufs.get(name)
+    if t is None:
+        t = pl.bufs[name] = pl.arena.alloc(pl, (n_tiles * 2 * cout * 2,), torch.float32)
+    gen = pl.stats_gen[name] = pl.stats_gen.get(name, 0) + 1
+    pl.stats_tag[out.data_ptr()] = (name, gen, cout)
+    return t
+
+
+def fresh_conv_stats(pl, x):
+    """The statistics buffer of the convolution that last wrote x, if nothing has reused it since."""
+    tag = pl.stats_tag.get(x.data_ptr())
+    if tag is None or pl.stats_gen.get(tag[0]) != tag[1] or tag[2] != x.shape[1]:
+        return None
+    return pl.bufs[tag[0]]
+
+
+def groupnorm_from_conv_stats(x, y, gamma, beta, row_group, conv_stats, lat_tiles, n_latents, workspace, *,
+                              groups=32, eps=1e-5, silu=False):
+    """GroupNorm of a tensor b200_conv3x3_bf16 has just written with stats_out: one read of x."""
+    _req(x), _req(y)
+    T, C = x.shape
+    _ev = _count("b200_groupnorm_nhwc_bf16")
+    check(lib.b200_groupnorm_from_conv_stats(_ptr(x), x.stride(0), T, C, groups, ctypes.c_float(eps),
+                                             _ptr(gamma), _ptr(beta), _ptr(row_group), _ptr(conv_stats),
+                                             _ptr(lat_tiles), n_latents, int(silu), _ptr(y), y.stride(0),
+                                             _ptr(workspace), _stream()), "b200_groupnorm_from_conv_stats")
     if _ev is not None:
         _ev.record()
     return y

@@ -300,3 +300,95 @@ def vae_decode_flops(cfg, h, w):
             px *= 4
             fl += 2.0 * 9 * c * c * px
     return fl + 2.0 * 9 * ch[-1] * cfg.out_channels * px
+
+
+# ---------------------------------------------------------------------------------------
+# Prepare stage stand-ins: random-init text encoders under transformers' state-dict names (generated
+# on the device: T5-XXL is 4.7 B parameters) and a deterministic tokenizer (the real vocabularies are
+# not in the image). Shapes are the public model configs of the encoders SD3.5 / SDXL ship with.
+# ---------------------------------------------------------------------------------------
+CLIP_L = dict(hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12,
+              hidden_act="quick_gelu", projection_dim=768, vocab_size=49408, max_position_embeddings=77,
+              layer_norm_eps=1e-5, eos_token_id=49407)
+CLIP_G = dict(hidden_size=1280, intermediate_size=5120, num_hidden_layers=32, num_attention_heads=20,
+              hidden_act="gelu", projection_dim=1280, vocab_size=49408, max_position_embeddings=77,
+              layer_norm_eps=1e-5, eos_token_id=49407)
+T5_XXL = dict(d_model=4096, d_kv=64, d_ff=10240, num_layers=24, num_heads=64, vocab_size=32128,
+              feed_forward_proj="gated-gelu", relative_attention_num_buckets=32,
+              relative_attention_max_distance=128, layer_norm_epsilon=1e-6)
+
+
+def random_clip_state_dict(cfg, device, seed=0, dtype=torch.bfloat16):
+    g = torch.Generator(device=device).manual_seed(seed)
+    D, F, P = cfg["hidden_size"], cfg["intermediate_size"], cfg["projection_dim"]
+    sd, p = {}, "text_model."
+    rn = lambda *s, std=0.02: (torch.randn(*s, generator=g, device=device) * std).to(dtype)
+    sd[p + "embeddings.token_embedding.weight"] = rn(cfg["vocab_size"], D)
+    sd[p + "embeddings.position_embedding.weight"] = rn(cfg["max_position_embeddings"], D, std=0.01)
+    for i in range(cfg["num_hidden_layers"]):
+        b = f"{p}encoder.layers.{i}."
+        for n in ("q", "k", "v", "out"):
+            sd[f"{b}self_attn.{n}_proj.weight"] = rn(D, D, std=D ** -0.5)
+            sd[f"{b}self_attn.{n}_proj.bias"] = rn(D)
+        for n in ("layer_norm1", "layer_norm2"):
+            sd[f"{b}{n}.weight"] = (1 + 0.1 * torch.randn(D, generator=g, device=device)).to(dtype)
+            sd[f"{b}{n}.bias"] = rn(D)
+        sd[b + "mlp.fc1.weight"], sd[b + "mlp.fc1.bias"] = rn(F, D, std=D ** -0.5), rn(F)
+        sd[b + "mlp.fc2.weight"], sd[b + "mlp.fc2.bias"] = rn(D, F, std=F ** -0.5), rn(D)
+    sd[p + "final_layer_norm.weight"] = (1 + 0.1 * torch.randn(D, generator=g, device=device)).to(dtype)
+    sd[p + "final_layer_norm.bias"] = rn(D)
+    sd["text_projection.weight"] = rn(P, D, std=D ** -0.5)
+    return sd
+
+
+def random_t5_state_dict(cfg, device, seed=0, dtype=torch.bfloat16):
+    g = torch.Generator(device=device).manual_seed(seed)
+    D, I, F = cfg["d_model"], cfg["num_heads"] * cfg["d_kv"], cfg["d_ff"]
+    rn = lambda *s, std=0.02: (torch.randn(*s, generator=g, device=device) * std).to(dtype)
+    sd = {"encoder.embed_tokens.weight": rn(cfg["vocab_size"], D, std=1.0)}
+    for i in range(cfg["num_layers"]):
+        b = f"encoder.block.{i}.layer."
+        for n in "qkv":
+            sd[f"{b}0.SelfAttention.{n}.weight"] = rn(I, D, std=(D * (cfg["d_kv"] if n == "q" else 1)) ** -0.5)
+        sd[b + "0.SelfAttention.o.weight"] = rn(D, I, std=I ** -0.5)
+        sd[b + "0.layer_norm.weight"] = torch.ones(D, device=device, dtype=dtype)
+        sd[b + "1.layer_norm.weight"] = torch.ones(D, device=device, dtype=dtype)
+        sd[b + "1.DenseReluDense.wi_0.weight"] = rn(F, D, std=D ** -0.5)
+        sd[b + "1.DenseReluDense.wi_1.weight"] = rn(F, D, std=D ** -0.5)
+        sd[b + "1.DenseReluDense.wo.weight"] = rn(D, F, std=F ** -0.5)
+    sd["encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"] = rn(
+        cfg["relative_attention_num_buckets"], cfg["num_heads"], std=0.5)
+    sd["encoder.final_layer_norm.weight"] = torch.ones(D, device=device, dtype=dtype)
+    return sd
+
+
+class HashTokenizer:
+    """Deterministic stand-in with the transformers tokenizer call signature: words hash to ids,
+    BOS / EOS framing, EOS (CLIP) or 0 (T5) padding to max_length."""
+
+    def __init__(self, vocab_size, bos=None, eos=1, pad=0):
+        self.vocab_size, self.bos, self.eos, self.pad = vocab_size, bos, eos, pad
+
+    def __call__(self, prompts, padding="max_length", max_length=77, truncation=True, return_tensors="pt"):
+        span = self.vocab_size - 16
+        rows = []
+        for p in prompts:
+            ids = ([self.bos] if self.bos is not None else []) + \
+                  [3 + (sum(ord(c) * (i + 1) for i, c in enumerate(w)) % span) for w in p.split()]
+            ids = ids[:max_length - 1] + [self.eos]
+            rows.append(ids + [self.pad] * (max_length - len(ids)))
+        return {"input_ids": torch.tensor(rows)}
+
+
+def make_prompt_encoder(kind, device, seed=0):
+    """B200PromptEncoder with random-init CLIP-L / CLIP-G (/ T5-XXL) + the matching HashTokenizers."""
+    from .text_encoders import B200CLIPTextEncoder, B200PromptEncoder, B200T5Encoder
+    cl = B200CLIPTextEncoder(random_clip_state_dict(CLIP_L, device, seed), CLIP_L, device=device)
+    cg = B200CLIPTextEncoder(random_clip_state_dict(CLIP_G, device, seed + 1), CLIP_G, device=device)
+    toks = [HashTokenizer(CLIP_L["vocab_size"], bos=49406, eos=49407, pad=49407),
+            HashTokenizer(CLIP_G["vocab_size"], bos=49406, eos=49407, pad=49407)]
+    t5 = None
+    if kind == "sd3":
+        t5 = B200T5Encoder(random_t5_state_dict(T5_XXL, device, seed + 2), T5_XXL, device=device)
+        toks.append(HashTokenizer(T5_XXL["vocab_size"], bos=None, eos=1, pad=0))
+    return B200PromptEncoder(kind, cl, cg, t5), toks

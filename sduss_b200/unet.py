@@ -105,6 +105,7 @@ class _Plan:
         self.arena, self.block, self.arena_off = model.arena, None, 0
         self.bufs: Dict[str, torch.Tensor] = {}
         self.maps: Dict[tuple, torch.Tensor] = {}
+        self.stats_tag, self.stats_gen = {}, {}   # conv-epilogue GroupNorm statistics (ops.conv_stats_buffer)
         self.attn_src: Dict[tuple, object] = {}
         self.t32 = torch.empty((L,), device=dev, dtype=torch.float32)
         self.ids32 = torch.empty((L * 6,), device=dev, dtype=torch.float32)
@@ -124,6 +125,7 @@ class _Plan:
     def reset_workspaces(self):
         """Forget every arena view and everything that captured its address (ops._run_eager)."""
         self.bufs, self.maps, self.block, self.arena_off = {}, {}, None, 0
+        self.stats_tag, self.stats_gen = {}, {}
         if hasattr(self, "attn_src"):
             self.attn_src = {}
 
@@ -272,9 +274,13 @@ class B200UNet(torch.nn.Module):
     # ------------------------------------------------------------------ building blocks
     def _gn(self, pl, x, name, level, out, silu, eps=None):
         lay = pl.levels[level]
+        kw = dict(groups=self.cfg.norm_num_groups, eps=self.cfg.norm_eps if eps is None else eps, silu=silu)
+        stats = ops.fresh_conv_stats(pl, x)
+        if stats is not None:  # the convolution that wrote x left its statistics: x is read once
+            return ops.groupnorm_from_conv_stats(x, out, self.w[name + ".weight"], self.w[name + ".bias"],
+                                                 lay.row_group, stats, lay.lat_tiles, lay.L, pl.gn_ws, **kw)
         ops.groupnorm_nhwc(x, out, self.w[name + ".weight"], self.w[name + ".bias"], lay.row_group,
-                           lay.lat_chunks, lay.L, pl.gn_ws, groups=self.cfg.norm_num_groups,
-                           eps=self.cfg.norm_eps if eps is None else eps, silu=silu)
+                           lay.lat_chunks, lay.L, pl.gn_ws, **kw)
         return out
 
     def _conv(self, pl, x, cin, name, in_level, stride, out, resid=None, **epi):
@@ -285,8 +291,12 @@ class B200UNet(torch.nn.Module):
         maps = pl.conv_maps(x, cin, in_level, stride)
         out_maps = pl.conv_maps(out, cout, out_level, 1)
         resid_maps = pl.conv_maps(resid, cout, out_level, 1) if resid is not None else None
+        # statistics of the output for the GroupNorm that usually reads it next (resnet norm2, the
+        # next resnet's norm1, a Transformer2D norm, conv_norm_out)
+        st = ops.conv_stats_buffer(pl, out, out_level, lay.n_tiles, cout) if cout % self.cfg.norm_num_groups == 0 else None
         return ops.conv3x3(maps, lay.tiles, lay.n_tiles, lay.desc, cin, cout, stride, w, out,
-                           out_maps=out_maps, resid_maps=resid_maps, bias=self.w[name + ".bias"], **epi)
+                           out_maps=out_maps, resid_maps=resid_maps, bias=self.w[name + ".bias"],
+                           stats_out=st, **epi)
 
     def _resnet(self, pl, x, name, level, temb_all):
         lay = pl.levels[level]

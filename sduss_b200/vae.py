@@ -84,6 +84,7 @@ class _Plan:
         self.arena, self.block, self.arena_off = model.arena, None, 0
         self.bufs: Dict[str, torch.Tensor] = {}
         self.maps: Dict[tuple, torch.Tensor] = {}
+        self.stats_tag, self.stats_gen = {}, {}   # conv-epilogue GroupNorm statistics (ops.conv_stats_buffer)
         self.device = dev
         self.graph = None
         self.graph_launches = 0
@@ -104,6 +105,7 @@ class _Plan:
     def reset_workspaces(self):
         """Forget every arena view and everything that captured its address (ops._run_eager)."""
         self.bufs, self.maps, self.block, self.arena_off = {}, {}, None, 0
+        self.stats_tag, self.stats_gen = {}, {}
         if hasattr(self, "attn_src"):
             self.attn_src = {}
 
@@ -214,19 +216,24 @@ class B200VAEDecoder(torch.nn.Module):
     # ------------------------------------------------------------------ building blocks
     def _gn(self, pl, x, name, level, out, silu):
         lay = pl.levels[level]
+        kw = dict(groups=self.cfg.norm_num_groups, eps=self.cfg.norm_eps, silu=silu)
+        stats = ops.fresh_conv_stats(pl, x)
+        if stats is not None:  # the convolution that wrote x left its statistics: x is read once
+            return ops.groupnorm_from_conv_stats(x, out, self.w[name + ".weight"], self.w[name + ".bias"],
+                                                 lay.row_group, stats, lay.lat_tiles, lay.L, pl.gn_ws, **kw)
         ops.groupnorm_nhwc(x, out, self.w[name + ".weight"], self.w[name + ".bias"], lay.row_group,
-                           lay.lat_chunks, lay.L, pl.gn_ws, groups=self.cfg.norm_num_groups,
-                           eps=self.cfg.norm_eps, silu=silu)
+                           lay.lat_chunks, lay.L, pl.gn_ws, **kw)
         return out
 
-    def _conv(self, pl, x, cin, name, level, out, resid=None, epi=ops.EPI_BIAS):
+    def _conv(self, pl, x, cin, name, level, out, resid=None, epi=ops.EPI_BIAS, stats=True):
         lay = pl.levels[level]
         w = self.w[name + ".weight"]
         cout = w.shape[0]
+        st = ops.conv_stats_buffer(pl, out, level, lay.n_tiles, cout) if stats and cout % self.cfg.norm_num_groups == 0 else None
         return ops.conv3x3(pl.conv_maps(x, cin, level), lay.tiles, lay.n_tiles, lay.desc, cin, cout, 1,
                            w, out, out_maps=pl.conv_maps(out, cout, level),
                            resid_maps=pl.conv_maps(resid, cout, level) if resid is not None else None,
-                           bias=self.w[name + ".bias"], epi=epi)
+                           bias=self.w[name + ".bias"], epi=epi, stats_out=st)
 
     def _resnet(self, pl, x, name, level, out_name):
         """ResnetBlock2D without time embedding (diffusers Decoder): x + conv2(act(conv1(act(x))))."""
@@ -320,7 +327,7 @@ class B200VAEDecoder(torch.nn.Module):
                 flip ^= 1
         lt = pl.levels[level]
         h = self._gn(pl, x, "decoder.conv_norm_out", level, pl.buf(f"gn{level}_{ch[-1]}", lt.T, ch[-1]), True)
-        o = self._conv(pl, h, ch[-1], "decoder.conv_out", level, pl.buf("conv_out", lt.T, self.n_out_pad))
+        o = self._conv(pl, h, ch[-1], "decoder.conv_out", level, pl.buf("conv_out", lt.T, self.n_out_pad), stats=False)
         ops.scatter_nchw(o, lt.desc, L, lt.max_pixels, cfg.out_channels, pl.out_ptr)
 
 

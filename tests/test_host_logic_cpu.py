@@ -406,7 +406,7 @@ class FakeWorker:
     # stands in for the GPU worker: a step advances every request's scheduler state and takes 2 ms
     dev = torch.device("cpu")
     def __init__(self): self.plans = set(); self.posted = []
-    def new_request(self, rid, res):
+    def admit(self, rid, res):
         return SimpleNamespace(request_id=rid, scheduler_states=SimpleNamespace(_step_index=0))
     def call(self, batch):
         self.plans.add(tuple(sorted((k, len(v)) for k, v in batch.items())))

@@ -203,3 +203,58 @@ def test_reference_patch_format_bit_exact(cuda):
         ops.concat_patches(inner, ld, pd, P, 4, 32, optr)
         for a, b in zip(outs, lats):
             assert torch.equal(a, b)  # concat(split(x)) == x
+
+
+@pytest.mark.parametrize("sizes,cin,cout,stride,epi", [
+    ([(32, 32), (64, 64)], 64, 128, 1, "bias"),                 # VAE-like: 4 channels per group
+    ([(8, 8), (16, 16), (24, 24)], 128, 320, 1, "rowvec"),      # groups straddle 64-column chunks, partial tiles
+    ([(16, 16), (48, 48)], 320, 640, 2, "bias"),                # stride 2
+    ([(64, 64), (128, 128)], 64, 320, 1, "resid"),              # residual epilogue (staging tile is refilled)
+    ([(512, 320), (16, 8)], 64, 128, 1, "resid"),               # two M tiles per CTA
+])
+def test_groupnorm_from_conv_epilogue_statistics(cuda, sizes, cin, cout, stride, epi):
+    """The convolution leaves per-(tile, half, channel) sums of its STORED outputs; GroupNorm built on
+    them (one read of the tensor) must agree with the three-launch GroupNorm on the same tensor and
+    with torch, be deterministic, and not depend on the latents packed around a latent."""
+    from sduss_b200 import ops
+    from sduss_b200.layout import LevelLayout
+    osz = [(h // stride, w // stride) for h, w in sizes]
+
+    def run(sel):
+        lats = [_rand((cin, *sizes[i]), 10 + i).bfloat16().float() for i in sel]
+        lin, lout = LevelLayout([sizes[i] for i in sel], cuda), LevelLayout([osz[i] for i in sel], cuda)
+        x = _pack(lats).cuda().bfloat16().contiguous()
+        wgt = _rand((cout, cin, 3, 3), 1, 1.0 / (3 * cin ** 0.5)).bfloat16()
+        wt = wgt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).cuda().contiguous()
+        bias = _rand((cout,), 2).cuda().bfloat16()
+        out = torch.zeros(lout.T, cout, device=cuda, dtype=torch.bfloat16)
+        stats = torch.zeros(lout.n_tiles * 2 * cout * 2, device=cuda)
+        kw = dict(out_maps=ops.conv3x3_encode_maps(out, cout, lout.desc_host, 1), bias=bias, stats_out=stats)
+        if epi == "resid":
+            resid = _pack([_rand((cout, *osz[i]), 30 + i) for i in sel]).cuda().bfloat16().contiguous()
+            kw.update(epi=ops.EPI_GATE_RESID, resid_maps=ops.conv3x3_encode_maps(resid, cout, lout.desc_host, 1))
+        elif epi == "rowvec":
+            kw.update(epi=ops.EPI_ROWVEC, rowvec=_rand((len(sizes), cout), 4).cuda().bfloat16()[sel].contiguous(),
+                      row_group=lout.row_group)
+        ops.conv3x3(ops.conv3x3_encode_maps(x, cin, lin.desc_host, stride), lout.tiles, lout.n_tiles, lout.desc,
+                    cin, cout, stride, wt, out, **kw)
+        gam, bet = (1 + 0.1 * _rand((cout,), 5)).cuda().bfloat16(), _rand((cout,), 6).cuda().bfloat16()
+        ws = ops.groupnorm_workspace(lout.T, lout.L, cuda)
+        y = torch.empty_like(out)
+        ops.groupnorm_from_conv_stats(out, y, gam, bet, lout.row_group, stats, lout.lat_tiles, lout.L, ws, silu=True)
+        y3 = torch.empty_like(out)
+        ops.groupnorm_nhwc(out, y3, gam, bet, lout.row_group, lout.lat_chunks, lout.L, ws, silu=True)
+        torch.cuda.synchronize()
+        return out, y, y3, lout, gam, bet
+
+    out, y, y3, lout, gam, bet = run(list(range(len(sizes))))
+    # same statistics up to summation order: outputs within one bf16 step of the 3-launch kernel
+    assert (y.float() - y3.float()).abs().max().item() <= 3e-2
+    ref = _pack([F.silu(F.group_norm(t[None], 32, gam.float().cpu(), bet.float().cpu(), 1e-5)[0])
+                 for t in _unpack(out.float().cpu(), lout.sizes)])
+    assert (y.float().cpu() - ref).abs().max().item() < 4e-2
+    out2, y2, _, _, _, _ = run(list(range(len(sizes))))
+    assert torch.equal(out, out2) and torch.equal(y, y2)                       # deterministic
+    last = len(sizes) - 1
+    _, ys, _, ls, _, _ = run([last])                                            # the last latent alone
+    assert torch.equal(ys, y[lout.row_off[last]:])                              # batch invariant
