@@ -260,6 +260,9 @@ class B200UNet(torch.nn.Module):
         self.arena = ops.Arena(self.device)  # per-step workspaces of all plans overlap here
         self._plans = ops.PlanCache(self.device, arena=self.arena)
         self.use_graphs = ops.graphs_enabled()
+        # GroupNorm statistics from the producing convolution's epilogue: built, parity-tested, OFF
+        # (SDXL step: convolutions +0.26 ms, GroupNorms -0.11 ms)
+        self.fuse_gn_stats = False
 
     @classmethod
     def from_diffusers(cls, model, device="cuda"):
@@ -293,7 +296,8 @@ class B200UNet(torch.nn.Module):
         resid_maps = pl.conv_maps(resid, cout, out_level, 1) if resid is not None else None
         # statistics of the output for the GroupNorm that usually reads it next (resnet norm2, the
         # next resnet's norm1, a Transformer2D norm, conv_norm_out)
-        st = ops.conv_stats_buffer(pl, out, out_level, lay.n_tiles, cout) if cout % self.cfg.norm_num_groups == 0 else None
+        st = ops.conv_stats_buffer(pl, out, out_level, lay.n_tiles, cout) \
+            if (self.fuse_gn_stats and cout % self.cfg.norm_num_groups == 0) else None
         return ops.conv3x3(maps, lay.tiles, lay.n_tiles, lay.desc, cin, cout, stride, w, out,
                            out_maps=out_maps, resid_maps=resid_maps, bias=self.w[name + ".bias"],
                            stats_out=st, **epi)

@@ -207,6 +207,11 @@ class B200VAEDecoder(torch.nn.Module):
         self.arena = ops.Arena(self.device)  # per-step workspaces of all plans overlap here
         self._plans = ops.PlanCache(self.device, arena=self.arena)
         self.use_graphs = ops.graphs_enabled()
+        # GroupNorm statistics from the producing convolution's epilogue (one read of the tensor).
+        # Built, parity-tested and OFF: measured on the decoder (profiles/r02_gn_conv_stats.txt) the
+        # column sums cost the convolutions +1.06 ms while the GroupNorms cannot save more than their
+        # statistics pass (a third of 3.8 ms): no net gain. DESIGN.md section 4.7.
+        self.fuse_gn_stats = False
 
     @classmethod
     def from_diffusers(cls, vae, device="cuda"):
@@ -229,7 +234,8 @@ class B200VAEDecoder(torch.nn.Module):
         lay = pl.levels[level]
         w = self.w[name + ".weight"]
         cout = w.shape[0]
-        st = ops.conv_stats_buffer(pl, out, level, lay.n_tiles, cout) if stats and cout % self.cfg.norm_num_groups == 0 else None
+        st = ops.conv_stats_buffer(pl, out, level, lay.n_tiles, cout) \
+            if (stats and self.fuse_gn_stats and cout % self.cfg.norm_num_groups == 0) else None
         return ops.conv3x3(pl.conv_maps(x, cin, level), lay.tiles, lay.n_tiles, lay.desc, cin, cout, 1,
                            w, out, out_maps=pl.conv_maps(out, cout, level),
                            resid_maps=pl.conv_maps(resid, cout, level) if resid is not None else None,

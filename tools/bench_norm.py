@@ -46,6 +46,10 @@ for lvl, C in ((0, 320), (0, 640), (0, 960), (1, 640), (1, 1280), (1, 1920), (2,
     ws = ops.groupnorm_workspace(lay.T, lay.L, dev)
     mk = lambda i: (lambda: ops.groupnorm_nhwc(xs[i], ys[i], g, b, lay.row_group, lay.lat_chunks, lay.L, ws, silu=True))
     report(f"groupnorm T={lay.T} C={C}", 2 * lay.T * C * 2, timeit([mk(0)]), timeit([mk(i) for i in range(nbuf)], 3 * nbuf))
+    # statistics already left by the producing convolution's epilogue: finalize + apply, one read of x
+    st = torch.ones(lay.n_tiles * 2 * C * 2, device=dev)
+    mk2 = lambda i: (lambda: ops.groupnorm_from_conv_stats(xs[i], ys[i], g, b, lay.row_group, st, lay.lat_tiles, lay.L, ws, silu=True))
+    report(f"  + stats from the conv epilogue", 2 * lay.T * C * 2, timeit([mk2(0)]), timeit([mk2(i) for i in range(nbuf)], 3 * nbuf))
 
 print("## GroupNorm + SiLU on the VAE decoder levels (512^2 + 1024^2 images: latents 64^2 + 128^2, levels x4 and x8)")
 for up, C in ((8, 128), (8, 256), (4, 256), (4, 512), (2, 512)):
@@ -57,7 +61,10 @@ for up, C in ((8, 128), (8, 256), (4, 256), (4, 512), (2, 512)):
     ws = ops.groupnorm_workspace(lay.T, lay.L, dev)
     mk = lambda i: (lambda: ops.groupnorm_nhwc(xs[i], ys[i], g, b, lay.row_group, lay.lat_chunks, lay.L, ws, silu=True))
     report(f"groupnorm T={lay.T} C={C}", 2 * lay.T * C * 2, timeit([mk(0)], 10), timeit([mk(0), mk(1)], 10))
-    del xs, ys
+    st = torch.ones(lay.n_tiles * 2 * C * 2, device=dev)
+    mk2 = lambda i: (lambda: ops.groupnorm_from_conv_stats(xs[i], ys[i], g, b, lay.row_group, st, lay.lat_tiles, lay.L, ws, silu=True))
+    report(f"  + stats from the conv epilogue", 2 * lay.T * C * 2, timeit([mk2(0)], 10), timeit([mk2(0), mk2(1)], 10))
+    del xs, ys, st
 
 print("## LayerNorm rows")
 for T, D, kind in ((10240, 640, "affine"), (2560, 1280, "affine"), (14848, 1536, "mod"), (14848, 1536, "dual"),
