@@ -338,6 +338,18 @@ def measure_model(model, args, rank, world, dev, dist):
     tags = prof.pop("tags", [])
     torch.cuda.synchronize()
     per_kernel = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in prof.items()}
+    shapes = {}
+    for n, t, ev in tags:   # per (M, N, K, epilogue | stride): ms per step, calls per step
+        k = (n.replace("b200_", "").replace("_bf16", ""),) + tuple(t)
+        e = shapes.setdefault(k, [0.0, 0])
+        e[0] += ev[0].elapsed_time(ev[1])
+        e[1] += 1
+    top_shapes = [{"kernel": k[0], "shape": list(k[1:]), "ms_per_step": round(v[0] / args.steps, 3),
+                   "calls_per_step": v[1] / args.steps,
+                   "tflops": round(2.0 * k[1] * k[2] * k[3] * v[1] / (v[0] / 1e3) / 1e12, 1)
+                   if v[0] > 0 and k[0] != "attn_varlen" else None}   # attention: (q rows, kv rows, units)
+                  for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][0])
+                  if k[0] == "attn_varlen" or v[0] / args.steps >= 0.4][:16]
     gemm_fl = sum(2.0 * t[0] * t[1] * t[2] for n, t, _ in tags if n == "b200_gemm_bf16") / args.steps
     conv_fl = sum(2.0 * t[0] * t[1] * t[2] for n, t, _ in tags if n == "b200_conv3x3_bf16") / args.steps
     # (b) the timed region proper: the step as the product runs it (CUDA-graph replay of the forward)
@@ -407,7 +419,8 @@ def measure_model(model, args, rank, world, dev, dist):
            "e2e": {"value": world * 1000.0 / ms_e2e, "unit": "denoise steps/s", "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
            "gpu_launches": launches, "clocks": clk, "roofline": roof,
-           "kernel_ms_per_step": {k: round(v, 3) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])}}
+           "kernel_ms_per_step": {k: round(v, 3) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])},
+           "top_shapes": top_shapes}
     return rec, sd
 
 

@@ -81,6 +81,16 @@ typedef struct B200EpilogueDesc {
                            /* per (16x8 output tile, row half, channel) the (sum, sum of squares) */
                            /* of the stored bf16 outputs: the statistics pass of the GroupNorm    */
                            /* that follows (b200_groupnorm_from_conv_stats), fused                */
+  const float* ln_stats;   /* b200_gemm_bf16 only, may be NULL: [M][2] fp32 (mean, rstd) per row of A */
+  const float* ln_colsum;  /* [N] fp32. LayerNorm FOLDED into the GEMM: A is the un-normalised x, W    */
+                           /* carries gamma (W' = W o gamma), colsum[n] = sum_k W'[n, k], bias carries  */
+                           /* beta W^T: acc <- rstd * (acc - mean * colsum) before the epilogue mode,   */
+                           /* so C = epilogue(LN(x) W^T + b) without a LayerNorm pass (b200_row_stats)  */
+  const float* ln_rowpart; /* ... or, instead of ln_stats, the partial sums the PRODUCER of A left:    */
+  int32_t ln_nparts;       /* [ln_nparts][M][2] fp32 (sum, sum of squares) per 64-column chunk of a    */
+  float ln_eps;            /* row of A, ln_nparts = K / 64; (mean, rstd) are reduced once per tile      */
+  float* rowpart_out;      /* producer side, may be NULL: [ceil(N/64)][M][2] partial sums of the rows   */
+                           /* of C (not with B200_EPI_GEGLU / fp32 outputs): no statistics kernel at all */
 } B200EpilogueDesc;
 
 /* A: [M, lda] bf16, W: [N, ldw] bf16 (K contiguous in both). N, K, lda, ldw, ldc multiples
@@ -166,6 +176,11 @@ int b200_layernorm_mod_bf16(const void* x, int ldx, int T, int D, float eps, con
                             int shift_col, int scale_col, void* y, int ldy, int shift2_col,
                             int scale2_col, void* y2, int ldy2, const int32_t* row_mask,
                             int row_mask_shift, void* stream);
+
+/* stats[row] = (mean, rstd = 1/sqrt(var + eps)) of x[row, :D] (fp32 pairs): the row statistics of
+ * a LayerNorm whose affine part is folded into the consuming GEMM (B200EpilogueDesc.ln_stats).
+ * D <= 2048, D % 8 == 0. */
+int b200_row_stats_bf16(const void* x, int ldx, int T, int D, float eps, float* stats, void* stream);
 
 /* y = x * sigmoid(x), n % 8 == 0 elements of bf16. */
 int b200_silu_bf16(const void* x, void* y, long long n, void* stream);

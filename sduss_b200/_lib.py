@@ -36,6 +36,9 @@ class EpilogueDesc(ctypes.Structure):
         ("act", ctypes.c_int32),
         ("row_mask", c_void_p), ("row_mask_shift", ctypes.c_int32),
         ("stats_out", c_void_p),
+        ("ln_stats", c_void_p), ("ln_colsum", c_void_p),
+        ("ln_rowpart", c_void_p), ("ln_nparts", ctypes.c_int32), ("ln_eps", c_float),
+        ("rowpart_out", c_void_p),
     ]
 
 
@@ -113,6 +116,7 @@ SIGNATURES = {
     "b200_patch_mask_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(Forest), c_int, c_int,
                              c_void_p, c_void_p],
+    "b200_row_stats_bf16": [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p],
     "b200_silu_bf16": [c_void_p, c_void_p, ctypes.c_longlong, c_void_p],
     "b200_timestep_embedding": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
     "b200_sd3_patchify": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,

@@ -392,6 +392,8 @@ extern "C" int b200_conv3x3_bf16(const void* in_maps_dev, const void* out_maps_d
   e.rms_wq = nullptr; e.rms_wk = nullptr; e.rms_q_cols = 0; e.rms_k_cols = 0;
   e.rms_eps = 0.f; e.q_scale = 1.f; e.act = 0; e.row_mask = nullptr; e.row_mask_shift = 0;
   e.stats_out = reinterpret_cast<float2*>(ep->stats_out);
+  e.ln_stats = nullptr; e.ln_colsum = nullptr; e.ln_rowpart = nullptr; e.ln_nparts = 0; e.part_ld = 0; e.ln_eps = 0.f;
+  e.rowpart_out = nullptr;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   if (bn256) return dispatch_conv<256, 1>(epi_mode, tmW, a, e, M_total, sms, st);
   // 128-wide tiles with several rounds of tile pairs: two M tiles per CTA share each weight tile

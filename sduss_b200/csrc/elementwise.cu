@@ -288,6 +288,46 @@ static int launch_ln(const LnArgs& a, cudaStream_t st) {
   return full ? launch_ln_v<NIT, true, PF, MB>(a, st) : launch_ln_v<NIT, false, PF, MB>(a, st);
 }
 
+// ------------------------------------------------------------------ row statistics (LN folded into a GEMM)
+// stats[row] = (mean, rstd) of x[row, :D]: what is left of a LayerNorm whose affine part has been
+// folded into the weights of the GEMM that consumes x (B200EpilogueDesc.ln_stats): one read of x
+// and 8 bytes per row written, instead of a full read + write. One warp per row, the row in
+// registers, two-pass variance like ln_center.
+__global__ void __launch_bounds__(256) row_stats_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int T,
+                                                        int D, float eps, float2* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= T) return;
+  const int nchunk = D >> 3;
+  const __nv_bfloat16* xr = x + size_t(row) * ldx;
+  float v[LN_MAXIT * 8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXIT; ++i) {
+    if (lane + 32 * i < nchunk) {
+      unpack8(*reinterpret_cast<const uint4*>(xr + (lane + 32 * i) * 8), v + 8 * i);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[8 * i + j];
+    }
+  }
+  const float mean = warp_sum(s) / float(D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXIT; ++i) {
+    if (lane + 32 * i < nchunk) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[8 * i + j] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  }
+  q = warp_sum(q);
+  if (lane == 0) stats[row] = make_float2(mean, rsqrtf(q / float(D) + eps));
+}
+
 // ------------------------------------------------------------------ small elementwise
 __global__ void silu_kernel(const __nv_bfloat16* x, __nv_bfloat16* y, long n8) {
   long i = blockIdx.x * long(blockDim.x) + threadIdx.x;
@@ -384,6 +424,13 @@ extern "C" int b200_layernorm_mod_bf16(const void* x, int ldx, int T, int D, flo
     case 7: return launch_ln<7>(a, st);
     default: return launch_ln<8>(a, st);
   }
+}
+
+extern "C" int b200_row_stats_bf16(const void* x, int ldx, int T, int D, float eps, float* stats,
+                                   void* stream) {
+  if (!x || !stats || T <= 0 || D <= 0 || (D & 7) || D > LN_MAXD || (ldx & 7)) return B200_ERR_INVALID;
+  return launch_pdl(row_stats_kernel, dim3((T + 7) / 8), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                    static_cast<const bf16*>(x), ldx, T, D, eps, reinterpret_cast<float2*>(stats));
 }
 
 extern "C" int b200_silu_bf16(const void* x, void* y, long long n, void* stream) {

@@ -39,7 +39,49 @@ struct EpiArgs {
   int row_mask_shift;          // skipped entirely (no loads, no MMA, C untouched); null = all tiles
   float2* stats_out;           // conv only: per (M tile, row half, channel) (sum, sum of squares) of the
                                // STORED bf16 outputs, for the GroupNorm that follows; null = off
+  // LayerNorm folded into this GEMM (A is the UN-normalised activation, W already carries gamma):
+  //   LN(x) W^T = rstd_row * (x (gamma o W)^T - mean_row * colsum), + beta W^T inside `bias`
+  const float2* ln_stats;      // [M] (mean, rstd) per row, or null
+  const float* ln_colsum;      // [N] sum_k gamma_k W[n, k] (of the bf16 weights actually multiplied)
+  // ... with the row statistics taken from the per-chunk partial sums the PRODUCER of A left behind:
+  const float2* ln_rowpart;    // [ln_nparts][M] (sum, sum of squares) over each 64-column chunk of A's row
+  int ln_nparts;               // = K / 64 of this GEMM   (chunk-major: a thread per row reads / writes
+  int part_ld;                 // = M                      coalesced across the 128 rows of a tile)
+  float ln_eps;
+  float2* rowpart_out;         // producer side: [ceil(N / 64)][M] partial sums of THIS GEMM's output rows
 };
+
+// (mean, rstd) of row `row` of A for the folded LayerNorm, from whichever source the caller gave
+__device__ __forceinline__ float2 ln_row_stats(const EpiArgs& e, int row, bool row_ok, int K) {
+  if (e.ln_colsum == nullptr || !row_ok) return make_float2(0.f, 0.f);
+  if (e.ln_rowpart == nullptr) return e.ln_stats[row];
+  const float2* p = e.ln_rowpart + row;
+  float s = 0.f, q = 0.f;
+#pragma unroll 4
+  for (int i = 0; i < e.ln_nparts; ++i) {  // fixed order
+    const float2 v = p[size_t(i) * e.part_ld];
+    s += v.x;
+    q += v.y;
+  }
+  const float mean = s / float(K);
+  const float var = fmaxf(q / float(K) - mean * mean, 0.f);
+  return make_float2(mean, rsqrtf(var + e.ln_eps));
+}
+
+// acc <- rstd * (acc - mean * colsum): turns x (gamma o W)^T into LN_noaffine(x) (gamma o W)^T
+// cs: the 64 column sums of this chunk (global, or staged in shared memory by the GEMM epilogue)
+__device__ __forceinline__ void ln_fold64(const float* cs_ptr, float* acc, float2 mr, int ncols) {
+#pragma unroll
+  for (int j = 0; j < 64; j += 4) {
+    if (j < ncols) {
+      const float4 cs = *reinterpret_cast<const float4*>(cs_ptr + j);
+      acc[j] = mr.y * fmaf(-mr.x, cs.x, acc[j]);
+      acc[j + 1] = mr.y * fmaf(-mr.x, cs.y, acc[j + 1]);
+      acc[j + 2] = mr.y * fmaf(-mr.x, cs.z, acc[j + 2]);
+      acc[j + 3] = mr.y * fmaf(-mr.x, cs.w, acc[j + 3]);
+    }
+  }
+}
 
 // true when the M tile starting at row m0 belongs to a clean patch (kept as it is)
 __device__ __forceinline__ bool tile_skipped(const EpiArgs& e, int m0, int M) {
@@ -94,6 +136,7 @@ __device__ __forceinline__ void epilogue_chunk64(const EpiArgs& e, float* acc, i
                                                  int M, int N) {
   if (row >= M || n0 >= N) return;
   const int ncols = min(64, N - n0);  // multiple of 8 by contract
+  if (e.ln_colsum != nullptr) ln_fold64(e.ln_colsum + n0, acc, ln_row_stats(e, row, true, e.ln_nparts * 64), ncols);
   if (e.bias != nullptr) {
 #pragma unroll
     for (int j = 0; j < 64; j += 8) {
@@ -226,8 +269,11 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int k) {  // row r, 16-byte
 // (32 for GEGLU, else 64).
 template <int EPI>
 __device__ __forceinline__ void epilogue_math64(const EpiArgs& e, float* acc, int row, bool row_ok,
-                                                int n0, int N, const uint8_t* resid_stage, int r) {
+                                                int n0, int N, const uint8_t* resid_stage, int r,
+                                                float2 ln_mr = make_float2(0.f, 0.f),
+                                                const float* ln_cs = nullptr) {
   const int ncols = min(64, N - n0);
+  if (ln_cs != nullptr) ln_fold64(ln_cs, acc, ln_mr, ncols);
   if (e.bias != nullptr) {
 #pragma unroll
     for (int j = 0; j < 64; j += 8) {
@@ -302,6 +348,21 @@ __device__ __forceinline__ void epilogue_math64(const EpiArgs& e, float* acc, in
     act_inplace<32>(acc + 32, e.act, 2);
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = acc[j] * acc[32 + j];
+  } else {
+    if (e.rowpart_out != nullptr && row_ok) {
+      // partial row statistics of the output for a LayerNorm folded into the NEXT GEMM
+      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; j += 2) {
+        if (j < ncols) {
+          s0 += acc[j];
+          s1 += acc[j + 1];
+          q0 = fmaf(acc[j], acc[j], q0);
+          q1 = fmaf(acc[j + 1], acc[j + 1], q1);
+        }
+      }
+      e.rowpart_out[size_t(n0 >> 6) * e.part_ld + row] = make_float2(s0 + s1, q0 + q1);
+    }
   }
 }
 

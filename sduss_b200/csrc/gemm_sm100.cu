@@ -28,7 +28,8 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   // + 2 staging tiles (16 KB each) for the TMA epilogue
   static constexpr int kSmemBytes =
-      kStages * kStageBytes + 2 * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+      kStages * kStageBytes + 2 * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
+      1024 /*column sums of a folded LayerNorm, one tile*/;
   static constexpr int kTmemCols = BN == 128 ? 256 : 512;  // two accumulator stages (power of two)
 };
 
@@ -58,6 +59,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tempty = tfull + 2;                // [2]
   uint64_t* rfull = tempty + 2;                // [2] residual chunk landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2);
+  float* colsum_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -199,9 +201,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       __syncwarp();
+      const int row = m0 + r;
+      // LayerNorm folded into this GEMM: the row's (mean, rstd) and the tile's column sums are
+      // fetched once per tile while the main loop is still running (a global load inside the
+      // per-chunk chain costs these epilogue-bound GEMMs more than the LayerNorm launch it saves)
+      const float2 ln_mr = ln_row_stats(e, row, row < s.M, s.K);
+      if (e.ln_colsum != nullptr) {
+        named_barrier<1, 128>();  // every thread is done with the previous tile's column sums
+        for (int j = int(threadIdx.x) - 128; j < BN; j += 128)
+          colsum_s[j] = n0 + j < s.N ? e.ln_colsum[n0 + j] : 0.f;
+        named_barrier<1, 128>();
+      }
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
-      const int row = m0 + r;
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
@@ -230,7 +242,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&rfull[b], (b ? ruse1 : ruse0) & 1);
           if (b) ++ruse1; else ++ruse0;
         }
-        epilogue_math64<EPI>(e, v, row, row < s.M, nc, s.N, has_resid ? stageC + b * EPI_STAGE_BYTES : nullptr, r);
+        epilogue_math64<EPI>(e, v, row, row < s.M, nc, s.N, has_resid ? stageC + b * EPI_STAGE_BYTES : nullptr, r, ln_mr,
+                             e.ln_colsum != nullptr ? colsum_s + c * 64 : nullptr);
         epilogue_stage64<EPI>(stageC + b * EPI_STAGE_BYTES, v, r);
         fence_proxy_async();                       // smem writes -> visible to the TMA engine
         if (leader) tma_store_wait_read<0>();      // chunk c-1 has left its staging tile
@@ -383,6 +396,17 @@ extern "C" int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
   e.row_mask = ep->row_mask;
   e.row_mask_shift = ep->row_mask_shift;
   e.stats_out = nullptr;  // produced by the convolution kernel only
+  e.ln_stats = reinterpret_cast<const float2*>(ep->ln_stats);
+  e.ln_colsum = ep->ln_colsum;
+  e.ln_rowpart = reinterpret_cast<const float2*>(ep->ln_rowpart);
+  e.ln_nparts = ep->ln_nparts;
+  e.part_ld = M;
+  e.ln_eps = ep->ln_eps;
+  e.rowpart_out = reinterpret_cast<float2*>(ep->rowpart_out);
+  if (ep->ln_colsum != nullptr && (ep->ln_stats == nullptr) == (ep->ln_rowpart == nullptr)) return B200_ERR_INVALID;
+  if (ep->ln_colsum == nullptr && (ep->ln_stats != nullptr || ep->ln_rowpart != nullptr)) return B200_ERR_INVALID;
+  if (ep->ln_rowpart != nullptr && ep->ln_nparts * 64 != K) return B200_ERR_INVALID;
+  if (ep->rowpart_out != nullptr && (epi_mode == EPI_GEGLU || ep->out_fp32)) return B200_ERR_INVALID;
   if (ep->row_mask && ep->row_mask_shift < 8) return B200_ERR_INVALID;  // a CTA pair covers 256 rows
   GemmShape s{M, N, K};
   // output / residual tensor maps of the staged epilogue (bf16 outputs only)

@@ -279,7 +279,8 @@ def _req(t, dtype=torch.bfloat16):
 
 def gemm(a, w, out=None, *, epi=EPI_BIAS, bias=None, resid=None, gate=None, row_group=None,
          rowvec=None, rms_wq=None, rms_wk=None, rms_q_cols=0, rms_k_cols=0, rms_eps=1e-6,
-         q_scale=1.0, out_fp32=False, act=0, row_mask=None, row_mask_shift=8):
+         q_scale=1.0, out_fp32=False, act=0, row_mask=None, row_mask_shift=8, ln_stats=None, ln_colsum=None,
+         ln_rowpart=None, ln_eps=1e-5, rowpart_out=None):
     """out = epilogue(a @ w.T). a: [M, K] bf16 (row stride may exceed K), w: [N, K] bf16."""
     _req(a), _req(w)
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
@@ -301,6 +302,18 @@ def gemm(a, w, out=None, *, epi=EPI_BIAS, bias=None, resid=None, gate=None, row_
     d.rms_wq, d.rms_wk = _ptr(rms_wq), _ptr(rms_wk)
     d.rms_q_cols, d.rms_k_cols = rms_q_cols, rms_k_cols
     d.rms_eps, d.q_scale, d.act = rms_eps, q_scale, act
+    if ln_colsum is not None:  # LayerNorm folded into this GEMM: a is the un-normalised activation
+        assert ln_colsum.dtype == torch.float32 and ln_colsum.numel() == N
+        d.ln_colsum = _ptr(ln_colsum)
+        if ln_rowpart is not None:   # row statistics from the partial sums a's producer left behind
+            assert ln_rowpart.dtype == torch.float32 and K % 64 == 0 and ln_rowpart.numel() >= M * (K // 64) * 2
+            d.ln_rowpart, d.ln_nparts, d.ln_eps = _ptr(ln_rowpart), K // 64, ln_eps
+        else:
+            assert ln_stats is not None and ln_stats.dtype == torch.float32
+            d.ln_stats = _ptr(ln_stats)
+    if rowpart_out is not None:  # leave per-chunk row sums of the output for a LayerNorm folded into the next GEMM
+        assert rowpart_out.dtype == torch.float32 and rowpart_out.numel() >= M * ((N + 63) // 64) * 2
+        d.rowpart_out = _ptr(rowpart_out)
     if row_mask is not None:  # patch cache: M tiles of clean patches are skipped, their rows of out kept
         _req(row_mask, torch.int32)
         d.row_mask, d.row_mask_shift = _ptr(row_mask), row_mask_shift
@@ -363,7 +376,7 @@ def attn_varlen(src_a, src_b, seq_table, work_units, n_units, sched_state, max_c
                 causal=False, rel_bias=None, rel_len=0, q_mask=None, q_mask_shift=8):
     """rel_bias: fp32 [heads, >= 2 rel_len - 1], bias of key offset (k - q) at column k - q + rel_len - 1,
     already divided by `scale` (T5); causal: CLIP's mask. Both off on the denoising path."""
-    _ev = _count("b200_attn_varlen_bf16")
+    _ev = _count("b200_attn_varlen_bf16", (src_a.q_rows, src_a.kv_rows, n_units))
     extra = None
     if causal or rel_bias is not None or q_mask is not None:
         extra = _lib.AttnExtra()
@@ -485,6 +498,31 @@ def layernorm_mod(x, y, *, eps, gamma=None, beta=None, mod=None, row_group=None,
     if _ev is not None:
         _ev.record()
     return y
+
+
+def row_stats(x, stats, eps):
+    """stats[row] = (mean, rstd) of x[row]: the row statistics of a LayerNorm folded into a GEMM."""
+    _req(x), _req(stats, torch.float32)
+    T, D = x.shape
+    assert stats.numel() >= 2 * T
+    _ev = _count("b200_row_stats_bf16")
+    check(lib.b200_row_stats_bf16(_ptr(x), x.stride(0), T, D, ctypes.c_float(eps), _ptr(stats), _stream()),
+          "b200_row_stats_bf16")
+    if _ev is not None:
+        _ev.record()
+    return stats
+
+
+def fold_layernorm(w, gamma, beta, bias=None):
+    """Weights of a GEMM that absorbs the LayerNorm in front of it: (W o gamma as bf16, colsum fp32 of
+    those bf16 weights, bias + beta W^T as bf16). LN(x) W^T + b = rstd (x W'^T - mean colsum) + b'."""
+    wf = w.float() * gamma.float()[None, :]
+    wq = wf.to(torch.bfloat16).contiguous()
+    colsum = wq.float().sum(dim=1).contiguous()
+    b = (beta.float()[None, :] @ w.float().t()).reshape(-1)
+    if bias is not None:
+        b = b + bias.float()
+    return wq, colsum, b.to(torch.bfloat16).contiguous()
 
 
 def silu(x, y=None):

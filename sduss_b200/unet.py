@@ -13,6 +13,7 @@ with halos, each UNet level keeps ONE packed channels-last buffer [sum_i h_i*w_i
     [L*77, 2048] (the reference recomputes them per patch);
   * time-embedding projections of all resnets come from ONE GEMM per step.
 """
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional, Tuple
 
@@ -122,6 +123,12 @@ class _Plan:
         assert t.shape == (rows, cols), (name, t.shape, rows, cols)
         return t
 
+    def fbuf(self, name, numel):
+        t = self.bufs.get(name)
+        if t is None:
+            t = self.bufs[name] = self.arena.alloc(self, (numel,), torch.float32)
+        return t
+
     def reset_workspaces(self):
         """Forget every arena view and everything that captured its address (ops._run_eager)."""
         self.bufs, self.maps, self.block, self.arena_off = {}, {}, None, 0
@@ -224,6 +231,14 @@ class B200UNet(torch.nn.Module):
                 idx = torch.arange(2 * Fh).view(2, Fh // 32, 32).permute(1, 0, 2).reshape(-1)
                 put(b + ".ff1.weight", w1[idx])
                 put(b + ".ff1.bias", b1[idx])
+                # The three LayerNorms of the block folded into the GEMMs that consume them
+                # (ops.fold_layernorm): W' = W o gamma, colsum(W'), bias' = bias + beta W^T
+                for ln, dst, wt, bias in ((".norm1", ".attn1.qkv_f", torch.cat([sd[f"{b}.attn1.to_{n}.weight"] for n in "qkv"], 0), None),
+                                          (".norm2", ".attn2.q_f", sd[b + ".attn2.to_q.weight"], None),
+                                          (".norm3", ".ff1_f", w1[idx], b1[idx])):
+                    wq, cs, bq = ops.fold_layernorm(wt.to(dev), sd[b + ln + ".weight"].to(dev), sd[b + ln + ".bias"].to(dev),
+                                                    None if bias is None else bias.to(dev))
+                    self.w[b + dst + ".weight"], self.w[b + dst + ".colsum"], self.w[b + dst + ".bias"] = wq, cs, bq
                 put(b + ".ff2.weight", sd[b + ".ff.net.2.weight"])
                 put(b + ".ff2.bias", sd[b + ".ff.net.2.bias"])
 
@@ -263,6 +278,9 @@ class B200UNet(torch.nn.Module):
         # GroupNorm statistics from the producing convolution's epilogue: built, parity-tested, OFF
         # (SDXL step: convolutions +0.26 ms, GroupNorms -0.11 ms)
         self.fuse_gn_stats = False
+        # The 210 LayerNorms of the 70 BasicTransformerBlocks folded into the GEMMs that consume them
+        # (row statistics + an epilogue correction instead of a read + write of the activation)
+        self.fold_ln = os.environ.get("SDUSS_B200_NO_LN_FOLD", "0") != "1"
 
     @classmethod
     def from_diffusers(cls, model, device="cuda"):
@@ -323,8 +341,15 @@ class B200UNet(torch.nn.Module):
         w = self.w
         T, C = x.shape
         G = ops.gemm
+        fold = self.fold_ln and C % 64 == 0
+        # Folded LayerNorms: every GEMM that writes h also leaves per-64-column partial sums of its
+        # output rows (rowpart_out), and the GEMM that consumes LN(h) reduces them to (mean, rstd) at
+        # the start of each tile and corrects its accumulators (ln_rowpart + ln_colsum): the 3
+        # LayerNorms of a block cost no launch and no pass over h.
+        rp = pl.fbuf(f"rowpart{level}", T * (C // 64) * 2) if fold else None
         n = self._gn(pl, x, name + ".norm", level, pl.buf(f"gn{level}_{C}", T, C), False, eps=1e-6)
-        h = G(n, w[name + ".proj_in.weight"], pl.buf(name + ".h", T, C), bias=w[name + ".proj_in.bias"])
+        h = G(n, w[name + ".proj_in.weight"], pl.buf(name + ".h", T, C), bias=w[name + ".proj_in.bias"],
+              rowpart_out=rp)
         ln = pl.buf(f"ln{level}_{C}", T, C)
         qkv = pl.buf(f"qkv{level}_{C}", T, 3 * C)
         att = pl.buf(f"att{level}_{C}", T, C)
@@ -334,23 +359,30 @@ class B200UNet(torch.nn.Module):
         if key not in pl.attn_src:
             pl.attn_src[key] = ops.attn_source(q=qkv, q_col=0, k=qkv, k_col=C, v=qkv, v_col=2 * C, out=att)
             pl.attn_src[(level, C, "q")] = ops.attn_source(q=q2, out=att)
+        def ln_gemm(norm, wname, out, **kw):
+            """out = epilogue(LayerNorm(h) W^T + b)."""
+            if fold:
+                return G(h, w[b + wname + "_f.weight"], out, bias=w[b + wname + "_f.bias"], ln_rowpart=rp,
+                         ln_colsum=w[b + wname + "_f.colsum"], ln_eps=1e-5, **kw)
+            ops.layernorm_mod(h, ln, eps=1e-5, gamma=w[b + norm + ".weight"], beta=w[b + norm + ".bias"])
+            return G(ln, w[b + wname + ".weight"], out, bias=w.get(b + wname + ".bias"), **kw)
+
         for j in range(layers):
             b = f"{name}.transformer_blocks.{j}"
-            ops.layernorm_mod(h, ln, eps=1e-5, gamma=w[b + ".norm1.weight"], beta=w[b + ".norm1.bias"])
-            G(ln, w[b + ".attn1.qkv.weight"], qkv)
+            ln_gemm(".norm1", ".attn1.qkv", qkv)
             ops.attn_varlen(pl.attn_src[key], None, *pl.self_plan[level], 0.125)
-            G(att, w[b + ".attn1.out.weight"], h, bias=w[b + ".attn1.out.bias"], epi=ops.EPI_GATE_RESID, resid=h)
-            ops.layernorm_mod(h, ln, eps=1e-5, gamma=w[b + ".norm2.weight"], beta=w[b + ".norm2.bias"])
-            G(ln, w[b + ".attn2.q.weight"], q2)
+            G(att, w[b + ".attn1.out.weight"], h, bias=w[b + ".attn1.out.bias"], epi=ops.EPI_GATE_RESID, resid=h,
+              rowpart_out=rp)
+            ln_gemm(".norm2", ".attn2.q", q2)
             ko = self.kv_off[b]
             src_kv = pl.attn_src.get((b, "kv"))
             if src_kv is None:
                 src_kv = pl.attn_src[(b, "kv")] = ops.attn_source(k=kv_all, k_col=ko, v=kv_all, v_col=ko + C)
             ops.attn_varlen(pl.attn_src[(level, C, "q")], src_kv, *pl.cross_plan[level], 0.125)
-            G(att, w[b + ".attn2.out.weight"], h, bias=w[b + ".attn2.out.bias"], epi=ops.EPI_GATE_RESID, resid=h)
-            ops.layernorm_mod(h, ln, eps=1e-5, gamma=w[b + ".norm3.weight"], beta=w[b + ".norm3.bias"])
-            G(ln, w[b + ".ff1.weight"], ff, bias=w[b + ".ff1.bias"], epi=ops.EPI_GEGLU)
-            G(ff, w[b + ".ff2.weight"], h, bias=w[b + ".ff2.bias"], epi=ops.EPI_GATE_RESID, resid=h)
+            G(att, w[b + ".attn2.out.weight"], h, bias=w[b + ".attn2.out.bias"], epi=ops.EPI_GATE_RESID, resid=h,
+              rowpart_out=rp)
+            ln_gemm(".norm3", ".ff1", ff, epi=ops.EPI_GEGLU)
+            G(ff, w[b + ".ff2.weight"], h, bias=w[b + ".ff2.bias"], epi=ops.EPI_GATE_RESID, resid=h, rowpart_out=rp)
         return G(h, w[name + ".proj_out.weight"], pl.buf(name + ".out", T, C),
                  bias=w[name + ".proj_out.bias"], epi=ops.EPI_GATE_RESID, resid=x)
 

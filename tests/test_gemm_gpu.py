@@ -149,3 +149,71 @@ def test_gemm_one_round_shapes_use_192_wide_tiles(cuda, M, N, K):
     _close(x, ref + resid.float())
     out = ops.gemm(a, w, bias=b, epi=ops.EPI_GELU_TANH)
     _close(out, torch.nn.functional.gelu(ref, approximate="tanh"))
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(2560, 3840, 1280, "bias"), (300, 1280, 640, "bias"), (2560, 10240, 1280, "geglu"),
+                                       (777, 256, 128, "resid")])
+def test_layernorm_folded_into_the_gemm(cuda, M, N, K, epi):
+    """LN(x) W^T + b computed as rstd * (x (W o gamma)^T - mean * colsum) + (b + beta W^T): row
+    statistics (b200_row_stats_bf16) + an epilogue correction instead of a LayerNorm pass. Checked
+    against fp32 LayerNorm -> linear in torch, with inputs that have a large row mean (the
+    cancellation case) and per-row scales."""
+    from sduss_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn(M, K, generator=g) * (0.5 + torch.rand(M, 1, generator=g) * 3) + torch.randn(M, 1, generator=g) * 4)
+    x = x.cuda().bfloat16()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().bfloat16()
+    gamma = (1 + 0.2 * torch.randn(K, generator=g)).cuda().bfloat16()
+    beta = (0.3 * torch.randn(K, generator=g)).cuda().bfloat16()
+    bias = torch.randn(N, generator=g).cuda().bfloat16()
+    stats = torch.empty(2 * M, device=cuda)
+    ops.row_stats(x, stats, 1e-5)
+    xf = x.float()
+    st = stats.view(M, 2)
+    assert torch.allclose(st[:, 0], xf.mean(1), atol=1e-3, rtol=1e-4)
+    assert torch.allclose(st[:, 1], torch.rsqrt(xf.var(1, unbiased=False) + 1e-5), rtol=1e-3)
+    wq, cs, bq = ops.fold_layernorm(w, gamma, beta, bias)
+    ln = torch.nn.functional.layer_norm(xf, (K,), gamma.float(), beta.float(), 1e-5)
+    ref = ln @ w.float().t() + bias.float()
+    kw = {}
+    if epi == "geglu":
+        kw["epi"] = ops.EPI_GEGLU
+        ref = ref.view(M, N // 64, 2, 32)
+        ref = (ref[:, :, 0] * torch.nn.functional.gelu(ref[:, :, 1])).reshape(M, N // 2)
+    elif epi == "resid":
+        r = torch.randn(M, N, generator=g).cuda().bfloat16()
+        kw.update(epi=ops.EPI_GATE_RESID, resid=r)
+        ref = ref + r.float()
+    out = ops.gemm(x, wq, bias=bq, ln_stats=stats, ln_colsum=cs, **kw)
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2.5e-2 * ref.abs().max().item() + 1e-2, (err, ref.abs().max().item())
+    cos = torch.nn.functional.cosine_similarity(out.float().flatten(), ref.flatten(), dim=0).item()
+    assert cos > 0.9995, cos
+    # the same with the statistics taken from partial sums a PRODUCER GEMM left behind (no statistics
+    # kernel): x2 = x0 @ P^T + resid written with rowpart_out, then consumed with ln_rowpart
+    if K % 64 == 0:
+        x0 = torch.randn(M, 128, generator=g).cuda().bfloat16()
+        pw = (torch.randn(K, 128, generator=g) / 11).cuda().bfloat16()
+        rs = (torch.randn(M, K, generator=g) * 2 + 3).cuda().bfloat16()
+        part = torch.zeros(M * (K // 64) * 2, device=cuda)
+        x2 = ops.gemm(x0, pw, epi=ops.EPI_GATE_RESID, resid=rs, rowpart_out=part)
+        pv = part.view(K // 64, M, 2).transpose(0, 1)         # chunk-major: [K/64][M] (sum, sum of squares)
+        x2f = x2.float()
+        assert torch.allclose(pv[:, :, 0].sum(1) / K, x2f.mean(1), atol=2e-2)          # sums of the pre-rounding values
+        ref2 = torch.nn.functional.layer_norm(x2f, (K,), gamma.float(), beta.float(), 1e-5) @ w.float().t() + bias.float()
+        if epi == "geglu":
+            ref2 = ref2.view(M, N // 64, 2, 32)
+            ref2 = (ref2[:, :, 0] * torch.nn.functional.gelu(ref2[:, :, 1])).reshape(M, N // 2)
+        elif epi == "resid":
+            ref2 = ref2 + kw["resid"].float()
+        out3 = ops.gemm(x2, wq, bias=bq, ln_rowpart=part, ln_colsum=cs, ln_eps=1e-5, **kw)
+        torch.cuda.synchronize()
+        err3 = (out3.float() - ref2).abs().max().item()
+        assert err3 <= 2.5e-2 * ref2.abs().max().item() + 1e-2, (err3, ref2.abs().max().item())
+        assert torch.nn.functional.cosine_similarity(out3.float().flatten(), ref2.flatten(), dim=0).item() > 0.9995
+    # same accuracy class as the unfolded path (LayerNorm kernel -> GEMM)
+    y = ops.layernorm_mod(x, torch.empty_like(x), eps=1e-5, gamma=gamma, beta=beta)
+    out2 = ops.gemm(y, w, bias=bias, **kw)
+    err2 = (out2.float() - ref).abs().max().item()
+    assert err <= 3 * err2 + 2e-2, (err, err2)

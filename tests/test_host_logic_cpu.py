@@ -454,3 +454,69 @@ def test_two_rank_gloo_serving_replay(tmp_path):
     assert rec["requests"] == 40 and rec["steps_per_request"] == 5 and rec["req_s"] > 0
     assert rec["latency_s"]["p99"] >= rec["latency_s"]["p50"] > 0
     assert len(rec["runner_cpu_utilisation_per_rank"]) == 2 and "host_cpu_percent" in rec
+
+
+def test_prepare_inference_hand_over_without_gpu():
+    """prepare_inference (row f-4) mirrors the reference's hand-over
+    (pipeline_stable_diffusion_3_esymred.py:49-230, ..._xl_esymred.py:56-258): prompt_2 / prompt_3 fall
+    back to prompt, negatives to "", SDXL ignores the requests' negative prompts and gets zeros under
+    force_zeros_for_empty_prompt, latents ~ N(0,1) * init_noise_sigma in the embedding dtype,
+    add_time_ids = (1024, 1024, crop, 1024, 1024), scheduler state at step 0. The encoders are fakes
+    that record what they were asked to encode."""
+    import torch
+    from sduss_b200.pipelines import B200StableDiffusion3Pipeline, B200StableDiffusionXLPipeline
+    from sduss_b200.schedulers import B200EulerDiscreteScheduler, B200FlowMatchEulerDiscreteScheduler
+
+    class Tok:
+        def __init__(self, log): self.log = log
+        def __call__(self, prompts, padding, max_length, truncation, return_tensors):
+            self.log.append((list(prompts), max_length))
+            return {"input_ids": torch.tensor([[len(p)] * 4 for p in prompts])}
+
+    class Enc:
+        def __init__(self, n): self.n, self.calls = n, []
+        def encode(self, *ids):
+            self.calls.append(ids)
+            B = ids[0].shape[0]
+            base = ids[0][:, :1].float()
+            return (base[:, :, None] + torch.zeros(B, 5, 8)).to(torch.bfloat16), (base + torch.zeros(B, 6)).to(torch.bfloat16)
+
+    def reqs():
+        mk = lambda i, res, p, n, p2=None: SimpleNamespace(request_id=i, sampling_params=SimpleNamespace(
+            prompt=p, prompt_2=p2, prompt_3=None, negative_prompt=n, negative_prompt_2=None, negative_prompt_3=None,
+            num_inference_steps=20 + i, height=res, width=res, latents=None))
+        return {"1024": [mk(0, 1024, "a cat", "blurry")], "512": [mk(1, 512, "two dogs!", "", p2="2nd prompt")]}
+
+    model = SimpleNamespace(device=torch.device("cpu"), cfg=SimpleNamespace(in_channels=16))
+    log = []
+    pipe = B200StableDiffusion3Pipeline(model, B200FlowMatchEulerDiscreteScheduler())
+    enc = Enc(3)
+    pipe.attach_text_encoders(enc, [Tok(log), Tok(log), Tok(log)])
+    r = reqs()
+    pipe.prepare_inference(r, guidance_scale=7.0, generator=torch.Generator().manual_seed(0), max_sequence_length=64)
+    # resolution keys are sorted as STRINGS like the reference does ("1024" < "512"); one pass per branch
+    assert log[:3] == [(["a cat", "two dogs!"], 77), (["a cat", "2nd prompt"], 77), (["a cat", "two dogs!"], 64)]
+    assert log[3:] == [(["blurry", ""], 77), (["blurry", ""], 77), (["blurry", ""], 64)]
+    a, b = r["1024"][0], r["512"][0]
+    assert a.sampling_params.prompt_embeds.shape == (1, 5, 8) and float(a.sampling_params.prompt_embeds[0, 0, 0]) == 5.0
+    assert float(b.sampling_params.prompt_embeds[0, 0, 0]) == 9.0 and float(a.sampling_params.negative_prompt_embeds[0, 0, 0]) == 6.0
+    assert a.prepare_output.pooled_prompt_embeds.shape == (1, 6) and float(b.prepare_output.negative_pooled_prompt_embeds[0, 0]) == 0.0
+    assert a.sampling_params.latents.shape == (1, 16, 128, 128) and b.sampling_params.latents.shape == (1, 16, 64, 64)
+    assert a.sampling_params.latents.dtype == torch.bfloat16 and abs(float(a.sampling_params.latents.float().std()) - 1) < 0.05
+    assert a.scheduler_states._step_index == 0 and len(a.scheduler_states.sigmas) == 21 and len(b.scheduler_states.sigmas) == 22
+    # SDXL
+    model = SimpleNamespace(device=torch.device("cpu"), cfg=SimpleNamespace(in_channels=4))
+    log.clear()
+    sched = B200EulerDiscreteScheduler()
+    pipe = B200StableDiffusionXLPipeline(model, sched)
+    pipe.attach_text_encoders(Enc(2), [Tok(log), Tok(log)])
+    r = reqs()
+    pipe.prepare_inference(r, guidance_scale=5.0, generator=torch.Generator().manual_seed(0), crops_coords_top_left=(8, 16))
+    assert log == [(["a cat", "two dogs!"], 77), (["a cat", "two dogs!"], 77)]       # prompt_2=None, no negative pass
+    a = r["1024"][0]
+    assert float(a.sampling_params.negative_prompt_embeds.abs().sum()) == 0.0        # force_zeros_for_empty_prompt
+    assert a.prepare_output.add_time_ids.float().tolist() == [[1024.0, 1024.0, 8.0, 16.0, 1024.0, 1024.0]]
+    assert a.prepare_output.negative_add_time_ids is a.prepare_output.add_time_ids
+    std = float(a.sampling_params.latents.float().std())
+    assert abs(std / sched.init_noise_sigma - 1) < 0.05 and a.sampling_params.latents.shape == (1, 4, 128, 128)
+    pipe.prepare_inference(reqs(), guidance_scale=1.0)                                # no CFG: no negative embeddings
