@@ -91,6 +91,9 @@ typedef struct B200EpilogueDesc {
   float ln_eps;            /* row of A, ln_nparts = K / 64; (mean, rstd) are reduced once per tile      */
   float* rowpart_out;      /* producer side, may be NULL: [ceil(N/64)][M][2] partial sums of the rows   */
                            /* of C (not with B200_EPI_GEGLU / fp32 outputs): no statistics kernel at all */
+  int32_t w_static;        /* 1: nothing on `stream` writes W (weights): the kernel may request its first */
+                           /* W tiles before waiting for the previous kernel (programmatic dependent       */
+                           /* launch); 0 (default): W is loaded after the wait, like A                     */
 } B200EpilogueDesc;
 
 /* A: [M, lda] bf16, W: [N, ldw] bf16 (K contiguous in both). N, K, lda, ldw, ldc multiples

@@ -49,6 +49,7 @@ struct EpiArgs {
   int part_ld;                 // = M                      coalesced across the 128 rows of a tile)
   float ln_eps;
   float2* rowpart_out;         // producer side: [ceil(N / 64)][M] partial sums of THIS GEMM's output rows
+  int w_static;                // W is never written on the stream (weights): may be loaded before pdl_wait
 };
 
 // (mean, rstd) of row `row` of A for the folded LayerNorm, from whichever source the caller gave
@@ -57,11 +58,18 @@ __device__ __forceinline__ float2 ln_row_stats(const EpiArgs& e, int row, bool r
   if (e.ln_rowpart == nullptr) return e.ln_stats[row];
   const float2* p = e.ln_rowpart + row;
   float s = 0.f, q = 0.f;
-#pragma unroll 4
-  for (int i = 0; i < e.ln_nparts; ++i) {  // fixed order
-    const float2 v = p[size_t(i) * e.part_ld];
-    s += v.x;
-    q += v.y;
+  // all loads of a batch are in flight together (one L2 round trip per 20 chunks = K 1280), then
+  // summed in a fixed order
+  for (int i0 = 0; i0 < e.ln_nparts; i0 += 20) {
+    float2 v[20];
+#pragma unroll
+    for (int j = 0; j < 20; ++j)
+      v[j] = i0 + j < e.ln_nparts ? p[size_t(i0 + j) * e.part_ld] : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 20; ++j) {
+      s += v[j].x;
+      q += v[j].y;
+    }
   }
   const float mean = s / float(K);
   const float var = fmaxf(q / float(K) - mean * mean, 0.f);
@@ -273,8 +281,31 @@ __device__ __forceinline__ void epilogue_math64(const EpiArgs& e, float* acc, in
                                                 float2 ln_mr = make_float2(0.f, 0.f),
                                                 const float* ln_cs = nullptr) {
   const int ncols = min(64, N - n0);
-  if (ln_cs != nullptr) ln_fold64(ln_cs, acc, ln_mr, ncols);
-  if (e.bias != nullptr) {
+  if (ln_cs != nullptr && e.ln_colsum != nullptr) {
+    // folded LayerNorm + bias in two FMAs per element: acc * rstd + (bias - mean * rstd * colsum);
+    // ln_cs[0..63] = column sums, ln_cs[256..319] = the bias in fp32 (both staged per tile)
+    const float nm = -ln_mr.x * ln_mr.y;
+#pragma unroll
+    for (int j = 0; j < 64; j += 4) {
+      const float4 cs = *reinterpret_cast<const float4*>(ln_cs + j);
+      const float4 bs = *reinterpret_cast<const float4*>(ln_cs + 256 + j);
+      acc[j] = fmaf(acc[j], ln_mr.y, fmaf(nm, cs.x, bs.x));
+      acc[j + 1] = fmaf(acc[j + 1], ln_mr.y, fmaf(nm, cs.y, bs.y));
+      acc[j + 2] = fmaf(acc[j + 2], ln_mr.y, fmaf(nm, cs.z, bs.z));
+      acc[j + 3] = fmaf(acc[j + 3], ln_mr.y, fmaf(nm, cs.w, bs.w));
+    }
+  } else if (ln_cs != nullptr) {
+    // bias staged in shared memory as fp32 (one add per element; the bf16 global path below costs
+    // a shift / mask per element on top, in epilogues that are issue-bound)
+#pragma unroll
+    for (int j = 0; j < 64; j += 4) {
+      const float4 bs = *reinterpret_cast<const float4*>(ln_cs + 256 + j);
+      acc[j] += bs.x;
+      acc[j + 1] += bs.y;
+      acc[j + 2] += bs.z;
+      acc[j + 3] += bs.w;
+    }
+  } else if (e.bias != nullptr) {
 #pragma unroll
     for (int j = 0; j < 64; j += 8) {
       if (j < ncols) {

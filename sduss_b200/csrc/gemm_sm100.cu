@@ -17,19 +17,24 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int GEMM_THREADS = 256;
 
-template <int BN, int EPI>
+// TWO: the CTA pair runs ONE tcgen05.mma.cta_group::2 of M = 256 per K step; each CTA keeps only its
+// half of the W tile, so a stage is 16 KB + BN x 64 B and the ring holds 6-8 K steps instead of 4-5
+// (these main loops are bound by operand latency x bytes in flight, not by the tensor pipe).
+template <int BN, int EPI, bool TWO = false>
 struct GemmCfg {
   // The residual chunk of a gate*y + residual epilogue is TMA-loaded INTO the output staging tile
   // and updated in place, so that epilogue costs no pipeline stage (a 3-stage 128 x 256 main loop
   // lost 27 % on the K = 1536 out-projections: operand latency, not the tensor pipe).
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192) ? 4 : 5;
+  static constexpr int kStages = TWO ? ((BN == 128) ? 8 : 6) : (BN == 256) ? 4 : (BN == 192) ? 4 : 5;
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (TWO ? BN / 2 : BN) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // + 2 staging tiles (16 KB each) for the TMA epilogue
   static constexpr int kSmemBytes =
-      kStages * kStageBytes + 2 * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
-      1024 /*column sums of a folded LayerNorm, one tile*/;
+      kStages * kStageBytes + 2 * EPI_STAGE_BYTES + 256 /*barriers*/ +
+      2048 /*column sums + fp32 bias of a folded LayerNorm, one tile: [2][256] floats*/;
+  // (no alignment slack: the dynamic shared memory window is declared 1024-byte aligned and the
+  //  kernel traps if it is not -- 4 x 48 KB stages + staging + the two tables fill the 227 KB)
   static constexpr int kTmemCols = BN == 128 ? 256 : 512;  // two accumulator stages (power of two)
 };
 
@@ -40,15 +45,16 @@ struct GemmShape {
 // MC = 2: CTA pairs (cluster of 2 along M) share every W tile: each CTA fetches half of it and
 // multicasts it into both CTAs' shared memory, cutting L2 -> SM operand traffic by a third
 // (the 128x256x64 main loop is L2-bandwidth bound: 96 B/clk/SM of operand loads on 148 SMs).
-template <int BN, int EPI, int MC>
+template <int BN, int EPI, int MC, bool TWO>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                  GemmShape s, EpiArgs e) {
-  using Cfg = GemmCfg<BN, EPI>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~uintptr_t(1023));
+  static_assert(!TWO || MC == 2, "cta_group::2 needs the CTA pair");
+  using Cfg = GemmCfg<BN, EPI, TWO>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (smem_u32(smem_raw) & 1023u) __trap();  // SW128 tiles need 1024-byte alignment (fail loudly)
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + Cfg::kStages * Cfg::kABytes;
   uint8_t* stageC = smem + Cfg::kStages * Cfg::kStageBytes;  // [2][16 KB] residual in / output out
@@ -81,18 +87,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], MC);  // released by the MMA warp of every CTA the stage is multicast to
+      // released by the MMA warp of every CTA the stage is multicast to / by the pair's one MMA warp
+      mbar_init(&empty[i], TWO ? 1 : MC);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], TWO ? 8 : 4);  // TWO: the epilogue warps of BOTH CTAs release the leader's
       mbar_init(&rfull[i], 1);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (TWO) {
+      tmem_alloc2(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -100,6 +112,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if constexpr (MC == 2) cluster_sync_all();  // peer barriers are initialised before any multicast
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
+  // bytes one phase of full[stage] waits for: TWO = both CTAs' A tiles and W halves, on the leader
+  constexpr uint32_t kExpect = TWO ? 2u * Cfg::kStageBytes : uint32_t(Cfg::kStageBytes);
+  auto load_w = [&](int stage, int kb, int n0) {
+    if constexpr (TWO) {
+      // my half of the W tile stays in MY shared memory; the bytes count on the leader's barrier
+      tma_load_2d_2sm(smemB + stage * Cfg::kBBytes, &tmB, &full[stage], kb * BK, n0 + int(rank) * (BN / 2));
+    } else if constexpr (MC == 2) {
+      // my half of the W tile (BN/2 rows), delivered to both CTAs of the pair
+      tma_load_2d_mc(smemB + stage * Cfg::kBBytes + rank * (Cfg::kBBytes / 2), &tmB, &full[stage],
+                     kb * BK, n0 + int(rank) * (BN / 2), uint16_t(3));
+    } else {
+      tma_load_2d(smemB + stage * Cfg::kBBytes, &tmB, &full[stage], kb * BK, n0);
+    }
+  };
+  // W holds weights (w_static: nothing on the stream writes it): the first ring stages of W are
+  // requested BEFORE waiting for the previous kernel, so their HBM latency runs under its tail;
+  // only the A loads (L2 hits: A was just written) remain after the wait.
+  int npre = 0;
+  if (warp == 0 && e.w_static && e.row_mask == nullptr && first_tile < num_tiles) {
+    npre = num_kb < Cfg::kStages ? num_kb : Cfg::kStages;
+    if (lane == 0) {
+      const int n0 = (first_tile % tiles_n) * BN;
+      for (int kb = 0; kb < npre; ++kb) {
+        if (!TWO || rank == 0) mbar_expect_tx(&full[kb], kExpect);
+        load_w(kb, kb, n0);
+      }
+    }
+    __syncwarp();
+  }
   pdl_wait();  // the prologue above overlapped the previous kernel; its outputs are visible now
 
   if (warp == 0) {
@@ -113,15 +154,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (lane == 0) {
-          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-          tma_load_2d(smemA + stage * Cfg::kABytes, &tmA, &full[stage], kb * BK, m0);
-          if constexpr (MC == 2) {
-            // my half of the W tile (BN/2 rows), delivered to both CTAs of the pair
-            tma_load_2d_mc(smemB + stage * Cfg::kBBytes + rank * (Cfg::kBBytes / 2), &tmB, &full[stage],
-                           kb * BK, n0 + int(rank) * (BN / 2), uint16_t(3));
-          } else {
-            tma_load_2d(smemB + stage * Cfg::kBBytes, &tmB, &full[stage], kb * BK, n0);
-          }
+          const bool pre = t == first_tile && kb < npre;  // W of this stage is already on its way
+          if (!pre && (!TWO || rank == 0)) mbar_expect_tx(&full[stage], kExpect);
+          if constexpr (TWO) tma_load_2d_2sm(smemA + stage * Cfg::kABytes, &tmA, &full[stage], kb * BK, m0);
+          else tma_load_2d(smemA + stage * Cfg::kABytes, &tmA, &full[stage], kb * BK, m0);
+          if (!pre) load_w(stage, kb, n0);
         }
         __syncwarp();
         if (++stage == Cfg::kStages) {
@@ -130,9 +167,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+  } else if (warp == 1 && (!TWO || rank == 0)) {
+    // ------------------------------------------------------------ MMA issuer (TWO: the leader's only)
+    constexpr uint32_t idesc = make_idesc_bf16(TWO ? 2 * BM : BM, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -151,12 +188,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 bytes (encoded >>4) per 16-element K step inside the 128B swizzle span
-            umma_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc,
-                    (kb | k) != 0 ? 1u : 0u);
+            if constexpr (TWO) umma_ss2(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          if constexpr (MC == 2) umma_commit_mc(&empty[stage], uint16_t(3));
+          if constexpr (TWO) umma_commit2_mc(&empty[stage], uint16_t(3));
+          else if constexpr (MC == 2) umma_commit_mc(&empty[stage], uint16_t(3));
           else umma_commit(&empty[stage]);
-          if (kb == num_kb - 1) umma_commit(&tfull[acc]);
+          if (kb == num_kb - 1) {
+            if constexpr (TWO) umma_commit2_mc(&tfull[acc], uint16_t(3));  // both CTAs' epilogues
+            else umma_commit(&tfull[acc]);
+          }
         }
         __syncwarp();
         if (++stage == Cfg::kStages) {
@@ -206,10 +247,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // fetched once per tile while the main loop is still running (a global load inside the
       // per-chunk chain costs these epilogue-bound GEMMs more than the LayerNorm launch it saves)
       const float2 ln_mr = ln_row_stats(e, row, row < s.M, s.K);
-      if (e.ln_colsum != nullptr) {
-        named_barrier<1, 128>();  // every thread is done with the previous tile's column sums
-        for (int j = int(threadIdx.x) - 128; j < BN; j += 128)
-          colsum_s[j] = n0 + j < s.N ? e.ln_colsum[n0 + j] : 0.f;
+      const bool tables = e.ln_colsum != nullptr || e.bias != nullptr;
+      if (tables) {
+        named_barrier<1, 128>();  // every thread is done with the previous tile's tables
+        for (int j = int(threadIdx.x) - 128; j < BN; j += 128) {
+          const bool ok = n0 + j < s.N;
+          colsum_s[j] = ok && e.ln_colsum != nullptr ? e.ln_colsum[n0 + j] : 0.f;
+          colsum_s[256 + j] = ok && e.bias != nullptr ? __bfloat162float(e.bias[n0 + j]) : 0.f;  // fp32 bias
+        }
         named_barrier<1, 128>();
       }
       mbar_wait(&tfull[acc], (it >> 1) & 1);
@@ -243,7 +288,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (b) ++ruse1; else ++ruse0;
         }
         epilogue_math64<EPI>(e, v, row, row < s.M, nc, s.N, has_resid ? stageC + b * EPI_STAGE_BYTES : nullptr, r, ln_mr,
-                             e.ln_colsum != nullptr ? colsum_s + c * 64 : nullptr);
+                             tables ? colsum_s + c * 64 : nullptr);
         epilogue_stage64<EPI>(stageC + b * EPI_STAGE_BYTES, v, r);
         fence_proxy_async();                       // smem writes -> visible to the TMA engine
         if (leader) tma_store_wait_read<0>();      // chunk c-1 has left its staging tile
@@ -259,7 +304,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if constexpr (TWO) mbar_arrive_leader(&tempty[acc]);
+        else mbar_arrive(&tempty[acc]);
+      }
       ++it;
     }
     if (leader) tma_store_wait<0>();
@@ -270,16 +318,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if constexpr (MC == 2) cluster_sync_all();  // the peer may still arrive on my barriers until here
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (TWO) tmem_dealloc2(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BN, int EPI, int MC>
+template <int BN, int EPI, int MC, bool TWO = false>
 static int launch_gemm_mc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                           const CUtensorMap& tmR, GemmShape s, const EpiArgs& e, int num_sms,
                           cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, EPI>;
-  auto kern = gemm_bf16_kernel<BN, EPI, MC>;
+  using Cfg = GemmCfg<BN, EPI, TWO>;
+  auto kern = gemm_bf16_kernel<BN, EPI, MC, TWO>;
   static bool configured = false;
   if (!configured) {
     cudaError_t err =
@@ -298,6 +347,10 @@ template <int BN, int EPI>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                        const CUtensorMap& tmR, GemmShape s, const EpiArgs& e, int num_sms,
                        cudaStream_t stream, bool multicast) {
+  // CTA pairs run as cta_group::2 (one M = 256 MMA per pair, W halves never duplicated in shared
+  // memory); SDUSS_B200_NO_2CTA=1 keeps the pair on two M = 128 MMAs with W multicast (round 1)
+  static const bool two = []() { const char* v = getenv("SDUSS_B200_NO_2CTA"); return !(v && v[0] == '1'); }();
+  if (multicast && two) return launch_gemm_mc<BN, EPI, 2, true>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
   return multicast ? launch_gemm_mc<BN, EPI, 2>(tmA, tmB, tmC, tmR, s, e, num_sms, stream)
                    : launch_gemm_mc<BN, EPI, 1>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
 }
@@ -401,6 +454,7 @@ extern "C" int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
   e.ln_rowpart = reinterpret_cast<const float2*>(ep->ln_rowpart);
   e.ln_nparts = ep->ln_nparts;
   e.part_ld = M;
+  e.w_static = ep->w_static;
   e.ln_eps = ep->ln_eps;
   e.rowpart_out = reinterpret_cast<float2*>(ep->rowpart_out);
   if (ep->ln_colsum != nullptr && (ep->ln_stats == nullptr) == (ep->ln_rowpart == nullptr)) return B200_ERR_INVALID;

@@ -280,7 +280,7 @@ def _req(t, dtype=torch.bfloat16):
 def gemm(a, w, out=None, *, epi=EPI_BIAS, bias=None, resid=None, gate=None, row_group=None,
          rowvec=None, rms_wq=None, rms_wk=None, rms_q_cols=0, rms_k_cols=0, rms_eps=1e-6,
          q_scale=1.0, out_fp32=False, act=0, row_mask=None, row_mask_shift=8, ln_stats=None, ln_colsum=None,
-         ln_rowpart=None, ln_eps=1e-5, rowpart_out=None):
+         ln_rowpart=None, ln_eps=1e-5, rowpart_out=None, w_static=False):
     """out = epilogue(a @ w.T). a: [M, K] bf16 (row stride may exceed K), w: [N, K] bf16."""
     _req(a), _req(w)
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
@@ -317,6 +317,7 @@ def gemm(a, w, out=None, *, epi=EPI_BIAS, bias=None, resid=None, gate=None, row_
     if row_mask is not None:  # patch cache: M tiles of clean patches are skipped, their rows of out kept
         _req(row_mask, torch.int32)
         d.row_mask, d.row_mask_shift = _ptr(row_mask), row_mask_shift
+    d.w_static = int(bool(w_static))  # w holds weights: its first tiles may be fetched under the previous kernel
     _ev = _count("b200_gemm_bf16", (M, N, K, epi))
     check(lib.b200_gemm_bf16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), M, N, K, epi,
                              ctypes.byref(d), _stream()), "b200_gemm_bf16")

@@ -21,6 +21,12 @@ import torch
 from . import ops
 
 
+def _G(*a, **k):
+    """ops.gemm against WEIGHTS (never written on the stream): W tiles may be fetched ahead of the wait
+    on the previous kernel."""
+    return ops.gemm(*a, w_static=True, **k)
+
+
 @dataclass
 class SD3Config:
     num_layers: int = 24
@@ -354,7 +360,7 @@ class B200SD3Transformer2DModel(torch.nn.Module):
     def _run(self, pl: _Plan):
         cfg = self.cfg
         D, H, p = cfg.inner_dim, cfg.num_attention_heads, cfg.patch_size
-        G = ops.gemm
+        G = _G
         te = self.te
         scale = 1.0 / math.sqrt(cfg.attention_head_dim)
         # conditioning: temb = MLP(sinusoid(t)) + MLP(pooled); all AdaLN vectors in one GEMM
@@ -443,7 +449,7 @@ class B200SD3Transformer2DModel(torch.nn.Module):
         place. The context stream (333 tokens per latent) is always recomputed."""
         cfg, cb = self.cfg, pl.cache
         D, H, p = cfg.inner_dim, cfg.num_attention_heads, cfg.patch_size
-        G = ops.gemm
+        G = _G
         te = self.te
         scale = 1.0 / math.sqrt(cfg.attention_head_dim)
         ops.timestep_embedding(pl.t32, 256, out=pl.tsin)

@@ -24,6 +24,12 @@ from . import ops
 from .layout import LevelLayout
 
 
+def _G(*a, **k):
+    """ops.gemm against WEIGHTS (never written on the stream): W tiles may be fetched ahead of the wait
+    on the previous kernel."""
+    return ops.gemm(*a, w_static=True, **k)
+
+
 @dataclass
 class UNetConfig:
     in_channels: int = 4
@@ -340,7 +346,7 @@ class B200UNet(torch.nn.Module):
     def _transformer(self, pl, x, name, level, heads, layers, kv_all):
         w = self.w
         T, C = x.shape
-        G = ops.gemm
+        G = _G
         fold = self.fold_ln and C % 64 == 0
         # Folded LayerNorms: every GEMM that writes h also leaves per-64-column partial sums of its
         # output rows (rowpart_out), and the GEMM that consumes LN(h) reduces them to (mean, rstd) at
@@ -442,7 +448,7 @@ class B200UNet(torch.nn.Module):
         return (out,)
 
     def _run(self, pl: _Plan):
-        cfg, w, G = self.cfg, self.w, ops.gemm
+        cfg, w, G = self.cfg, self.w, _G
         ch = cfg.block_out_channels
         L = pl.L
         Tdim = ch[0] * 4

@@ -34,7 +34,7 @@ def test_ctypes_signatures_cover_header():
 def test_struct_layouts_match_header():
     from sduss_b200 import _lib
     # B200EpilogueDesc: 8B ptr, 2x i32, 2 ptr, i32(+pad), ptr, i32(+pad), ptr, ptr, i32(+pad), 2 ptr, 2 i32, 2 f32
-    assert ctypes.sizeof(_lib.EpilogueDesc) == 184 and _lib.EpilogueDesc.act.offset == 112
+    assert ctypes.sizeof(_lib.EpilogueDesc) == 192 and _lib.EpilogueDesc.w_static.offset == 184 and _lib.EpilogueDesc.act.offset == 112
     assert _lib.EpilogueDesc.ln_rowpart.offset == 160 and _lib.EpilogueDesc.rowpart_out.offset == 176
     assert _lib.EpilogueDesc.ln_stats.offset == 144
     assert _lib.EpilogueDesc.stats_out.offset == 136
