@@ -103,8 +103,24 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
   return 0.5f * x * (1.f + t);
 }
+// x * Phi(x), Phi through erf(|x| / sqrt 2) = 1 - (a1 t + ... + a5 t^5) exp(-x^2 / 2), t = 1 / (1 + p |x| / sqrt 2)
+// (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7 -- five orders below the bf16 rounding of the result).
+// Branch-free: 2 MUFU (rcp, ex2) + 11 FMA-pipe ops. The libdevice erff() takes ~40 instructions with a
+// divergent branch at |x| ~ 0.9, which made the GEGLU epilogue (128 x 128 activations per tile on 4
+// warps) 1.5x longer than the tile's main loop (SDXL ff1: 70 us per call against 47 us plain).
 __device__ __forceinline__ float gelu_erf_f(float x) {
-  return 0.5f * x * (1.f + erff(x * 0.7071067811865476f));
+  const float z = fabsf(x);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(z, 0.3275911f * 0.7071067811865476f, 1.f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * (-0.5f * 1.4426950408889634f)));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  p *= t;
+  const float erf_abs = fmaf(-p, e, 1.f);                   // erf(|x| / sqrt 2) in [0, 1]
+  const float phi = fmaf(copysignf(0.5f, x), erf_abs, 0.5f);
+  return x * phi;
 }
 
 __device__ __forceinline__ float quick_gelu_f(float x) {  // x * sigmoid(1.702 x)   (CLIP-L)

@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                  GemmShape s, EpiArgs e) {
-  static_assert(!TWO || MC == 2, "cta_group::2 needs the CTA pair");
+  static_assert(MC == 1 || MC == 2 || (MC == 4 && TWO), "clusters: 1, a pair, or two cta_group::2 pairs");
+  static_assert(!TWO || MC >= 2, "cta_group::2 needs the CTA pair");
   using Cfg = GemmCfg<BN, EPI, TWO>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -76,9 +77,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int tiles_m = (s.M + BM * MC - 1) / (BM * MC);
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (s.K + BK - 1) / BK;
-  const uint32_t rank = MC == 2 ? cluster_ctarank() : 0;
-  const int first_tile = MC == 2 ? int(blockIdx.x >> 1) : int(blockIdx.x);
-  const int tile_step = MC == 2 ? int(gridDim.x >> 1) : int(gridDim.x);
+  // MC == 4 (TWO only): two pairs stacked along M share every W half: CTA (pair p, half r) fetches
+  // quarter p of half r and multicasts it to the CTA holding half r in both pairs -- 16 + BN/4 x 128 B
+  // per CTA and K step instead of 16 + BN/2 x 128 B through L2 -> SM, the bound of these main loops.
+  const uint32_t rank = MC >= 2 ? cluster_ctarank() : 0;
+  const int first_tile = int(blockIdx.x) / MC;
+  const int tile_step = int(gridDim.x) / MC;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -88,7 +92,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int i = 0; i < Cfg::kStages; ++i) {
       mbar_init(&full[i], 1);
       // released by the MMA warp of every CTA the stage is multicast to / by the pair's one MMA warp
-      mbar_init(&empty[i], TWO ? 1 : MC);
+      mbar_init(&empty[i], TWO ? MC / 2 : MC);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -109,13 +113,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if constexpr (MC == 2) cluster_sync_all();  // peer barriers are initialised before any multicast
+  if constexpr (MC >= 2) cluster_sync_all();  // peer barriers are initialised before any multicast
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
   // bytes one phase of full[stage] waits for: TWO = both CTAs' A tiles and W halves, on the leader
   constexpr uint32_t kExpect = TWO ? 2u * Cfg::kStageBytes : uint32_t(Cfg::kStageBytes);
   auto load_w = [&](int stage, int kb, int n0) {
-    if constexpr (TWO) {
+    if constexpr (TWO && MC == 4) {
+      const int r = int(rank & 1), p = int(rank >> 1);
+      tma_load_2d_2sm_mc(smemB + stage * Cfg::kBBytes + p * (Cfg::kBBytes / 2), &tmB, &full[stage], kb * BK,
+                         n0 + r * (BN / 2) + p * (BN / 4), uint16_t(5u << r));
+    } else if constexpr (TWO) {
       // my half of the W tile stays in MY shared memory; the bytes count on the leader's barrier
       tma_load_2d_2sm(smemB + stage * Cfg::kBBytes, &tmB, &full[stage], kb * BK, n0 + int(rank) * (BN / 2));
     } else if constexpr (MC == 2) {
@@ -135,7 +143,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       const int n0 = (first_tile % tiles_n) * BN;
       for (int kb = 0; kb < npre; ++kb) {
-        if (!TWO || rank == 0) mbar_expect_tx(&full[kb], kExpect);
+        if (!TWO || (rank & 1) == 0) mbar_expect_tx(&full[kb], kExpect);
         load_w(kb, kb, n0);
       }
     }
@@ -155,7 +163,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&empty[stage], phase ^ 1);
         if (lane == 0) {
           const bool pre = t == first_tile && kb < npre;  // W of this stage is already on its way
-          if (!pre && (!TWO || rank == 0)) mbar_expect_tx(&full[stage], kExpect);
+          if (!pre && (!TWO || (rank & 1) == 0)) mbar_expect_tx(&full[stage], kExpect);
           if constexpr (TWO) tma_load_2d_2sm(smemA + stage * Cfg::kABytes, &tmA, &full[stage], kb * BK, m0);
           else tma_load_2d(smemA + stage * Cfg::kABytes, &tmA, &full[stage], kb * BK, m0);
           if (!pre) load_w(stage, kb, n0);
@@ -167,7 +175,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1 && (!TWO || rank == 0)) {
+  } else if (warp == 1 && (!TWO || (rank & 1) == 0)) {
     // ------------------------------------------------------------ MMA issuer (TWO: the leader's only)
     constexpr uint32_t idesc = make_idesc_bf16(TWO ? 2 * BM : BM, BN, 0, 0);
     int stage = 0;
@@ -191,11 +199,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if constexpr (TWO) umma_ss2(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
             else umma_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          if constexpr (TWO) umma_commit2_mc(&empty[stage], uint16_t(3));
+          if constexpr (TWO) umma_commit2_mc(&empty[stage], uint16_t(MC == 4 ? 0xF : 3));  // every CTA that writes or is written
           else if constexpr (MC == 2) umma_commit_mc(&empty[stage], uint16_t(3));
           else umma_commit(&empty[stage]);
           if (kb == num_kb - 1) {
-            if constexpr (TWO) umma_commit2_mc(&tfull[acc], uint16_t(3));  // both CTAs' epilogues
+            if constexpr (TWO) umma_commit2_mc(&tfull[acc], uint16_t(3u << (rank & 2)));  // both CTAs' epilogues
             else umma_commit(&tfull[acc]);
           }
         }
@@ -315,7 +323,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC == 2) cluster_sync_all();  // the peer may still arrive on my barriers until here
+  if constexpr (MC >= 2) cluster_sync_all();  // the peer may still arrive on my barriers until here
   if (warp == 2) {
     tc_fence_after();
     if constexpr (TWO) tmem_dealloc2(tmem_base, Cfg::kTmemCols);
@@ -337,35 +345,55 @@ static int launch_gemm_mc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     configured = true;
   }
   const int tiles = ((s.M + BM * MC - 1) / (BM * MC)) * ((s.N + BN - 1) / BN);
-  const int slots = num_sms / MC;
+  int slots = num_sms / MC;
+  if constexpr (MC == 4) {  // clusters of 4 do not pack all GPCs: ask how many are co-resident
+    static int quads = 0;
+    if (quads == 0) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(num_sms / 4 * 4);
+      cfg.blockDim = dim3(GEMM_THREADS);
+      cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) n = num_sms / 4 - 4;
+      quads = n;
+    }
+    slots = quads;
+  }
   const int grid = (tiles < slots ? tiles : slots) * MC;
   return launch_pdl_cluster(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::kSmemBytes, stream, MC, tmA, tmB,
                             tmC, tmR, s, e);
 }
 
+// mode: 0 one CTA per tile, 1 CTA pairs with W multicast (two M = 128 MMAs, round 1), 2 CTA pairs as
+// cta_group::2 (one M = 256 MMA, W halves never duplicated in shared memory), 3 two such pairs
+// sharing every W half (cluster of 4)
 template <int BN, int EPI>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                        const CUtensorMap& tmR, GemmShape s, const EpiArgs& e, int num_sms,
-                       cudaStream_t stream, bool multicast) {
-  // CTA pairs run as cta_group::2 (one M = 256 MMA per pair, W halves never duplicated in shared
-  // memory); SDUSS_B200_NO_2CTA=1 keeps the pair on two M = 128 MMAs with W multicast (round 1)
-  static const bool two = []() { const char* v = getenv("SDUSS_B200_NO_2CTA"); return !(v && v[0] == '1'); }();
-  if (multicast && two) return launch_gemm_mc<BN, EPI, 2, true>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
-  return multicast ? launch_gemm_mc<BN, EPI, 2>(tmA, tmB, tmC, tmR, s, e, num_sms, stream)
-                   : launch_gemm_mc<BN, EPI, 1>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
+                       cudaStream_t stream, int mode) {
+  switch (mode) {
+    case 3: return launch_gemm_mc<BN, EPI, 4, true>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
+    case 2: return launch_gemm_mc<BN, EPI, 2, true>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
+    case 1: return launch_gemm_mc<BN, EPI, 2>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
+    default: return launch_gemm_mc<BN, EPI, 1>(tmA, tmB, tmC, tmR, s, e, num_sms, stream);
+  }
 }
 
 template <int BN>
 static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
                         const CUtensorMap& tmC, const CUtensorMap& tmR, GemmShape s,
-                        const EpiArgs& e, int num_sms, cudaStream_t stream, bool multicast) {
+                        const EpiArgs& e, int num_sms, cudaStream_t stream, int mode) {
   switch (epi) {
-    case EPI_BIAS: return launch_gemm<BN, EPI_BIAS>(tmA, tmB, tmC, tmR, s, e, num_sms, stream, multicast);
-    case EPI_GELU_TANH: return launch_gemm<BN, EPI_GELU_TANH>(tmA, tmB, tmC, tmR, s, e, num_sms, stream, multicast);
-    case EPI_GATE_RESID: return launch_gemm<BN, EPI_GATE_RESID>(tmA, tmB, tmC, tmR, s, e, num_sms, stream, multicast);
-    case EPI_QK_RMSNORM: return launch_gemm<BN, EPI_QK_RMSNORM>(tmA, tmB, tmC, tmR, s, e, num_sms, stream, multicast);
-    case EPI_GEGLU: return launch_gemm<BN, EPI_GEGLU>(tmA, tmB, tmC, tmR, s, e, num_sms, stream, multicast);
-    case EPI_ROWVEC: return launch_gemm<BN, EPI_ROWVEC>(tmA, tmB, tmC, tmR, s, e, num_sms, stream, multicast);
+    case EPI_BIAS: return launch_gemm<BN, EPI_BIAS>(tmA, tmB, tmC, tmR, s, e, num_sms, stream, mode);
+    case EPI_GELU_TANH: return launch_gemm<BN, EPI_GELU_TANH>(tmA, tmB, tmC, tmR, s, e, num_sms, stream, mode);
+    case EPI_GATE_RESID: return launch_gemm<BN, EPI_GATE_RESID>(tmA, tmB, tmC, tmR, s, e, num_sms, stream, mode);
+    case EPI_QK_RMSNORM: return launch_gemm<BN, EPI_QK_RMSNORM>(tmA, tmB, tmC, tmR, s, e, num_sms, stream, mode);
+    case EPI_GEGLU: return launch_gemm<BN, EPI_GEGLU>(tmA, tmB, tmC, tmR, s, e, num_sms, stream, mode);
+    case EPI_ROWVEC: return launch_gemm<BN, EPI_ROWVEC>(tmA, tmB, tmC, tmR, s, e, num_sms, stream, mode);
     default: return B200_ERR_INVALID;
   }
 }
@@ -417,13 +445,19 @@ extern "C" int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
   static const bool mc_allowed = []() { const char* v = getenv("SDUSS_B200_NO_MULTICAST"); return !(v && v[0] == '1'); }();
   const long pair_tiles = long((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
   const bool multicast = mc_allowed && M > BM && pair_tiles >= (sms / 2) / 2;
+  // SDUSS_B200_NO_2CTA=1 / SDUSS_B200_QUAD=1 are read per call: A/B runs flip them inside one process
+  const char* no2 = getenv("SDUSS_B200_NO_2CTA");
+  const char* qd = getenv("SDUSS_B200_QUAD");
+  const bool two = multicast && !(no2 && no2[0] == '1');
+  const bool quad = two && qd && qd[0] == '1' && M > 2 * BM && ep->row_mask == nullptr;
+  const int mode = quad ? 3 : two ? 2 : multicast ? 1 : 0;
   CUtensorMap tmA, tmB;
   uint64_t dA[2] = {uint64_t(K), uint64_t(M)}, sA[1] = {uint64_t(lda) * 2};
   uint32_t bA[2] = {BK, BM};
   int rc = get_tmap_bf16_sw128(&tmA, A, 2, dA, sA, bA);
   if (rc) return rc;
   uint64_t dB[2] = {uint64_t(K), uint64_t(N)}, sB[1] = {uint64_t(ldw) * 2};
-  uint32_t bB[2] = {BK, uint32_t(multicast ? BN / 2 : BN)};
+  uint32_t bB[2] = {BK, uint32_t(quad ? BN / 4 : multicast ? BN / 2 : BN)};
   rc = get_tmap_bf16_sw128(&tmB, W, 2, dB, sB, bB);
   if (rc) return rc;
 
@@ -480,7 +514,7 @@ extern "C" int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
       if (rc) return rc;
     }
   }
-  if (BN == 256) return dispatch_epi<256>(epi_mode, tmA, tmB, tmC, tmR, s, e, sms, stream, multicast);
-  if (BN == 192) return dispatch_epi<192>(epi_mode, tmA, tmB, tmC, tmR, s, e, sms, stream, multicast);
-  return dispatch_epi<128>(epi_mode, tmA, tmB, tmC, tmR, s, e, sms, stream, multicast);
+  if (BN == 256) return dispatch_epi<256>(epi_mode, tmA, tmB, tmC, tmR, s, e, sms, stream, mode);
+  if (BN == 192) return dispatch_epi<192>(epi_mode, tmA, tmB, tmC, tmR, s, e, sms, stream, mode);
+  return dispatch_epi<128>(epi_mode, tmA, tmB, tmC, tmR, s, e, sms, stream, mode);
 }
