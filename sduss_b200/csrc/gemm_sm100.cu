@@ -42,6 +42,20 @@ struct GemmShape {
   int M, N, K;
 };
 
+#ifdef GEMM_TRACE
+// tools/gemm_trace.py: per launch (ring of 64) and for CTA 0, clock64 / globaltimer stamps of the phases
+__device__ unsigned long long g_trace[64][10];
+__device__ unsigned int g_trace_launch;
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TRACE(slot) do { if (blockIdx.x == 0) g_trace[trace_row][slot] = clock64(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
+
 // MC = 2: CTA pairs (cluster of 2 along M) share every W tile: each CTA fetches half of it and
 // multicasts it into both CTAs' shared memory, cutting L2 -> SM operand traffic by a third
 // (the 128x256x64 main loop is L2-bandwidth bound: 96 B/clk/SM of operand loads on 148 SMs).
@@ -70,6 +84,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef GEMM_TRACE
+  __shared__ unsigned int trace_row_s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    trace_row_s = atomicAdd(&g_trace_launch, 1u) & 63u;
+    g_trace[trace_row_s][0] = clock64();
+    g_trace[trace_row_s][8] = gtimer();
+  }
+  __syncthreads();
+  const unsigned int trace_row = blockIdx.x == 0 ? trace_row_s : 0;
+#endif
 
   const int tiles_n = (s.N + BN - 1) / BN;
   // MC == 2: tiles are enumerated per CTA pair; rank r of the pair owns M tile 2 * pair + r
@@ -115,6 +139,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   if constexpr (MC >= 2) cluster_sync_all();  // peer barriers are initialised before any multicast
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TRACE(1);
   pdl_launch_dependents();
   // bytes one phase of full[stage] waits for: TWO = both CTAs' A tiles and W halves, on the leader
   constexpr uint32_t kExpect = TWO ? 2u * Cfg::kStageBytes : uint32_t(Cfg::kStageBytes);
@@ -150,6 +175,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   }
   pdl_wait();  // the prologue above overlapped the previous kernel; its outputs are visible now
+  if (threadIdx.x == 0) TRACE(2);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -190,6 +216,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
+        if (lane == 0 && t == first_tile && kb == 0) TRACE(3);
+        if (lane == 0 && t == first_tile && kb == num_kb - 1) TRACE(4);
         if (lane == 0) {
           const uint64_t da = make_sdesc_sw128(smem_u32(smemA + stage * Cfg::kABytes));
           const uint64_t db = make_sdesc_sw128(smem_u32(smemB + stage * Cfg::kBBytes));
@@ -267,6 +295,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
+      if (leader && t == first_tile) TRACE(5);
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
@@ -319,6 +348,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ++it;
     }
     if (leader) tma_store_wait<0>();
+    if (leader) TRACE(6);
   }
 
   tc_fence_before();
@@ -329,6 +359,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if constexpr (TWO) tmem_dealloc2(tmem_base, Cfg::kTmemCols);
     else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+#ifdef GEMM_TRACE
+  if (threadIdx.x == 64 && blockIdx.x == 0) { g_trace[trace_row][7] = clock64(); g_trace[trace_row][9] = gtimer(); }
+#endif
 }
 
 template <int BN, int EPI, int MC, bool TWO = false>
@@ -518,3 +551,11 @@ extern "C" int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
   if (BN == 192) return dispatch_epi<192>(epi_mode, tmA, tmB, tmC, tmR, s, e, sms, stream, mode);
   return dispatch_epi<128>(epi_mode, tmA, tmB, tmC, tmR, s, e, sms, stream, mode);
 }
+
+#ifdef GEMM_TRACE
+extern "C" int b200_debug_gemm_trace(unsigned long long* out /* [64][10] */, unsigned int* n_launches) {
+  cudaError_t e1 = cudaMemcpyFromSymbol(out, b200::g_trace, sizeof(unsigned long long) * 640);
+  cudaError_t e2 = cudaMemcpyFromSymbol(n_launches, b200::g_trace_launch, sizeof(unsigned int));
+  return (e1 == cudaSuccess && e2 == cudaSuccess) ? 0 : 1;
+}
+#endif
