@@ -285,7 +285,9 @@ int b200_conv3x3_bf16(const void* in_maps_dev, const void* out_maps_dev,
  * (kernels/norm_silu_concat.cu:41,361,87; pybind `groupnorm`, norm_silu_concat.cpp:66-86)
  * without their approximated variance (D1), in-place race and per-call device syncs.
  * Every latent's pixel count must be a multiple of 64. lat_chunks: int32 [n][4] = {first
- * 64-row chunk, number of chunks, 0, 0}; workspace: b200_groupnorm_workspace_bytes() bytes. */
+ * 64-row chunk, number of chunks, 0, 0}; workspace: b200_groupnorm_workspace_bytes() bytes, ZEROED once
+ * by the caller before its first use and not written by anything else (it carries the epoch of the
+ * grid barrier of the single-launch kernel across calls); one workspace per stream. */
 long long b200_groupnorm_workspace_bytes(long long total_rows, int n_latents);
 int b200_groupnorm_nhwc_bf16(const void* x, int ldx, long long T, int C, int groups, float eps,
                              const void* gamma, const void* beta, const int32_t* row_group,

@@ -3,6 +3,8 @@
 // (NHWC -> NCHW), nearest 2x upsample, column-block copy (skip concat), and the reference's own
 // patch pack/scatter format (split_sample / concat_sample) for index-exact interoperability.
 #include "../../include/sduss_b200.h"
+#include <cstdlib>
+
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -64,20 +66,18 @@ inline GnMap gn_map(int C, int G) {
   return m;
 }
 
-__global__ void __launch_bounds__(GN_THREADS, 5) gn_stats_kernel(const __nv_bfloat16* x, int ldx,
-                                                                 int W, int RL, int cpg,
-                                                                 int gps, int n_chunks,
-                                                                 float* partial) {
-  __shared__ float ch_sum[GN_THREADS * 8], ch_sq[GN_THREADS * 8];  // [RL][W * 8]
-  pdl_launch_dependents();
-  const int chunk = blockIdx.x, slice = blockIdx.y;
+// ---- the three phases as device functions: the three-launch path and the single-launch kernel below
+// run the SAME code per (chunk, slice) / per (latent, group), so a latent's result does not depend on
+// which of the two ran (the choice is a function of the batch size).
+__device__ __forceinline__ void gn_stats_item(const __nv_bfloat16* x, int ldx, int W, int RL, int cpg,
+                                              int gps, int n_chunks, float* partial, int chunk, int slice,
+                                              float* ch_sum, float* ch_sq) {
   const int rl = threadIdx.x / W, col = threadIdx.x - rl * W;
   const int CW = W * 8;  // channels of the slice
   const __nv_bfloat16* base = x + size_t(chunk) * GN_CHUNK * ldx + size_t(slice) * CW + col * 8;
   float sum[8], sq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
-  pdl_wait();
   uint4 v[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -134,22 +134,27 @@ __global__ void __launch_bounds__(GN_THREADS, 5) gn_stats_kernel(const __nv_bflo
   }
 }
 
-// lat: [L][4] = {first 64-row chunk, number of chunks, 0, 0}. One warp per (latent, group): lanes
-// stride the latent's chunks (coalesced float2 reads), then a fixed-order fp64 shuffle tree.
-__global__ void gn_finalize_kernel(const float* partial, const int4* lat, int L, int G, int cpg,
-                                   int n_chunks, float eps, float* stats) {
+__global__ void __launch_bounds__(GN_THREADS, 5) gn_stats_kernel(const __nv_bfloat16* x, int ldx,
+                                                                 int W, int RL, int cpg,
+                                                                 int gps, int n_chunks,
+                                                                 float* partial) {
+  __shared__ float ch_sum[GN_THREADS * 8], ch_sq[GN_THREADS * 8];  // [RL][W * 8]
   pdl_launch_dependents();
   pdl_wait();
-  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (idx >= L * G) return;
+  gn_stats_item(x, ldx, W, RL, cpg, gps, n_chunks, partial, blockIdx.x, blockIdx.y, ch_sum, ch_sq);
+}
+
+// lat: [L][4] = {first 64-row chunk, number of chunks, 0, 0}. One warp per (latent, group): lanes
+// stride the latent's chunks (coalesced float2 reads), then a fixed-order fp64 shuffle tree.
+__device__ __forceinline__ void gn_finalize_one(const float* partial, const int4* lat, int G, int cpg,
+                                                int n_chunks, float eps, float* stats, int idx, int lane) {
   const int l = idx / G, g = idx % G;
   const int4 d = lat[l];
   const float2* p = reinterpret_cast<const float2*>(partial) + size_t(g) * n_chunks + d.x;
   double s = 0.0, q = 0.0;
 #pragma unroll 4
   for (int c = lane; c < d.y; c += 32) {
-    const float2 v = p[c];
+    const float2 v = __ldcg(p + c);  // written by other SMs (of this launch, in the single-launch kernel)
     s += double(v.x);
     q += double(v.y);
   }
@@ -166,6 +171,15 @@ __global__ void gn_finalize_kernel(const float* partial, const int4* lat, int L,
     stats[idx * 2] = float(mean);
     stats[idx * 2 + 1] = float(1.0 / sqrt(var + double(eps)));
   }
+}
+
+__global__ void gn_finalize_kernel(const float* partial, const int4* lat, int L, int G, int cpg,
+                                   int n_chunks, float eps, float* stats) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (idx >= L * G) return;
+  gn_finalize_one(partial, lat, G, cpg, n_chunks, eps, stats, idx, threadIdx.x & 31);
 }
 
 // Finalize from the statistics the producing convolution left behind (conv_sm100.cu, stats_out):
@@ -216,20 +230,14 @@ __global__ void __launch_bounds__(256) gn_finalize_tiles_kernel(const float2* pa
 // has just streamed x front to back, so its tail is what the 126 MB L2 still holds when x is larger
 // than L2 (and the whole of x when it is not).
 template <bool SILU>
-__global__ void __launch_bounds__(GN_THREADS, 4) gn_apply_kernel(
-    const __nv_bfloat16* x, int ldx, int W, int RL, int cpg, int G, int n_chunks,
-    const float* stats, const int* row_group, const __nv_bfloat16* gamma,
-    const __nv_bfloat16* beta, __nv_bfloat16* y, int ldy) {
-  pdl_launch_dependents();
-  const int rl = threadIdx.x / W, col = threadIdx.x - rl * W;
-  const int ch0 = (blockIdx.y * W + col) * 8;  // first channel of this thread's vector
-  const size_t row0 = size_t(n_chunks - 1 - int(blockIdx.x)) * GN_CHUNK;
+__device__ __forceinline__ void gn_apply_item(const __nv_bfloat16* x, int ldx, int W, int RL, int cpg, int G,
+                                              const float* stats, const int* row_group,
+                                              const float* a0, const float* b0, __nv_bfloat16* y, int ldy,
+                                              int chunk, int ch0) {
+  const int rl = threadIdx.x / W;
+  const size_t row0 = size_t(chunk) * GN_CHUNK;
   const __nv_bfloat16* xb = x + row0 * ldx + ch0;
   __nv_bfloat16* yb = y + row0 * ldy + ch0;
-  float a[8], b[8];
-  unpack8s(*reinterpret_cast<const uint4*>(gamma + ch0), a);  // parameters: not written by the
-  unpack8s(*reinterpret_cast<const uint4*>(beta + ch0), b);   // preceding kernels
-  pdl_wait();
   uint4 v[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {  // first rows in flight while a, b are folded
@@ -237,11 +245,12 @@ __global__ void __launch_bounds__(GN_THREADS, 4) gn_apply_kernel(
     if (r < GN_CHUNK) v[k] = *reinterpret_cast<const uint4*>(xb + size_t(r) * ldx);
   }
   const float* st = stats + size_t(row_group[row0]) * G * 2;
+  float a[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float2 mr = *reinterpret_cast<const float2*>(st + ((ch0 + j) / cpg) * 2);
-    a[j] *= mr.y;
-    b[j] = fmaf(-mr.x, a[j], b[j]);
+    const float2 mr = __ldcg(reinterpret_cast<const float2*>(st + ((ch0 + j) / cpg) * 2));
+    a[j] = a0[j] * mr.y;
+    b[j] = fmaf(-mr.x, a[j], b0[j]);
     if (SILU) {
       a[j] *= 0.5f;
       b[j] *= 0.5f;
@@ -269,6 +278,91 @@ __global__ void __launch_bounds__(GN_THREADS, 4) gn_apply_kernel(
       const int r = r0 + k * RL;
       if (r < GN_CHUNK) v[k] = *reinterpret_cast<const uint4*>(xb + size_t(r) * ldx);
     }
+  }
+}
+
+template <bool SILU>
+__global__ void __launch_bounds__(GN_THREADS, 4) gn_apply_kernel(
+    const __nv_bfloat16* x, int ldx, int W, int RL, int cpg, int G, int n_chunks,
+    const float* stats, const int* row_group, const __nv_bfloat16* gamma,
+    const __nv_bfloat16* beta, __nv_bfloat16* y, int ldy) {
+  pdl_launch_dependents();
+  const int col = threadIdx.x % W;
+  const int ch0 = (blockIdx.y * W + col) * 8;  // first channel of this thread's vector
+  float a[8], b[8];
+  unpack8s(*reinterpret_cast<const uint4*>(gamma + ch0), a);  // parameters: not written by the
+  unpack8s(*reinterpret_cast<const uint4*>(beta + ch0), b);   // preceding kernels
+  pdl_wait();
+  gn_apply_item<SILU>(x, ldx, W, RL, cpg, G, stats, row_group, a, b, y, ldy, n_chunks - 1 - int(blockIdx.x), ch0);
+}
+
+// ---- single launch: statistics -> grid barrier -> finalize -> grid barrier -> apply, by a grid that
+// is co-resident by construction (host: grid <= occupancy x SMs; every CTA runs
+// griddepcontrol.launch_dependents first, so the next kernel cannot take a slot before all CTAs of
+// this one are running). The barrier costs no atomics: CTA b stores the epoch into flag[b], CTA 0
+// polls the flags (coalesced) and publishes the epoch in `gen`, everyone else polls `gen`
+// (~1 us per barrier; 444 atomics on one word would serialise to ~6 us). bar[0] = gen, bar[1 + b] =
+// flags; zero-initialised once by the caller, the epoch keeps counting across launches.
+// The second read of x comes from L2 whenever the tensor fits (<= ~100 MB), walked in reverse order.
+__device__ __forceinline__ void gn_grid_barrier(volatile unsigned int* bar, unsigned int epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    bar[1 + blockIdx.x] = epoch;
+  }
+  if (blockIdx.x == 0) {
+    for (int b = threadIdx.x; b < int(gridDim.x); b += blockDim.x)
+      while (bar[1 + b] != epoch) {
+      }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      bar[0] = epoch;
+    }
+  } else if (threadIdx.x == 0) {
+    while (bar[0] != epoch) {
+    }
+  }
+  __syncthreads();
+  __threadfence();
+}
+
+template <bool SILU>
+__global__ void __launch_bounds__(GN_THREADS, 3) gn_fused_kernel(
+    const __nv_bfloat16* x, int ldx, int W, int RL, int cpg, int G, int S, int n_chunks, int L, float eps,
+    const int4* lat, const int* row_group, const __nv_bfloat16* gamma, const __nv_bfloat16* beta,
+    __nv_bfloat16* y, int ldy, float* partial, float* stats, unsigned int* bar) {
+  __shared__ float ch_sum[GN_THREADS * 8], ch_sq[GN_THREADS * 8];
+  pdl_launch_dependents();
+  const int n_items = n_chunks * S;
+  pdl_wait();
+  // last epoch of the previous launch on this workspace (complete and flushed: read after the wait);
+  // CTA 0 publishes epoch0 + 1 only after every CTA has stored its flag, i.e. has read epoch0
+  const unsigned int epoch0 = *reinterpret_cast<volatile unsigned int*>(bar);
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    gn_stats_item(x, ldx, W, RL, cpg, G / S, n_chunks, partial, it / S, it % S, ch_sum, ch_sq);
+    __syncthreads();
+  }
+  gn_grid_barrier(bar, epoch0 + 1);
+  {
+    const int nw = blockDim.x >> 5, w = threadIdx.x >> 5;  // full warps only
+    if (w < nw)
+      for (int idx = blockIdx.x * nw + w; idx < L * G; idx += gridDim.x * nw)
+        gn_finalize_one(partial, lat, G, cpg, n_chunks, eps, stats, idx, threadIdx.x & 31);
+  }
+  gn_grid_barrier(bar, epoch0 + 2);
+  const int col = threadIdx.x % W;
+  int last_slice = -1;
+  float a[8], b[8];
+  for (int it = n_items - 1 - int(blockIdx.x); it >= 0; it -= gridDim.x) {
+    const int chunk = it / S, slice = it % S;
+    const int ch0 = (slice * W + col) * 8;
+    if (slice != last_slice) {
+      unpack8s(*reinterpret_cast<const uint4*>(gamma + ch0), a);
+      unpack8s(*reinterpret_cast<const uint4*>(beta + ch0), b);
+      last_slice = slice;
+    }
+    gn_apply_item<SILU>(x, ldx, W, RL, cpg, G, stats, row_group, a, b, y, ldy, chunk, ch0);
   }
 }
 
@@ -380,8 +474,30 @@ using namespace b200;
 typedef __nv_bfloat16 bf16;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
+constexpr int GN_MAX_GRID = 1023;  // CTAs of the single-launch kernel (flags of its grid barrier)
 extern "C" long long b200_groupnorm_workspace_bytes(long long total_rows, int n_latents) {
-  return (total_rows / GN_CHUNK) * GN_MAXG * 2 * 4 + (long long)n_latents * GN_MAXG * 2 * 4;
+  return (total_rows / GN_CHUNK) * GN_MAXG * 2 * 4 + (long long)n_latents * GN_MAXG * 2 * 4 +
+         (1 + GN_MAX_GRID) * 4;
+}
+
+// co-resident CTAs of gn_fused_kernel<SILU> with `threads` threads (queried once per variant)
+template <bool SILU>
+static int gn_fused_capacity(int threads) {
+  static int per_sm[GN_THREADS / 32 + 1] = {0};
+  int& v = per_sm[(threads + 31) / 32];
+  if (v == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gn_fused_kernel<SILU>, threads, 0) != cudaSuccess || n <= 0)
+      n = -1;
+    v = n;
+  }
+  if (v <= 0) return 0;
+  // two CTAs per SM: enough loads in flight for the HBM-bound passes (296 x 256 x 64 B), and half of what
+  // fits, so that two such kernels on different streams are always co-resident together (a third
+  // concurrent one could starve the barriers: one GroupNorm stream per workspace, two per device)
+  const int per = v < 2 ? v : 2;
+  const int cap = per * device_sm_count();
+  return cap < GN_MAX_GRID ? cap : GN_MAX_GRID;
 }
 
 extern "C" int b200_groupnorm_nhwc_bf16(const void* x, int ldx, long long T, int C, int groups,
@@ -399,6 +515,24 @@ extern "C" int b200_groupnorm_nhwc_bf16(const void* x, int ldx, long long T, int
   if (m.RL < 1) return B200_ERR_INVALID;
   float* partial = static_cast<float*>(workspace);
   float* stats = partial + size_t(chunks) * GN_MAXG * 2;
+  // SDUSS_B200_GN_FUSED=1: one launch (statistics, finalize and apply around two grid barriers). Same
+  // arithmetic per chunk / per (latent, group), bit-identical results -- and measured SLOWER than the
+  // three launches (profiles/r02_gn_single_launch.txt: a barrier costs what a kernel boundary costs,
+  // and 2 CTAs per SM keep fewer loads in flight than the 4-5 of the separate kernels), so it is off.
+  {
+    const char* vf = getenv("SDUSS_B200_GN_FUSED");
+    const int cap = !(vf && vf[0] == '1') ? 0 : silu ? gn_fused_capacity<true>(m.threads) : gn_fused_capacity<false>(m.threads);
+    if (cap > 0) {
+      const long items = long(chunks) * m.S;
+      const int grid = int(items < cap ? items : cap);
+      unsigned int* bar = reinterpret_cast<unsigned int*>(stats + size_t(n_latents) * GN_MAXG * 2);
+      auto fk = silu ? gn_fused_kernel<true> : gn_fused_kernel<false>;
+      return launch_pdl(fk, dim3(grid), dim3(m.threads), 0, ST(stream), static_cast<const bf16*>(x), ldx, m.W,
+                        m.RL, cpg, groups, m.S, chunks, n_latents, eps, reinterpret_cast<const int4*>(lat_chunks),
+                        row_group, static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta),
+                        static_cast<bf16*>(y), ldy, partial, stats, bar);
+    }
+  }
   int rc = launch_pdl(gn_stats_kernel, dim3(chunks, m.S), dim3(m.threads), 0, ST(stream),
                       static_cast<const bf16*>(x), ldx, m.W, m.RL, cpg, groups / m.S, chunks,
                       partial);

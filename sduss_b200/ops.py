@@ -691,7 +691,7 @@ def conv3x3(maps_dev, tiles, n_mtiles, out_lat, cin, cout, stride, weight, out, 
 
 def groupnorm_workspace(total_rows, n_latents, device):
     n = lib.b200_groupnorm_workspace_bytes(total_rows, n_latents)
-    return torch.empty(n, dtype=torch.uint8, device=device)
+    return torch.zeros(n, dtype=torch.uint8, device=device)   # zeroed once: epoch / flags of the grid barrier
 
 
 def groupnorm_nhwc(x, y, gamma, beta, row_group, lat_chunks, n_latents, workspace, *, groups=32,

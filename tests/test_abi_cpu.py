@@ -49,7 +49,7 @@ def test_invalid_arguments_are_rejected_without_a_device():
     lib = _lib.lib
     assert lib.b200_gemm_bf16(None, 0, None, 0, 0, 0, 0, 0, None, None) == _lib.ERR_INVALID
     assert lib.b200_silu_bf16(None, None, 8, None) == _lib.ERR_INVALID
-    assert lib.b200_groupnorm_workspace_bytes(128, 2) == 2 * 32 * 2 * 4 + 2 * 32 * 2 * 4
+    assert lib.b200_groupnorm_workspace_bytes(128, 2) == 2 * 32 * 2 * 4 + 2 * 32 * 2 * 4 + 1024 * 4  # + grid-barrier words
     assert lib.b200_attn_workspace_bytes() == 8 and lib.b200_conv3x3_maps_bytes(3) == 384
     assert lib.b200_patch_mask_workspace_bytes(10) == 10 * (16 * 4 + 4)
 

@@ -102,6 +102,32 @@ def test_groupnorm(cuda, sizes, C, silu, eps):
     assert torch.equal(y, y2)  # deterministic (no atomics)
 
 
+@pytest.mark.parametrize("sizes,C", [([(32, 32), (64, 64)], 1280), ([(128, 128), (64, 64), (128, 128)], 320),
+                                     ([(256, 256)], 128), ([(8, 8)], 64)])
+def test_groupnorm_single_launch_equals_three_launches(cuda, sizes, C, monkeypatch):
+    """The opt-in single-launch kernel (statistics -> grid barrier -> finalize -> grid barrier -> apply; persistent
+    grid, several items per CTA on the larger tensors) runs the same arithmetic as the three-launch path:
+    bit-identical, also when repeated on one workspace (the barrier epoch keeps counting)."""
+    from sduss_b200 import ops
+    from sduss_b200.layout import LevelLayout
+    lats = [(_rand((C, h, w), 70 + i) * (1 + i) - 0.3 * i).bfloat16().float() for i, (h, w) in enumerate(sizes)]
+    gam, bet = (1 + 0.1 * _rand((C,), 5)).cuda().bfloat16(), _rand((C,), 6).cuda().bfloat16()
+    lay = LevelLayout(sizes, cuda)
+    x = _pack(lats).cuda().bfloat16().contiguous()
+    ws = ops.groupnorm_workspace(lay.T, lay.L, cuda)
+    outs = []
+    for mode in ("1", "0", "1", "1"):
+        monkeypatch.setenv("SDUSS_B200_GN_FUSED", mode)
+        y = torch.empty_like(x)
+        ops.groupnorm_nhwc(x, y, gam, bet, lay.row_group, lay.lat_chunks, lay.L, ws, silu=True)
+        torch.cuda.synchronize()
+        outs.append(y)
+    for y in outs[1:]:
+        assert torch.equal(outs[0], y)
+    ref = _pack([F.silu(F.group_norm(t[None], 32, gam.float().cpu(), bet.float().cpu(), 1e-5)[0]) for t in lats])
+    assert (outs[0].float().cpu() - ref).abs().max().item() < 4e-2
+
+
 @pytest.mark.parametrize("C", [320, 1280])
 def test_groupnorm_batch_invariant(cuda, C):
     """A latent's GroupNorm output must not depend on the latents packed around it (the launch
