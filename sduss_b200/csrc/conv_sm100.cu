@@ -25,15 +25,19 @@ constexpr int CV_BM = 128, CV_BK = 64, CV_TW = 8, CV_TH = 16, CV_THREADS = 256;
 // weight tile per k-step. A 128 x 128 tile loads 32 KB of operands per 2.1 MFLOP, more than L2
 // delivers per SM (the 128-channel convolutions of the VAE decoder ran at 0.8 PFLOP/s); with two
 // M tiles the ratio is that of the 128 x 256 configuration (48 KB per 4.2 MFLOP).
-template <int BN, int EPI, int MT = 1>
+// TWO: a CTA pair (cluster of 2) runs one tcgen05.mma.cta_group::2 of M = 256 per K step: each CTA gathers
+// ITS pixel block (one M tile) and keeps half of the weight tile (gemm_sm100.cu, same scheme): 16 KB +
+// BN x 64 B per stage, 6-8 stages, and the W bytes through L2 -> SM halve.
+template <int BN, int EPI, int MT = 1, bool TWO = false>
 struct ConvCfg {
   static_assert(MT == 1 || BN == 128, "two M tiles: 2 x 2 x 128 TMEM columns");
+  static_assert(!TWO || MT == 1, "the pair already covers two M tiles");
   // residual chunks are TMA-loaded into the output staging tiles and updated in place (see
   // gemm_sm100.cu): the residual epilogue costs no pipeline stage
-  static constexpr int kStages = (BN == 256 || MT == 2) ? 4 : 5;
+  static constexpr int kStages = TWO ? (BN == 256 ? 6 : 8) : (BN == 256 || MT == 2) ? 4 : 5;
   static constexpr int kATile = CV_BM * CV_BK * 2;
   static constexpr int kABytes = MT * kATile;
-  static constexpr int kBBytes = BN * CV_BK * 2;
+  static constexpr int kBBytes = (TWO ? BN / 2 : BN) * CV_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSmemBytes =
       kStages * kStageBytes + 2 * EPI_STAGE_BYTES + 1024 + 256;
@@ -49,10 +53,10 @@ struct ConvArgs {
   int n_mtiles, Cin, Cout, stride;
 };
 
-template <int BN, int EPI, int MT>
+template <int BN, int EPI, int MT, bool TWO>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, int M_total) {
-  using Cfg = ConvCfg<BN, EPI, MT>;
+  using Cfg = ConvCfg<BN, EPI, MT, TWO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
@@ -70,8 +74,13 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_n = (a.Cout + BN - 1) / BN;
-  const int m_items = (a.n_mtiles + MT - 1) / MT;  // work item = MT consecutive M tiles x one N tile
+  // work item = MT consecutive M tiles x one N tile; TWO: the pair's item = 2 M tiles (one per CTA)
+  constexpr int MTI = TWO ? 2 : MT;
+  const int m_items = (a.n_mtiles + MTI - 1) / MTI;
   const int num_tiles = m_items * tiles_n;
+  const int rank = TWO ? int(cluster_ctarank()) : 0;
+  const int first_tile = TWO ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int tile_step = TWO ? int(gridDim.x >> 1) : int(gridDim.x);
   const int cblocks = a.Cin / CV_BK;
   const int num_kb = 9 * cblocks;
 
@@ -83,36 +92,72 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], TWO ? 8 : 4);  // TWO: the epilogue warps of both CTAs release the leader's
       mbar_init(&rfull[i], 1);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (TWO) {
+      tmem_alloc2(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if constexpr (TWO) cluster_sync_all();  // the peer's barriers exist before anything signals them
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
+  // bytes one phase of full[stage] waits for (TWO: on the leader, both CTAs' loads; the second CTA of
+  // the last pair may have no pixel block)
+  auto expect_bytes = [&](int t) -> uint32_t {
+    if constexpr (TWO) {
+      const bool peer = (t / tiles_n) * 2 + 1 < a.n_mtiles;
+      return uint32_t((peer ? 2 : 1) * Cfg::kATile + 2 * Cfg::kBBytes);
+    } else {
+      return uint32_t(min(MT, a.n_mtiles - (t / tiles_n) * MT) * Cfg::kATile + Cfg::kBBytes);
+    }
+  };
+  auto load_w = [&](int stage, int kb, int n0) {
+    if constexpr (TWO) tma_load_2d_2sm(smemB + stage * Cfg::kBBytes, &tmW, &full[stage], kb * CV_BK, n0 + rank * (BN / 2));
+    else tma_load_2d(smemB + stage * Cfg::kBBytes, &tmW, &full[stage], kb * CV_BK, n0);
+  };
+  // the weight tiles of the first ring stages are requested before the wait on the previous kernel
+  // (weights are never written on the stream; see gemm_sm100.cu): their HBM latency runs under its tail
+  int npre = 0;
+  if (warp == 0 && first_tile < num_tiles) {
+    npre = num_kb < Cfg::kStages ? num_kb : Cfg::kStages;
+    if (lane == 0) {
+      const int t = first_tile;
+      const int n0 = (t % tiles_n) * BN;
+      for (int kb = 0; kb < npre; ++kb) {
+        if (rank == 0) mbar_expect_tx(&full[kb], expect_bytes(t));
+        load_w(kb, kb, n0);
+      }
+    }
+    __syncwarp();
+  }
   pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t / tiles_n) * MT;
-      const int nmt = min(MT, a.n_mtiles - m0);
+    for (int t = first_tile; t < num_tiles; t += tile_step) {
+      const int m0 = TWO ? (t / tiles_n) * 2 + rank : (t / tiles_n) * MT;
+      const int nmt = TWO ? (m0 < a.n_mtiles ? 1 : 0) : min(MT, a.n_mtiles - m0);
       const int n0 = (t % tiles_n) * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * CV_BK;
         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
         mbar_wait(&empty[stage], phase ^ 1);
         if (lane == 0) {
-          mbar_expect_tx(&full[stage], nmt * Cfg::kATile + Cfg::kBBytes);
+          const bool pre = t == first_tile && kb < npre;  // W of this stage is already on its way
+          if (!pre && rank == 0) mbar_expect_tx(&full[stage], expect_bytes(t));
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
             if (mt < nmt) {
@@ -120,33 +165,36 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
               const CUtensorMap* im = a.in_maps + tl.x;
               void* dstA = smemA + stage * Cfg::kABytes + mt * Cfg::kATile;
               if (a.stride == 1) {
-                tma_load_3d(dstA, im, &full[stage], c0, tl.z + dx, tl.y + dy);
+                if constexpr (TWO) tma_load_3d_2sm(dstA, im, &full[stage], c0, tl.z + dx, tl.y + dy);
+                else tma_load_3d(dstA, im, &full[stage], c0, tl.z + dx, tl.y + dy);
               } else {
                 // input pixel (2y+dy, 2x+dx) = (parity, half index): -1 -> (1, i-1); 0 -> (0, i); 1 -> (1, i)
                 const int py = dy == 0 ? 0 : 1, px = dx == 0 ? 0 : 1;
-                tma_load_5d(dstA, im, &full[stage], c0, px, tl.z + (dx < 0 ? -1 : 0), py,
-                            tl.y + (dy < 0 ? -1 : 0));
+                if constexpr (TWO)
+                  tma_load_5d_2sm(dstA, im, &full[stage], c0, px, tl.z + (dx < 0 ? -1 : 0), py, tl.y + (dy < 0 ? -1 : 0));
+                else
+                  tma_load_5d(dstA, im, &full[stage], c0, px, tl.z + (dx < 0 ? -1 : 0), py, tl.y + (dy < 0 ? -1 : 0));
               }
             }
           }
-          tma_load_2d(smemB + stage * Cfg::kBBytes, &tmW, &full[stage], kb * CV_BK, n0);
+          if (!pre) load_w(stage, kb, n0);
         }
         __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(CV_BM, BN, 0, 0);
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (TWO: the leader's only)
+    constexpr uint32_t idesc = make_idesc_bf16(TWO ? 2 * CV_BM : CV_BM, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = first_tile; t < num_tiles; t += tile_step, ++it) {
       const int acc = it & 1;
       mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * (MT * BN);
-      const int nmt = min(MT, a.n_mtiles - (t / tiles_n) * MT);
+      const int nmt = TWO ? 1 : min(MT, a.n_mtiles - (t / tiles_n) * MT);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
@@ -157,13 +205,19 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
             if (mt < nmt) {
               const uint64_t da = make_sdesc_sw128(smem_u32(smemA + stage * Cfg::kABytes + mt * Cfg::kATile));
 #pragma unroll
-              for (int k = 0; k < CV_BK / 16; ++k)
-                umma_ss(d_tmem + mt * BN, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc,
-                        (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < CV_BK / 16; ++k) {
+                if constexpr (TWO) umma_ss2(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                else umma_ss(d_tmem + mt * BN, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+              }
             }
           }
-          umma_commit(&empty[stage]);
-          if (kb == num_kb - 1) umma_commit(&tfull[acc]);
+          if constexpr (TWO) {
+            umma_commit2_mc(&empty[stage], uint16_t(3));
+            if (kb == num_kb - 1) umma_commit2_mc(&tfull[acc], uint16_t(3));
+          } else {
+            umma_commit(&empty[stage]);
+            if (kb == num_kb - 1) umma_commit(&tfull[acc]);
+          }
         }
         __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -183,11 +237,14 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
     // chunk has been staged). Seen as corrupted tail columns on short-K GEMMs (conv_in: K = 64).
     uint32_t chunk_ctr = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = first_tile; t < num_tiles; t += tile_step, ++it) {
       const int acc = it & 1;
-      const int m0 = (t / tiles_n) * MT;
-      const int nmt = min(MT, a.n_mtiles - m0);
+      const int m0 = TWO ? (t / tiles_n) * 2 + rank : (t / tiles_n) * MT;
+      const int nmt = TWO ? (m0 < a.n_mtiles ? 1 : 0) : min(MT, a.n_mtiles - m0);
       const int n0 = (t % tiles_n) * BN;
+      if (TWO && nmt == 0) {  // the last pair's second CTA without a pixel block: hand the accumulator back
+        mbar_wait(&tfull[acc], (it >> 1) & 1);
+      }
 #pragma unroll 1
       for (int mt = 0; mt < nmt; ++mt) {
         const int4 tl = a.tiles[m0 + mt];
@@ -278,24 +335,29 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if constexpr (TWO) mbar_arrive_leader(&tempty[acc]);
+        else mbar_arrive(&tempty[acc]);
+      }
     }
     if (leader) tma_store_wait<0>();
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (TWO) cluster_sync_all();  // the peer may still signal my barriers / read my tiles until here
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (TWO) tmem_dealloc2(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BN, int EPI, int MT>
+template <int BN, int EPI, int MT, bool TWO = false>
 static int launch_conv(const CUtensorMap& tmW, const ConvArgs& a, const EpiArgs& e, int M_total,
                        int num_sms, cudaStream_t stream) {
-  using Cfg = ConvCfg<BN, EPI, MT>;
-  auto kern = conv3x3_kernel<BN, EPI, MT>;
+  using Cfg = ConvCfg<BN, EPI, MT, TWO>;
+  auto kern = conv3x3_kernel<BN, EPI, MT, TWO>;
   static bool configured = false;
   if (!configured) {
     cudaError_t err =
@@ -303,18 +365,23 @@ static int launch_conv(const CUtensorMap& tmW, const ConvArgs& a, const EpiArgs&
     if (err != cudaSuccess) return static_cast<int>(err);
     configured = true;
   }
+  if constexpr (TWO) {
+    const int tiles = ((a.n_mtiles + 1) / 2) * ((a.Cout + BN - 1) / BN);
+    const int grid = (tiles < num_sms / 2 ? tiles : num_sms / 2) * 2;
+    return launch_pdl_cluster(kern, dim3(grid), dim3(CV_THREADS), Cfg::kSmemBytes, stream, 2, tmW, a, e, M_total);
+  }
   const int tiles = ((a.n_mtiles + MT - 1) / MT) * ((a.Cout + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
   return launch_pdl(kern, dim3(grid), dim3(CV_THREADS), Cfg::kSmemBytes, stream, tmW, a, e, M_total);
 }
 
-template <int BN, int MT>
+template <int BN, int MT, bool TWO = false>
 static int dispatch_conv(int epi, const CUtensorMap& tmW, const ConvArgs& a, const EpiArgs& e,
                          int M_total, int sms, cudaStream_t st) {
   switch (epi) {
-    case EPI_BIAS: return launch_conv<BN, EPI_BIAS, MT>(tmW, a, e, M_total, sms, st);
-    case EPI_GATE_RESID: return launch_conv<BN, EPI_GATE_RESID, MT>(tmW, a, e, M_total, sms, st);
-    case EPI_ROWVEC: return launch_conv<BN, EPI_ROWVEC, MT>(tmW, a, e, M_total, sms, st);
+    case EPI_BIAS: return launch_conv<BN, EPI_BIAS, MT, TWO>(tmW, a, e, M_total, sms, st);
+    case EPI_GATE_RESID: return launch_conv<BN, EPI_GATE_RESID, MT, TWO>(tmW, a, e, M_total, sms, st);
+    case EPI_ROWVEC: return launch_conv<BN, EPI_ROWVEC, MT, TWO>(tmW, a, e, M_total, sms, st);
     default: return B200_ERR_UNSUPPORTED;
   }
 }
@@ -373,9 +440,15 @@ extern "C" int b200_conv3x3_bf16(const void* in_maps_dev, const void* out_maps_d
   if (sms <= 0) return B200_ERR_DRIVER;
   const int BN = choose_tile_n(n_mtiles, Cout, 9 * (Cin / CV_BK), sms, /*multicast=*/false);
   const bool bn256 = BN == 256;
+  // CTA pairs as cta_group::2 (one pixel block per CTA, half of the weight tile each) once there is more
+  // than one round of pair tiles; SDUSS_B200_CONV_NO_2CTA=1 (read per call, for A/B runs) keeps round 1's
+  // single-CTA tiles
+  const char* no2 = getenv("SDUSS_B200_CONV_NO_2CTA");
+  const long pair_tiles = long((n_mtiles + 1) / 2) * ((Cout + BN - 1) / BN);
+  const bool two = !(no2 && no2[0] == '1') && n_mtiles >= 2 && pair_tiles > sms / 2;
   CUtensorMap tmW;
   uint64_t d[2] = {uint64_t(9) * Cin, uint64_t(Cout)}, s[1] = {uint64_t(9) * Cin * 2};
-  uint32_t b[2] = {CV_BK, uint32_t(BN)};
+  uint32_t b[2] = {CV_BK, uint32_t(two ? BN / 2 : BN)};
   int rc = get_tmap_bf16_sw128(&tmW, Wt, 2, d, s, b);
   if (rc) return rc;
   ConvArgs a{static_cast<const CUtensorMap*>(in_maps_dev),
@@ -395,6 +468,8 @@ extern "C" int b200_conv3x3_bf16(const void* in_maps_dev, const void* out_maps_d
   e.ln_stats = nullptr; e.ln_colsum = nullptr; e.ln_rowpart = nullptr; e.ln_nparts = 0; e.part_ld = 0; e.ln_eps = 0.f;
   e.rowpart_out = nullptr;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  if (two) return bn256 ? dispatch_conv<256, 1, true>(epi_mode, tmW, a, e, M_total, sms, st)
+                        : dispatch_conv<128, 1, true>(epi_mode, tmW, a, e, M_total, sms, st);
   if (bn256) return dispatch_conv<256, 1>(epi_mode, tmW, a, e, M_total, sms, st);
   // 128-wide tiles with several rounds of tile pairs: two M tiles per CTA share each weight tile
   // (halves the operand bytes per FLOP, see ConvCfg). Preferring this over 256-wide tiles where it

@@ -481,7 +481,11 @@ extern "C" int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
   // SDUSS_B200_NO_2CTA=1 / SDUSS_B200_QUAD=1 are read per call: A/B runs flip them inside one process
   const char* no2 = getenv("SDUSS_B200_NO_2CTA");
   const char* qd = getenv("SDUSS_B200_QUAD");
-  const bool two = multicast && !(no2 && no2[0] == '1');
+  // cta_group::2 pays above one round of pair tiles (deeper ring, half the W bytes in shared memory);
+  // a single round gains nothing from it and pays ~1 us more prologue + teardown (TMEM alloc / release
+  // across the pair): those keep the W-multicast pairs (in-process A/B, profiles/r02_gemm_ab.txt)
+  const long tiles_two = long((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+  const bool two = multicast && !(no2 && no2[0] == '1') && (tiles_two > sms / 2 || (no2 && no2[0] == '2'));
   const bool quad = two && qd && qd[0] == '1' && M > 2 * BM && ep->row_mask == nullptr;
   const int mode = quad ? 3 : two ? 2 : multicast ? 1 : 0;
   CUtensorMap tmA, tmB;

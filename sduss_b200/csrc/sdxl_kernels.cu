@@ -229,9 +229,13 @@ __global__ void __launch_bounds__(256) gn_finalize_tiles_kernel(const float2* pa
 // Chunks are walked from the END of the tensor (CTA 0 takes the last one): the statistics pass
 // has just streamed x front to back, so its tail is what the 126 MB L2 still holds when x is larger
 // than L2 (and the whole of x when it is not).
-template <bool SILU>
+// st: (mean, rstd) pairs of the latent's groups, indexed by group - g_base: global memory (read through
+// L1: every thread of a CTA asks for the same few pairs) in the three-launch path, a shared-memory copy
+// of the slice's groups in the single-launch kernel (the statistics were written by other SMs during
+// the same launch: fetched once per item through L2).
+template <bool SILU, bool ST_SMEM>
 __device__ __forceinline__ void gn_apply_item(const __nv_bfloat16* x, int ldx, int W, int RL, int cpg, int G,
-                                              const float* stats, const int* row_group,
+                                              const float2* st_in, int g_base, const int* row_group,
                                               const float* a0, const float* b0, __nv_bfloat16* y, int ldy,
                                               int chunk, int ch0) {
   const int rl = threadIdx.x / W;
@@ -244,11 +248,12 @@ __device__ __forceinline__ void gn_apply_item(const __nv_bfloat16* x, int ldx, i
     const int r = rl + k * RL;
     if (r < GN_CHUNK) v[k] = *reinterpret_cast<const uint4*>(xb + size_t(r) * ldx);
   }
-  const float* st = stats + size_t(row_group[row0]) * G * 2;
-  float a[8], b[8];
+  // (the x loads above are already in flight when the latent index is fetched)
+  const float2* st = ST_SMEM ? st_in : st_in + size_t(row_group[row0]) * G;
+  float a[8], b[8];  // (a0, b0 die here in the three-launch kernel: 64 registers without spills)
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float2 mr = __ldcg(reinterpret_cast<const float2*>(st + ((ch0 + j) / cpg) * 2));
+    const float2 mr = st[(ch0 + j) / cpg - g_base];
     a[j] = a0[j] * mr.y;
     b[j] = fmaf(-mr.x, a[j], b0[j]);
     if (SILU) {
@@ -293,7 +298,8 @@ __global__ void __launch_bounds__(GN_THREADS, 4) gn_apply_kernel(
   unpack8s(*reinterpret_cast<const uint4*>(gamma + ch0), a);  // parameters: not written by the
   unpack8s(*reinterpret_cast<const uint4*>(beta + ch0), b);   // preceding kernels
   pdl_wait();
-  gn_apply_item<SILU>(x, ldx, W, RL, cpg, G, stats, row_group, a, b, y, ldy, n_chunks - 1 - int(blockIdx.x), ch0);
+  gn_apply_item<SILU, false>(x, ldx, W, RL, cpg, G, reinterpret_cast<const float2*>(stats), 0, row_group, a, b, y,
+                             ldy, n_chunks - 1 - int(blockIdx.x), ch0);
 }
 
 // ---- single launch: statistics -> grid barrier -> finalize -> grid barrier -> apply, by a grid that
@@ -352,6 +358,8 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_fused_kernel(
   }
   gn_grid_barrier(bar, epoch0 + 2);
   const int col = threadIdx.x % W;
+  const int gps = G / S;
+  __shared__ float2 st_s[GN_MAXG];
   int last_slice = -1;
   float a[8], b[8];
   for (int it = n_items - 1 - int(blockIdx.x); it >= 0; it -= gridDim.x) {
@@ -362,7 +370,12 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_fused_kernel(
       unpack8s(*reinterpret_cast<const uint4*>(beta + ch0), b);
       last_slice = slice;
     }
-    gn_apply_item<SILU>(x, ldx, W, RL, cpg, G, stats, row_group, a, b, y, ldy, chunk, ch0);
+    __syncthreads();  // the previous item's readers of st_s are done
+    if (int(threadIdx.x) < gps)
+      st_s[threadIdx.x] = __ldcg(reinterpret_cast<const float2*>(stats) +
+                                 size_t(row_group[size_t(chunk) * GN_CHUNK]) * G + slice * gps + threadIdx.x);
+    __syncthreads();
+    gn_apply_item<SILU, true>(x, ldx, W, RL, cpg, G, st_s, slice * gps, row_group, a, b, y, ldy, chunk, ch0);
   }
 }
 
