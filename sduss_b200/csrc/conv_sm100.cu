@@ -445,7 +445,9 @@ extern "C" int b200_conv3x3_bf16(const void* in_maps_dev, const void* out_maps_d
   // single-CTA tiles
   const char* no2 = getenv("SDUSS_B200_CONV_NO_2CTA");
   const long pair_tiles = long((n_mtiles + 1) / 2) * ((Cout + BN - 1) / BN);
-  const bool two = !(no2 && no2[0] == '1') && n_mtiles >= 2 && pair_tiles > sms / 2;
+  // (256-wide tiles only: with 128 output channels the two-M-tiles-per-CTA variant below moves the same
+  //  bytes per FLOP and measured 911 vs 729 TFLOP/s on the VAE's 128-channel level)
+  const bool two = !(no2 && no2[0] == '1') && bn256 && n_mtiles >= 2 && pair_tiles > sms / 2;
   CUtensorMap tmW;
   uint64_t d[2] = {uint64_t(9) * Cin, uint64_t(Cout)}, s[1] = {uint64_t(9) * Cin * 2};
   uint32_t b[2] = {CV_BK, uint32_t(two ? BN / 2 : BN)};
@@ -468,8 +470,7 @@ extern "C" int b200_conv3x3_bf16(const void* in_maps_dev, const void* out_maps_d
   e.ln_stats = nullptr; e.ln_colsum = nullptr; e.ln_rowpart = nullptr; e.ln_nparts = 0; e.part_ld = 0; e.ln_eps = 0.f;
   e.rowpart_out = nullptr;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
-  if (two) return bn256 ? dispatch_conv<256, 1, true>(epi_mode, tmW, a, e, M_total, sms, st)
-                        : dispatch_conv<128, 1, true>(epi_mode, tmW, a, e, M_total, sms, st);
+  if (two) return dispatch_conv<256, 1, true>(epi_mode, tmW, a, e, M_total, sms, st);
   if (bn256) return dispatch_conv<256, 1>(epi_mode, tmW, a, e, M_total, sms, st);
   // 128-wide tiles with several rounds of tile pairs: two M tiles per CTA share each weight tile
   // (halves the operand bytes per FLOP, see ConvCfg). Preferring this over 256-wide tiles where it
