@@ -477,7 +477,9 @@ extern "C" int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
   // tiles to occupy the 74 SM pairs
   static const bool mc_allowed = []() { const char* v = getenv("SDUSS_B200_NO_MULTICAST"); return !(v && v[0] == '1'); }();
   const long pair_tiles = long((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
-  const bool multicast = mc_allowed && M > BM && pair_tiles >= (sms / 2) / 2;
+  const char* mp = getenv("SDUSS_B200_MC_MIN_PAIRS");  // experiment hook (read per call)
+  const long min_pairs = mp ? atol(mp) : (sms / 2) / 2;
+  const bool multicast = mc_allowed && M > BM && pair_tiles >= min_pairs;
   // SDUSS_B200_NO_2CTA=1 / SDUSS_B200_QUAD=1 are read per call: A/B runs flip them inside one process
   const char* no2 = getenv("SDUSS_B200_NO_2CTA");
   const char* qd = getenv("SDUSS_B200_QUAD");
