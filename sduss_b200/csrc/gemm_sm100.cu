@@ -16,6 +16,9 @@ namespace b200 {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int GEMM_THREADS = 256;
+#ifndef GEMM_STAGES_128
+#define GEMM_STAGES_128 5
+#endif
 
 // TWO: the CTA pair runs ONE tcgen05.mma.cta_group::2 of M = 256 per K step; each CTA keeps only its
 // half of the W tile, so a stage is 16 KB + BN x 64 B and the ring holds 6-8 K steps instead of 4-5
@@ -25,7 +28,7 @@ struct GemmCfg {
   // The residual chunk of a gate*y + residual epilogue is TMA-loaded INTO the output staging tile
   // and updated in place, so that epilogue costs no pipeline stage (a 3-stage 128 x 256 main loop
   // lost 27 % on the K = 1536 out-projections: operand latency, not the tensor pipe).
-  static constexpr int kStages = TWO ? ((BN == 128) ? 8 : 6) : (BN == 256) ? 4 : (BN == 192) ? 4 : 5;
+  static constexpr int kStages = TWO ? ((BN == 128) ? 8 : 6) : (BN == 256) ? 4 : (BN == 192) ? 4 : GEMM_STAGES_128;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (TWO ? BN / 2 : BN) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
