@@ -166,8 +166,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // requested BEFORE waiting for the previous kernel, so their HBM latency runs under its tail;
   // only the A loads (L2 hits: A was just written) remain after the wait.
   int npre = 0;
-  if (warp == 0 && e.w_static && e.row_mask == nullptr && first_tile < num_tiles) {
+  if ((warp == 0 || warp == 3) && e.w_static && e.row_mask == nullptr && first_tile < num_tiles)
     npre = num_kb < Cfg::kStages ? num_kb : Cfg::kStages;
+  if (warp == 0 && npre > 0) {
     if (lane == 0) {
       const int n0 = (first_tile % tiles_n) * BN;
       for (int kb = 0; kb < npre; ++kb) {
@@ -195,7 +196,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (!pre && (!TWO || (rank & 1) == 0)) mbar_expect_tx(&full[stage], kExpect);
           if constexpr (TWO) tma_load_2d_2sm(smemA + stage * Cfg::kABytes, &tmA, &full[stage], kb * BK, m0);
           else tma_load_2d(smemA + stage * Cfg::kABytes, &tmA, &full[stage], kb * BK, m0);
+#ifndef GEMM_SPLIT_PRODUCER
           if (!pre) load_w(stage, kb, n0);
+#endif
         }
         __syncwarp();
         if (++stage == Cfg::kStages) {
@@ -204,6 +207,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
+#ifdef GEMM_SPLIT_PRODUCER
+  } else if (warp == 3) {
+    // ------------------------------------------------------------ second TMA producer: the W tiles
+    // (experiment: is one thread issuing both loads of a K step the serial bottleneck?)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = first_tile; t < num_tiles; t += tile_step) {
+      const int m0 = ((t / tiles_n) * MC + int(rank)) * BM;
+      const int n0 = (t % tiles_n) * BN;
+      if (tile_skipped(e, m0 - int(rank) * BM, s.M)) continue;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (lane == 0 && !(t == first_tile && kb < npre)) load_w(stage, kb, n0);
+        __syncwarp();
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+#endif
   } else if (warp == 1 && (!TWO || (rank & 1) == 0)) {
     // ------------------------------------------------------------ MMA issuer (TWO: the leader's only)
     constexpr uint32_t idesc = make_idesc_bf16(TWO ? 2 * BM : BM, BN, 0, 0);
