@@ -352,6 +352,17 @@ int b200_patch_mask_bf16(const void* x, int ldx, void* prev, int ldp, int n_patc
                          const float* latent_t, const float* latent_valid, int32_t* skipped,
                          int32_t* mask, float* mse, const B200Forest* forest, int block_index,
                          int refresh, void* workspace, void* stream);
+/* The SDXL UNet variant (CacheManager.get_mask, cache_manager.py:101-159; called per down / mid / up
+ * block, modules/unet_2d_blocks.py:40,102,180,250,345). Down and mid blocks use the three features
+ * above (refresh = 4, :147). An up block's feature row continues with the MSE of every skip tensor it
+ * consumes (is_upsample, :106-121): launch this once per skip tensor with forest == NULL (MSE-only:
+ * `mse` [n_patches] is written, `prev` refreshed, mask / skipped may be NULL) and then once on the block
+ * input with extra_mse = those results, [n_extra][n_patches], n_extra <= 3 (features 3 .. 2 + n_extra). */
+int b200_patch_mask_ex(const void* x, int ldx, void* prev, int ldp, int n_patches, int rows_per_patch,
+                       int D, const int32_t* patch_latent, const float* latent_t,
+                       const float* latent_valid, int32_t* skipped, int32_t* mask, float* mse,
+                       const B200Forest* forest, int block_index, int refresh, const float* extra_mse,
+                       int n_extra, void* workspace, void* stream);
 
 /* ---- Prepare stage (text encoders behind encode_prompt,
  * pipeline_stable_diffusion_3_esymred.py:119-141, pipeline_stable_diffusion_xl_esymred.py:120-160).

@@ -116,6 +116,9 @@ SIGNATURES = {
     "b200_patch_mask_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(Forest), c_int, c_int,
                              c_void_p, c_void_p],
+    "b200_patch_mask_ex": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                           c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(Forest), c_int, c_int,
+                           c_void_p, c_int, c_void_p, c_void_p],
     "b200_row_stats_bf16": [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p],
     "b200_silu_bf16": [c_void_p, c_void_p, ctypes.c_longlong, c_void_p],
     "b200_timestep_embedding": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],

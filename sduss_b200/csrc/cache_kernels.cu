@@ -45,6 +45,10 @@ struct PatchMaskArgs {
   float* partial;                      // [n_patches][PC_SPLIT] workspace
   unsigned* arrive;                    // [n_patches] workspace, zero on entry, left zero
   float block_index; int refresh;
+  // up-block variant (CacheManager.get_mask(is_upsample=True), cache_manager.py:106-135): the feature row
+  // continues with the MSE of every skip tensor of the block; those come from earlier launches of this
+  // kernel in MSE-only mode (f.n_trees == 0: no decision, mask / skipped untouched).
+  const float* extra; int n_extra;     // [n_extra][n_patches], n_extra <= 3
   ForestDev f;
 };
 
@@ -100,8 +104,11 @@ patch_mask_kernel(const __grid_constant__ PatchMaskArgs a) {
   const bool valid = a.latent_valid[lat] != 0.f;
   // cache_manager.py:19,166: a patch without a kept input gets MSE = float(sys.maxsize)
   const float mse = valid ? s / (float(a.rows_per_patch) * float(a.D)) : 9223372036854775807.f;
+  if (a.mse != nullptr) a.mse[p] = mse;
+  if (a.f.n_trees == 0) return;  // MSE-only launch (a skip tensor of an up block)
   const int prev_skips = valid ? a.skipped[p] : 0;
-  const float feat[3] = {a.block_index, a.latent_t[lat], mse};
+  float feat[6] = {a.block_index, a.latent_t[lat], mse, 0.f, 0.f, 0.f};
+  for (int k = 0; k < a.n_extra; ++k) feat[3 + k] = __ldcg(a.extra + size_t(k) * a.n_patches + p);
   float votes = 0.f;
   for (int t = 0; t < a.f.n_trees; ++t) {
     int n = a.f.roots[t];
@@ -114,7 +121,6 @@ patch_mask_kernel(const __grid_constant__ PatchMaskArgs a) {
   const bool flagged = !valid || votes > 0.5f * float(a.f.n_trees) || prev_skips == a.refresh;
   a.mask[p] = flagged ? 1 : 0;
   a.skipped[p] = (flagged || prev_skips == a.refresh) ? 0 : prev_skips + 1;
-  if (a.mse != nullptr) a.mse[p] = mse;
 }
 
 }  // namespace b200
@@ -130,11 +136,29 @@ extern "C" int b200_patch_mask_bf16(const void* x, int ldx, void* prev, int ldp,
                                     const float* latent_t, const float* latent_valid, int32_t* skipped,
                                     int32_t* mask, float* mse, const B200Forest* forest, int block_index,
                                     int refresh, void* workspace, void* stream) {
-  if (!x || !prev || !patch_latent || !latent_t || !latent_valid || !skipped || !mask || !forest ||
-      !workspace || n_patches <= 0 || rows_per_patch <= 0 || (rows_per_patch % PC_SPLIT) || D <= 0 ||
-      (D & 7) || (ldx & 7) || (ldp & 7) || forest->n_trees <= 0 || !forest->feature || !forest->threshold ||
-      !forest->left || !forest->right || !forest->value || !forest->roots)
+  if (!forest) return B200_ERR_INVALID;
+  return b200_patch_mask_ex(x, ldx, prev, ldp, n_patches, rows_per_patch, D, patch_latent, latent_t,
+                            latent_valid, skipped, mask, mse, forest, block_index, refresh, nullptr, 0,
+                            workspace, stream);
+}
+
+extern "C" int b200_patch_mask_ex(const void* x, int ldx, void* prev, int ldp, int n_patches,
+                                  int rows_per_patch, int D, const int32_t* patch_latent,
+                                  const float* latent_t, const float* latent_valid, int32_t* skipped,
+                                  int32_t* mask, float* mse, const B200Forest* forest, int block_index,
+                                  int refresh, const float* extra_mse, int n_extra, void* workspace,
+                                  void* stream) {
+  if (!x || !prev || !patch_latent || !latent_t || !latent_valid || !workspace || n_patches <= 0 ||
+      rows_per_patch <= 0 || (rows_per_patch % PC_SPLIT) || D <= 0 || (D & 7) || (ldx & 7) || (ldp & 7) ||
+      n_extra < 0 || n_extra > 3 || (n_extra > 0 && !extra_mse))
     return B200_ERR_INVALID;
+  if (forest) {
+    if (!skipped || !mask || forest->n_trees <= 0 || !forest->feature || !forest->threshold ||
+        !forest->left || !forest->right || !forest->value || !forest->roots)
+      return B200_ERR_INVALID;
+  } else if (!mse) {
+    return B200_ERR_INVALID;  // an MSE-only launch without an output
+  }
   PatchMaskArgs a;
   a.x = static_cast<const __nv_bfloat16*>(x); a.ldx = ldx;
   a.prev = static_cast<__nv_bfloat16*>(prev); a.ldp = ldp;
@@ -144,8 +168,12 @@ extern "C" int b200_patch_mask_bf16(const void* x, int ldx, void* prev, int ldp,
   a.partial = static_cast<float*>(workspace);
   a.arrive = reinterpret_cast<unsigned*>(a.partial + size_t(n_patches) * PC_SPLIT);
   a.block_index = float(block_index); a.refresh = refresh;
-  a.f = ForestDev{forest->feature, forest->threshold, forest->left, forest->right, forest->value,
-                  forest->roots, forest->n_trees};
+  a.extra = extra_mse; a.n_extra = n_extra;
+  if (forest)
+    a.f = ForestDev{forest->feature, forest->threshold, forest->left, forest->right, forest->value,
+                    forest->roots, forest->n_trees};
+  else
+    a.f = ForestDev{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
   return launch_pdl(patch_mask_kernel, dim3(n_patches * PC_SPLIT), dim3(PC_THREADS), 0,
                     reinterpret_cast<cudaStream_t>(stream), a);
 }

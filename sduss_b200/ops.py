@@ -446,18 +446,43 @@ def patch_mask_workspace(n_patches, device):
 
 
 def patch_mask(x, prev, patch_latent, latent_t, latent_valid, skipped, mask, forest, block_index,
-               refresh, workspace, rows_per_patch=256, mse=None):
-    """mask[p] = 1 where patch p (rows_per_patch rows of x) must be recomputed; prev <- x."""
+               refresh, workspace, rows_per_patch=256, mse=None, extra_mse=None):
+    """mask[p] = 1 where patch p (rows_per_patch rows of x) must be recomputed; prev <- x.
+    extra_mse [n_extra, n_patches] fp32: further features of an SDXL up block (patch_mse of its skips)."""
     _req(x), _req(prev)
     n = mask.numel()
-    _ev = _count("b200_patch_mask_bf16")
-    check(lib.b200_patch_mask_bf16(_ptr(x), x.stride(0), _ptr(prev), prev.stride(0), n, rows_per_patch,
-                                   x.shape[1], _ptr(patch_latent), _ptr(latent_t), _ptr(latent_valid),
-                                   _ptr(skipped), _ptr(mask), _ptr(mse), ctypes.byref(forest.c), block_index,
-                                   refresh, _ptr(workspace), _stream()), "b200_patch_mask_bf16")
+    if extra_mse is None:
+        _ev = _count("b200_patch_mask_bf16")
+        check(lib.b200_patch_mask_bf16(_ptr(x), x.stride(0), _ptr(prev), prev.stride(0), n, rows_per_patch,
+                                       x.shape[1], _ptr(patch_latent), _ptr(latent_t), _ptr(latent_valid),
+                                       _ptr(skipped), _ptr(mask), _ptr(mse), ctypes.byref(forest.c), block_index,
+                                       refresh, _ptr(workspace), _stream()), "b200_patch_mask_bf16")
+    else:
+        _req(extra_mse, torch.float32)
+        assert extra_mse.shape[1] == n and extra_mse.is_contiguous()
+        _ev = _count("b200_patch_mask_ex")
+        check(lib.b200_patch_mask_ex(_ptr(x), x.stride(0), _ptr(prev), prev.stride(0), n, rows_per_patch,
+                                     x.shape[1], _ptr(patch_latent), _ptr(latent_t), _ptr(latent_valid),
+                                     _ptr(skipped), _ptr(mask), _ptr(mse), ctypes.byref(forest.c), block_index,
+                                     refresh, _ptr(extra_mse), extra_mse.shape[0], _ptr(workspace), _stream()),
+              "b200_patch_mask_ex")
     if _ev is not None:
         _ev.record()
     return mask
+
+
+def patch_mse(x, prev, patch_latent, latent_t, latent_valid, mse, workspace, rows_per_patch=256):
+    """mse[p] = mean squared difference of patch p of x against prev (float(sys.maxsize) where the
+    latent's kept copies are not valid); prev <- x. No decision (b200_patch_mask_ex, forest = NULL)."""
+    _req(x), _req(prev), _req(mse, torch.float32)
+    _ev = _count("b200_patch_mask_ex")
+    check(lib.b200_patch_mask_ex(_ptr(x), x.stride(0), _ptr(prev), prev.stride(0), mse.numel(), rows_per_patch,
+                                 x.shape[1], _ptr(patch_latent), _ptr(latent_t), _ptr(latent_valid),
+                                 None, None, _ptr(mse), None, 0, 0, None, 0, _ptr(workspace), _stream()),
+          "b200_patch_mask_ex")
+    if _ev is not None:
+        _ev.record()
+    return mse
 
 
 def embed_rows(ids, table, out, pos=None, seq_len=0):

@@ -121,6 +121,8 @@ class _Plan:
         self.device = dev
         self.graph = None
         self.graph_launches = 0
+        self.cache = None          # _UNetPatchCache, allocated when the plan first runs with the patch cache
+        self.cached_state = None   # graph / use counters of the cached way of running this plan
 
     def buf(self, name, rows, cols):
         t = self.bufs.get(name)
@@ -141,6 +143,8 @@ class _Plan:
         self.stats_tag, self.stats_gen = {}, {}
         if hasattr(self, "attn_src"):
             self.attn_src = {}
+        if getattr(self, "cache", None) is not None:
+            self.cache.src = {}   # attention sources of the cached forward point at arena views too
 
     def conv_maps(self, x, cin, level, stride):
         key = (x.data_ptr(), x.stride(0), cin, level, stride)
@@ -148,6 +152,76 @@ class _Plan:
         if m is None:
             m = self.maps[key] = ops.conv3x3_encode_maps(x, cin, self.levels[level].desc_host, stride)
         return m
+
+
+class _CachedState:
+    graph = None
+    graph_launches = 0
+    uses = 0
+    warm = False
+
+
+class _UNetPatchCache:
+    """What a plan keeps ACROSS steps when the patch cache is on (SURVEY.md row f-3, SDXL variant;
+    reference: CacheManager.get_mask, cache_manager.py:101-159, called once per down / mid / up block,
+    modules/unet_2d_blocks.py:40,102,180,250,345). Per UNet block with attention: the block input of the
+    previous step (and, for an up block, of every skip tensor it consumes) for the MSE features, the skip
+    counters and the mask of its 256-row patches. Per Transformer2D of such a block: its residual
+    stream, its output and the fused q|k|v of every layer -- rows of clean patches are not rewritten, so
+    they hold what the patch had when it was last computed. These buffers are owned here, not carved
+    from the model's arena (the arena is shared by all plans and overwritten by whichever ran last).
+    Validity is per latent and by plan slot, exactly as for the SD3.5 cache (sd3_transformer._PatchCache)."""
+
+    PATCH = 256
+
+    def __init__(self, model, pl):
+        self.device = model.device
+        self.L = pl.L
+        self.bufs: Dict[str, torch.Tensor] = {}
+        self.blocks: Dict[str, object] = {}
+        self.level_tabs: Dict[int, tuple] = {}
+        self.src: Dict[tuple, object] = {}
+        self.valid = torch.zeros((pl.L,), device=self.device, dtype=torch.float32)
+        self.tags = [None] * pl.L     # (request id, CFG branch, step index the kept data is good for)
+
+    def buf(self, name, rows, cols, dtype=torch.bfloat16):
+        t = self.bufs.get(name)
+        if t is None:   # zeros: kept K / V rows must be finite before their first computation
+            t = self.bufs[name] = torch.zeros((rows, cols), device=self.device, dtype=dtype)
+        assert t.shape == (rows, cols), (name, t.shape, rows, cols)
+        return t
+
+    def block(self, key, lay, level):
+        """Decision state of one UNet block, or None when a latent of this level is not made of whole
+        256-row patches (768^2 at the deepest level: 24 x 24 pixels) -- that block then runs uncached."""
+        if key in self.blocks:
+            return self.blocks[key]
+        st = None
+        if all(r % self.PATCH == 0 for r in lay.rows):
+            n = lay.T // self.PATCH
+            if level not in self.level_tabs:
+                pat = np.repeat(np.arange(lay.L, dtype=np.int32), [r // self.PATCH for r in lay.rows])
+                self.level_tabs[level] = (torch.from_numpy(pat).to(self.device),
+                                          ops.patch_mask_workspace(n, self.device))
+            st = _G_ns()
+            st.n = n
+            st.patch_latent, st.ws = self.level_tabs[level]
+            st.skipped = torch.zeros((n,), device=self.device, dtype=torch.int32)
+            st.mask = torch.ones((n,), device=self.device, dtype=torch.int32)
+            st.mse = torch.zeros((n,), device=self.device, dtype=torch.float32)
+        self.blocks[key] = st
+        return st
+
+    def masks(self):
+        """{block key: int32 mask tensor} of the blocks that decide (diagnostics / tests)."""
+        return {k: st.mask for k, st in self.blocks.items() if st is not None}
+
+    def bytes(self):
+        return sum(t.numel() * t.element_size() for t in self.bufs.values())
+
+
+class _G_ns:
+    pass
 
 
 class B200UNet(torch.nn.Module):
@@ -343,10 +417,18 @@ class B200UNet(torch.nn.Module):
         return self._conv(pl, h2, cout, name + ".conv2", level, 1, pl.buf(name + ".out", T, cout),
                           epi=ops.EPI_GATE_RESID, resid=s)
 
-    def _transformer(self, pl, x, name, level, heads, layers, kv_all):
+    def _transformer(self, pl, x, name, level, heads, layers, kv_all, cb=None, mask=None):
+        """cb / mask (patch cache, see _run): every token-wise kernel skips the 256-row tiles of clean
+        patches; the residual stream, the output and the per-layer q|k|v live in cb's own buffers, so the
+        skipped rows still hold the values of their last computation (clean patches keep their keys /
+        values for the flagged patches' queries and their Transformer2D output for what follows)."""
         w = self.w
         T, C = x.shape
-        G = _G
+        rm = dict(row_mask=mask) if mask is not None else {}
+        pbuf = (lambda nm, r, c: cb.buf(nm, r, c)) if cb is not None else pl.buf
+
+        def G(*a, **k):
+            return _G(*a, **rm, **k)
         fold = self.fold_ln and C % 64 == 0
         # Folded LayerNorms: every GEMM that writes h also leaves per-64-column partial sums of its
         # output rows (rowpart_out), and the GEMM that consumes LN(h) reduces them to (mean, rstd) at
@@ -354,7 +436,7 @@ class B200UNet(torch.nn.Module):
         # LayerNorms of a block cost no launch and no pass over h.
         rp = pl.fbuf(f"rowpart{level}", T * (C // 64) * 2) if fold else None
         n = self._gn(pl, x, name + ".norm", level, pl.buf(f"gn{level}_{C}", T, C), False, eps=1e-6)
-        h = G(n, w[name + ".proj_in.weight"], pl.buf(name + ".h", T, C), bias=w[name + ".proj_in.bias"],
+        h = G(n, w[name + ".proj_in.weight"], pbuf(name + ".h", T, C), bias=w[name + ".proj_in.bias"],
               rowpart_out=rp)
         ln = pl.buf(f"ln{level}_{C}", T, C)
         qkv = pl.buf(f"qkv{level}_{C}", T, 3 * C)
@@ -375,8 +457,14 @@ class B200UNet(torch.nn.Module):
 
         for j in range(layers):
             b = f"{name}.transformer_blocks.{j}"
+            src_self = pl.attn_src[key]
+            if cb is not None:   # this layer's own q|k|v: the keys / values of clean patches persist
+                qkv = cb.buf(b + ".qkv", T, 3 * C)
+                src_self = cb.src.get(b)
+                if src_self is None:
+                    src_self = cb.src[b] = ops.attn_source(q=qkv, q_col=0, k=qkv, k_col=C, v=qkv, v_col=2 * C, out=att)
             ln_gemm(".norm1", ".attn1.qkv", qkv)
-            ops.attn_varlen(pl.attn_src[key], None, *pl.self_plan[level], 0.125)
+            ops.attn_varlen(src_self, None, *pl.self_plan[level], 0.125, q_mask=mask)
             G(att, w[b + ".attn1.out.weight"], h, bias=w[b + ".attn1.out.bias"], epi=ops.EPI_GATE_RESID, resid=h,
               rowpart_out=rp)
             ln_gemm(".norm2", ".attn2.q", q2)
@@ -384,12 +472,12 @@ class B200UNet(torch.nn.Module):
             src_kv = pl.attn_src.get((b, "kv"))
             if src_kv is None:
                 src_kv = pl.attn_src[(b, "kv")] = ops.attn_source(k=kv_all, k_col=ko, v=kv_all, v_col=ko + C)
-            ops.attn_varlen(pl.attn_src[(level, C, "q")], src_kv, *pl.cross_plan[level], 0.125)
+            ops.attn_varlen(pl.attn_src[(level, C, "q")], src_kv, *pl.cross_plan[level], 0.125, q_mask=mask)
             G(att, w[b + ".attn2.out.weight"], h, bias=w[b + ".attn2.out.bias"], epi=ops.EPI_GATE_RESID, resid=h,
               rowpart_out=rp)
             ln_gemm(".norm3", ".ff1", ff, epi=ops.EPI_GEGLU)
             G(ff, w[b + ".ff2.weight"], h, bias=w[b + ".ff2.bias"], epi=ops.EPI_GATE_RESID, resid=h, rowpart_out=rp)
-        return G(h, w[name + ".proj_out.weight"], pl.buf(name + ".out", T, C),
+        return G(h, w[name + ".proj_out.weight"], pbuf(name + ".out", T, C),
                  bias=w[name + ".proj_out.bias"], epi=ops.EPI_GATE_RESID, resid=x)
 
     # ------------------------------------------------------------------ forward
@@ -447,7 +535,67 @@ class B200UNet(torch.nn.Module):
         out = pl.stage_out if _borrow else {k: v.clone() for k, v in pl.stage_out.items()}
         return (out,)
 
-    def _run(self, pl: _Plan):
+    # ---- patch cache (SDXL variant)
+    def enable_patch_cache(self, forest, forest_up=None, refresh: int = 4, max_cached_plans: int = 3):
+        """forest: ops.DeviceForest on [block, timestep, MSE of the block input against the previous
+        step] for the down and mid blocks; forest_up (default: forest) for the up blocks, whose feature
+        row continues with the MSE of each of the block's skip tensors (reference: the cuML forests of
+        ESYMRED_DOWNSAMPLE_PATH / ESYMRED_UPSAMPLE_PATH, cache_manager.py:27-36,101-159; refresh = 4:
+        forced recompute after four skips, :147). forest=None switches the cache off.
+        What is skipped here: the Transformer2D modules of a block (76 % of the step's time), per 256-row
+        patch of the packed pixel rows; resnets, samplers and GroupNorms are always recomputed (DESIGN.md
+        section 10)."""
+        import collections
+        self.patch_forest, self.patch_forest_up, self.patch_refresh = forest, forest_up or forest, refresh
+        self._cache_lru, self._cache_max = collections.OrderedDict(), max_cached_plans
+        for pl in self._plans.values():
+            # captured graphs of the cached forward hold the previous forest's device pointers
+            pl.cached_state = _CachedState() if (forest is not None and pl.cache is not None) else None
+            if forest is None:
+                pl.cache = None
+            elif pl.cache is not None:
+                self._cache_lru[id(pl)] = pl
+
+    def patch_cache_enabled(self):
+        return getattr(self, "patch_forest", None) is not None
+
+    def cache_for(self, pl):
+        """The plan's cache buffers (allocated on first use; least recently used plans lose theirs)."""
+        key = id(pl)
+        if pl.cache is None:
+            while len(self._cache_lru) >= self._cache_max:
+                _, old = self._cache_lru.popitem(last=False)
+                old.cached_state = None   # its graph points into the buffers: drop it first
+                old.cache = None
+            pl.cache, pl.cached_state = _UNetPatchCache(self, pl), _CachedState()
+        self._cache_lru[key] = pl
+        self._cache_lru.move_to_end(key)
+        return pl.cache
+
+    def _decide(self, pl, cb, key, level, index, x, skips=()):
+        """One get_mask call of the reference, on the device: the block's patch mask (or None when this
+        level is not made of whole 256-row patches). An up block first takes the MSE of every skip
+        tensor it is about to consume (in the order of the reference's res_hidden_states_tuple)."""
+        st = cb.block(key, pl.levels[level], level)
+        if st is None:
+            return None
+        extra = None
+        if skips:
+            extra = cb.buf(key + ".rmse", len(skips), st.n, torch.float32)
+            for k, sk in enumerate(skips):
+                ops.patch_mse(sk, cb.buf(f"{key}.rprev{k}", *sk.shape), st.patch_latent, pl.t32, cb.valid,
+                              extra[k], st.ws)
+        ops.patch_mask(x, cb.buf(key + ".xprev", *x.shape), st.patch_latent, pl.t32, cb.valid, st.skipped,
+                       st.mask, self.patch_forest_up if skips else self.patch_forest, index,
+                       self.patch_refresh, st.ws, mse=st.mse, extra_mse=extra)
+        return st.mask
+
+    def _run_cached(self, pl: _Plan):
+        """The forward with the patch cache: _run plus one decision per UNet block with attention
+        (total_blocks numbering of modules/unet.py:369-503: down blocks 0.., mid, up blocks)."""
+        return self._run(pl, pl.cache)
+
+    def _run(self, pl: _Plan, cb=None):
         cfg, w, G = self.cfg, self.w, _G
         ch = cfg.block_out_channels
         L = pl.L
@@ -478,11 +626,14 @@ class B200UNet(torch.nn.Module):
         skips = [x]
         level = 0
         for i in range(len(ch)):
+            mask = self._decide(pl, cb, f"down_blocks.{i}", level, i, x) \
+                if (cb is not None and cfg.down_has_attn[i]) else None
             for j in range(cfg.layers_per_block):
                 x = self._resnet(pl, x, f"down_blocks.{i}.resnets.{j}", level, temb_all)
                 if cfg.down_has_attn[i]:
                     x = self._transformer(pl, x, f"down_blocks.{i}.attentions.{j}", level,
-                                          cfg.num_heads[i], cfg.transformer_layers_per_block[i], kv_all)
+                                          cfg.num_heads[i], cfg.transformer_layers_per_block[i], kv_all,
+                                          cb, mask)
                 skips.append(x)
             if i != len(ch) - 1:
                 name = f"down_blocks.{i}.downsamplers.0.conv"
@@ -490,14 +641,18 @@ class B200UNet(torch.nn.Module):
                                pl.buf(name, pl.levels[level + 1].T, x.shape[1]), epi=ops.EPI_BIAS)
                 level += 1
                 skips.append(x)
+        mask = self._decide(pl, cb, "mid_block", level, len(ch), x) if cb is not None else None
         x = self._resnet(pl, x, "mid_block.resnets.0", level, temb_all)
         x = self._transformer(pl, x, "mid_block.attentions.0", level, cfg.num_heads[-1],
-                              cfg.transformer_layers_per_block[-1], kv_all)
+                              cfg.transformer_layers_per_block[-1], kv_all, cb, mask)
         x = self._resnet(pl, x, "mid_block.resnets.1", level, temb_all)
         rev_layers = list(reversed(cfg.transformer_layers_per_block))
         rev_attn = list(reversed(cfg.down_has_attn))
         rev_heads = list(reversed(cfg.num_heads))
         for i in range(len(ch)):
+            mask = self._decide(pl, cb, f"up_blocks.{i}", level, len(ch) + 1 + i, x,
+                                skips[-(cfg.layers_per_block + 1):]) \
+                if (cb is not None and rev_attn[i]) else None
             for j in range(cfg.layers_per_block + 1):
                 skip = skips.pop()
                 T, c1, c2 = x.shape[0], x.shape[1], skip.shape[1]
@@ -507,7 +662,7 @@ class B200UNet(torch.nn.Module):
                 x = self._resnet(pl, cat, f"up_blocks.{i}.resnets.{j}", level, temb_all)
                 if rev_attn[i]:
                     x = self._transformer(pl, x, f"up_blocks.{i}.attentions.{j}", level, rev_heads[i],
-                                          rev_layers[i], kv_all)
+                                          rev_layers[i], kv_all, cb, mask)
             if i != len(ch) - 1:
                 name = f"up_blocks.{i}.upsamplers.0.conv"
                 lo, hi = pl.levels[level], pl.levels[level - 1]

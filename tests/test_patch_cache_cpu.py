@@ -75,3 +75,46 @@ def test_cached_oracle_is_exact_when_everything_is_flagged_and_skips_clean_patch
     # forced all-true masks reproduce the exact forward whatever the cache holds
     out5, _ = orc.forward_latent("a", lat2, ehs, pooled, 900.0, forced_masks=[[True] * 4] * cfg.num_layers)
     assert torch.allclose(out5, ref2, atol=1e-5)
+
+
+def test_cached_sdxl_oracle_is_exact_when_everything_is_flagged_and_follows_the_refresh_rule():
+    """SDXL variant (oracle.patch_cache.CachedSDXLOracle): one decision per UNet block with attention,
+    refresh = 4 (cache_manager.py:147), an up block's features include the MSE of its skip tensors."""
+    from oracle import patch_cache as pc
+    from oracle import sdxl_unet as ox
+    cfg = ox.sdxl_tiny_config()
+    sd = ox.init_unet_weights(cfg, 0)
+    g = torch.Generator().manual_seed(0)
+    lat = torch.randn(1, 4, 64, 64, generator=g)                    # level 1: 1024 rows = 4 patches, level 2: 1
+    ctx = torch.randn(1, cfg.context_len, cfg.cross_attention_dim, generator=g)
+    emb = ox.conditioning(sd, cfg, torch.tensor([801.0]), torch.randn(1, cfg.pooled_dim, generator=g),
+                          torch.tensor([[512.0, 512, 0, 0, 512, 512]]))
+    ref = ox.unet_single(sd, cfg, lat, emb, ctx)
+    seen_feats = []
+
+    def rule(index, t, feats):
+        seen_feats.append((index, tuple(feats.shape)))
+        return (feats > 1e-4).any(dim=1).int()
+    orc = pc.CachedSDXLOracle(sd, cfg, rule, refresh=4)
+    out, masks = orc.forward_latent("a", lat, emb, ctx, 801.0)
+    assert torch.equal(out, ref)                                     # first sight: everything computed
+    assert set(masks) == {"down_blocks.1", "down_blocks.2", "mid_block", "up_blocks.0", "up_blocks.1"}
+    assert [len(masks[k]) for k in ("down_blocks.1", "down_blocks.2", "mid_block", "up_blocks.0", "up_blocks.1")] \
+        == [4, 1, 1, 1, 4] and all(all(m) for m in masks.values())
+    # block numbering of modules/unet.py:369-503 and the feature count (up blocks: input + 3 skips)
+    assert seen_feats == [(1, (4, 1)), (2, (1, 1)), (3, (1, 1)), (4, (1, 4)), (5, (4, 4))]
+    pattern = []
+    for _ in range(6):                                               # the same input again and again
+        out2, masks2 = orc.forward_latent("a", lat, emb, ctx, 801.0)
+        pattern.append([any(m) for m in masks2.values()])
+        assert torch.allclose(out2, ref, atol=1e-5)                  # reuse of unchanged patches is exact
+    assert pattern == [[False] * 5] * 4 + [[True] * 5] + [[False] * 5]   # four skips, then the forced refresh
+    lat2 = lat.clone()
+    lat2[:, :, :16] += 0.5 * torch.randn(1, 4, 16, 64, generator=g)  # the top quarter of the image changes
+    out3, masks3 = orc.forward_latent("a", lat2, emb, ctx, 801.0)
+    assert masks3["down_blocks.1"][0]            # (GroupNorm couples the whole image: the other bands move too)
+    ref3 = ox.unet_single(sd, cfg, lat2, emb, ctx)
+    assert torch.nn.functional.cosine_similarity(out3.flatten(), ref3.flatten(), dim=0) > 0.99
+    full = {k: [True] * len(m) for k, m in masks3.items()}
+    out4, _ = orc.forward_latent("a", lat2, emb, ctx, 801.0, forced_masks=full)
+    assert torch.allclose(out4, ref3, atol=1e-5)
