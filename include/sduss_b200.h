@@ -94,6 +94,11 @@ typedef struct B200EpilogueDesc {
   int32_t w_static;        /* 1: nothing on `stream` writes W (weights): the kernel may request its first */
                            /* W tiles before waiting for the previous kernel (programmatic dependent       */
                            /* launch); 0 (default): W is loaded after the wait, like A                     */
+  int32_t row_mask_scale;  /* b200_conv3x3_bf16 only: log2(rows of the level row_mask describes / output   */
+                           /* rows): 0 same level, +2 a stride-2 downsampler, -2 the convolution after a    */
+                           /* 2x upsample. A 16 x 8 pixel block is skipped when every patch its 16 pixel    */
+                           /* rows touch is clean (reference: masked conv1 / conv2 / samplers,              */
+                           /* modules/resnet.py:328-339,365-377,414-454)                                    */
 } B200EpilogueDesc;
 
 /* A: [M, lda] bf16, W: [N, ldw] bf16 (K contiguous in both). N, K, lda, ldw, ldc multiples

@@ -38,7 +38,7 @@ class EpilogueDesc(ctypes.Structure):
         ("stats_out", c_void_p),
         ("ln_stats", c_void_p), ("ln_colsum", c_void_p),
         ("ln_rowpart", c_void_p), ("ln_nparts", ctypes.c_int32), ("ln_eps", c_float),
-        ("rowpart_out", c_void_p), ("w_static", ctypes.c_int32),
+        ("rowpart_out", c_void_p), ("w_static", ctypes.c_int32), ("row_mask_scale", ctypes.c_int32),
     ]
 
 

@@ -51,7 +51,34 @@ struct ConvArgs {
   const int4* tiles;           // [n_mtiles] {latent, y0, x0, 0} in OUTPUT pixel coordinates
   const int4* lat;             // [n_latents] {output row offset, Hout, Wout, 0}
   int n_mtiles, Cin, Cout, stride;
+  // patch cache (SDXL variant): pixel blocks whose rows all lie in clean patches are
+  // skipped (no loads, no MMA, no store: the output keeps what it had). mask: int32 per 2^shift packed
+  // rows of the level the block's decision was taken on; scale = log2(rows there / output rows):
+  // 0 same level, +2 a stride-2 downsampler (output one level down), -2 the upsampler's convolution.
+  const int* mask; int mask_shift, mask_scale;
 };
+
+// all rows of M tile m (16 output pixel rows of one latent, whatever the columns) lie in clean patches
+__device__ __forceinline__ bool conv_mtile_clean(const ConvArgs& a, int m) {
+  const int4 tl = a.tiles[m];
+  const int4 ld = a.lat[tl.x];
+  long lo = ld.x + long(tl.y) * ld.z, hi = ld.x + long(min(tl.y + 16, ld.y)) * ld.z;  // output rows [lo, hi)
+  if (a.mask_scale > 0) { lo <<= a.mask_scale; hi <<= a.mask_scale; }
+  else if (a.mask_scale < 0) { lo >>= -a.mask_scale; hi = (hi + (1L << -a.mask_scale) - 1) >> -a.mask_scale; }
+  for (long b = lo >> a.mask_shift; b <= ((hi - 1) >> a.mask_shift); ++b)
+    if (a.mask[b] != 0) return false;
+  return true;
+}
+// a work item (MTI consecutive M tiles starting at m_first) is skipped when all its tiles are clean:
+// the same answer in every warp role and in both CTAs of a pair
+template <int MTI>
+__device__ __forceinline__ bool conv_item_skipped(const ConvArgs& a, int m_first) {
+  if (a.mask == nullptr) return false;
+#pragma unroll
+  for (int i = 0; i < MTI; ++i)
+    if (m_first + i < a.n_mtiles && !conv_mtile_clean(a, m_first + i)) return false;
+  return true;
+}
 
 template <int BN, int EPI, int MT, bool TWO>
 __global__ void __launch_bounds__(CV_THREADS, 1)
@@ -129,7 +156,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
   // the weight tiles of the first ring stages are requested before the wait on the previous kernel
   // (weights are never written on the stream; see gemm_sm100.cu): their HBM latency runs under its tail
   int npre = 0;
-  if (warp == 0 && first_tile < num_tiles) {
+  if (warp == 0 && first_tile < num_tiles && a.mask == nullptr) {  // (the mask is written by the previous kernel)
     npre = num_kb < Cfg::kStages ? num_kb : Cfg::kStages;
     if (lane == 0) {
       const int t = first_tile;
@@ -151,6 +178,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
       const int m0 = TWO ? (t / tiles_n) * 2 + rank : (t / tiles_n) * MT;
       const int nmt = TWO ? (m0 < a.n_mtiles ? 1 : 0) : min(MT, a.n_mtiles - m0);
       const int n0 = (t % tiles_n) * BN;
+      if (conv_item_skipped<MTI>(a, (t / tiles_n) * MTI)) continue;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * CV_BK;
         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -189,7 +217,8 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = first_tile; t < num_tiles; t += tile_step, ++it) {
+    for (int t = first_tile; t < num_tiles; t += tile_step) {
+      if (conv_item_skipped<MTI>(a, (t / tiles_n) * MTI)) continue;
       const int acc = it & 1;
       mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -222,6 +251,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
         __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
+      ++it;  // accumulator stages count the items actually computed
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (TMA-staged)
@@ -237,7 +267,8 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
     // chunk has been staged). Seen as corrupted tail columns on short-K GEMMs (conv_in: K = 64).
     uint32_t chunk_ctr = 0;
     int it = 0;
-    for (int t = first_tile; t < num_tiles; t += tile_step, ++it) {
+    for (int t = first_tile; t < num_tiles; t += tile_step) {
+      if (conv_item_skipped<MTI>(a, (t / tiles_n) * MTI)) continue;
       const int acc = it & 1;
       const int m0 = TWO ? (t / tiles_n) * 2 + rank : (t / tiles_n) * MT;
       const int nmt = TWO ? (m0 < a.n_mtiles ? 1 : 0) : min(MT, a.n_mtiles - m0);
@@ -339,6 +370,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmW, ConvArgs a, EpiArgs e, i
         if constexpr (TWO) mbar_arrive_leader(&tempty[acc]);
         else mbar_arrive(&tempty[acc]);
       }
+      ++it;
     }
     if (leader) tma_store_wait<0>();
   }
@@ -456,7 +488,10 @@ extern "C" int b200_conv3x3_bf16(const void* in_maps_dev, const void* out_maps_d
   ConvArgs a{static_cast<const CUtensorMap*>(in_maps_dev),
              static_cast<const CUtensorMap*>(out_maps_dev),
              static_cast<const CUtensorMap*>(resid_maps_dev), reinterpret_cast<const int4*>(tiles_dev),
-             reinterpret_cast<const int4*>(out_lat_dev), n_mtiles, Cin, Cout, stride};
+             reinterpret_cast<const int4*>(out_lat_dev), n_mtiles, Cin, Cout, stride,
+             ep->row_mask, ep->row_mask_shift, ep->row_mask_scale};
+  if (ep->row_mask && (ep->row_mask_shift < 6 || ep->row_mask_scale < -4 || ep->row_mask_scale > 4 || ep->stats_out))
+    return B200_ERR_INVALID;
   EpiArgs e;
   e.C = ep->C; e.ldc = ep->ldc; e.out_fp32 = ep->out_fp32;
   e.bias = static_cast<const __nv_bfloat16*>(ep->bias);

@@ -696,11 +696,18 @@ def conv3x3_encode_maps(x, cin, in_desc_host, stride):
 
 
 def conv3x3(maps_dev, tiles, n_mtiles, out_lat, cin, cout, stride, weight, out, *, out_maps,
-            resid_maps=None, epi=EPI_BIAS, bias=None, rowvec=None, row_group=None, stats_out=None):
+            resid_maps=None, epi=EPI_BIAS, bias=None, rowvec=None, row_group=None, stats_out=None,
+            row_mask=None, row_mask_shift=8, row_mask_scale=0):
     """out[M_total, cout] = conv3x3(x) through the implicit-GEMM kernel (see conv_sm100.cu).
-    out_maps / resid_maps: conv3x3_encode_maps(out or resid buffer, cout, out_desc_host, 1)."""
+    out_maps / resid_maps: conv3x3_encode_maps(out or resid buffer, cout, out_desc_host, 1).
+    row_mask (patch cache): int32 per 2^shift rows of the level the decision was taken on, `scale` =
+    log2(rows there / output rows); pixel blocks whose 16 pixel rows touch only clean patches keep
+    their previous output."""
     _req(weight), _req(out)
     d = _epi_desc(out, bias=bias, rowvec=rowvec, row_group=row_group)
+    if row_mask is not None:
+        _req(row_mask, torch.int32)
+        d.row_mask, d.row_mask_shift, d.row_mask_scale = _ptr(row_mask), row_mask_shift, row_mask_scale
     if stats_out is not None:  # per (tile, half, channel) sums for the GroupNorm that follows
         assert stats_out.dtype == torch.float32 and stats_out.numel() >= n_mtiles * 2 * cout * 2
         d.stats_out = _ptr(stats_out)

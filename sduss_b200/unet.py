@@ -384,7 +384,7 @@ class B200UNet(torch.nn.Module):
                            lay.lat_chunks, lay.L, pl.gn_ws, **kw)
         return out
 
-    def _conv(self, pl, x, cin, name, in_level, stride, out, resid=None, **epi):
+    def _conv(self, pl, x, cin, name, in_level, stride, out, resid=None, mask=None, mask_scale=0, **epi):
         out_level = in_level + (1 if stride == 2 else 0)
         lay = pl.levels[out_level]
         w = self.w[name + ".weight"]
@@ -396,25 +396,32 @@ class B200UNet(torch.nn.Module):
         # next resnet's norm1, a Transformer2D norm, conv_norm_out)
         st = ops.conv_stats_buffer(pl, out, out_level, lay.n_tiles, cout) \
             if (self.fuse_gn_stats and cout % self.cfg.norm_num_groups == 0) else None
+        if mask is not None:
+            st = None   # (a skipped pixel block would leave no statistics)
+            epi = dict(epi, row_mask=mask, row_mask_scale=mask_scale)
         return ops.conv3x3(maps, lay.tiles, lay.n_tiles, lay.desc, cin, cout, stride, w, out,
                            out_maps=out_maps, resid_maps=resid_maps, bias=self.w[name + ".bias"],
                            stats_out=st, **epi)
 
-    def _resnet(self, pl, x, name, level, temb_all):
+    def _resnet(self, pl, x, name, level, temb_all, cb=None, mask=None):
+        """cb / mask (patch cache, see _run): both GroupNorms run over the whole tensor; conv1, conv2 and
+        the 1x1 shortcut skip what lies in clean patches and their outputs live in cb's own buffers
+        (reference: modules/resnet.py:399-458, conv1_output / conv2_output caches)."""
         lay = pl.levels[level]
         T, cin = x.shape
         cout = self.w[name + ".conv1.weight"].shape[0]
+        pbuf = cb.buf if cb is not None else pl.buf
         h = self._gn(pl, x, name + ".norm1", level, pl.buf(f"gn{level}_{cin}", T, cin), True)
         off, n = self.temb_off[name]
-        h1 = self._conv(pl, h, cin, name + ".conv1", level, 1, pl.buf(name + ".h1", T, cout),
+        h1 = self._conv(pl, h, cin, name + ".conv1", level, 1, pbuf(name + ".h1", T, cout), mask=mask,
                         epi=ops.EPI_ROWVEC, rowvec=temb_all[:, off:off + n], row_group=lay.row_group)
         h2 = self._gn(pl, h1, name + ".norm2", level, pl.buf(f"gn{level}_{cout}", T, cout), True)
         if name + ".conv_shortcut.weight" in self.w:
-            s = ops.gemm(x, self.w[name + ".conv_shortcut.weight"], pl.buf(name + ".sc", T, cout),
-                         bias=self.w[name + ".conv_shortcut.bias"])
+            s = ops.gemm(x, self.w[name + ".conv_shortcut.weight"], pbuf(name + ".sc", T, cout),
+                         bias=self.w[name + ".conv_shortcut.bias"], row_mask=mask)
         else:
             s = x
-        return self._conv(pl, h2, cout, name + ".conv2", level, 1, pl.buf(name + ".out", T, cout),
+        return self._conv(pl, h2, cout, name + ".conv2", level, 1, pbuf(name + ".out", T, cout), mask=mask,
                           epi=ops.EPI_GATE_RESID, resid=s)
 
     def _transformer(self, pl, x, name, level, heads, layers, kv_all, cb=None, mask=None):
@@ -628,8 +635,9 @@ class B200UNet(torch.nn.Module):
         for i in range(len(ch)):
             mask = self._decide(pl, cb, f"down_blocks.{i}", level, i, x) \
                 if (cb is not None and cfg.down_has_attn[i]) else None
+            cbi = cb if (cb is not None and cfg.down_has_attn[i]) else None
             for j in range(cfg.layers_per_block):
-                x = self._resnet(pl, x, f"down_blocks.{i}.resnets.{j}", level, temb_all)
+                x = self._resnet(pl, x, f"down_blocks.{i}.resnets.{j}", level, temb_all, cbi, mask)
                 if cfg.down_has_attn[i]:
                     x = self._transformer(pl, x, f"down_blocks.{i}.attentions.{j}", level,
                                           cfg.num_heads[i], cfg.transformer_layers_per_block[i], kv_all,
@@ -638,14 +646,15 @@ class B200UNet(torch.nn.Module):
             if i != len(ch) - 1:
                 name = f"down_blocks.{i}.downsamplers.0.conv"
                 x = self._conv(pl, x, x.shape[1], name, level, 2,
-                               pl.buf(name, pl.levels[level + 1].T, x.shape[1]), epi=ops.EPI_BIAS)
+                               (cbi.buf if cbi is not None else pl.buf)(name, pl.levels[level + 1].T, x.shape[1]),
+                               mask=mask, mask_scale=2, epi=ops.EPI_BIAS)
                 level += 1
                 skips.append(x)
         mask = self._decide(pl, cb, "mid_block", level, len(ch), x) if cb is not None else None
-        x = self._resnet(pl, x, "mid_block.resnets.0", level, temb_all)
+        x = self._resnet(pl, x, "mid_block.resnets.0", level, temb_all, cb, mask)
         x = self._transformer(pl, x, "mid_block.attentions.0", level, cfg.num_heads[-1],
                               cfg.transformer_layers_per_block[-1], kv_all, cb, mask)
-        x = self._resnet(pl, x, "mid_block.resnets.1", level, temb_all)
+        x = self._resnet(pl, x, "mid_block.resnets.1", level, temb_all, cb, mask)
         rev_layers = list(reversed(cfg.transformer_layers_per_block))
         rev_attn = list(reversed(cfg.down_has_attn))
         rev_heads = list(reversed(cfg.num_heads))
@@ -659,7 +668,8 @@ class B200UNet(torch.nn.Module):
                 cat = pl.buf(f"up_blocks.{i}.cat{j}", T, c1 + c2)
                 ops.copy_cols(x, cat, c1)
                 ops.copy_cols(skip, cat[:, c1:], c2)
-                x = self._resnet(pl, cat, f"up_blocks.{i}.resnets.{j}", level, temb_all)
+                x = self._resnet(pl, cat, f"up_blocks.{i}.resnets.{j}", level, temb_all,
+                                 cb if rev_attn[i] else None, mask)
                 if rev_attn[i]:
                     x = self._transformer(pl, x, f"up_blocks.{i}.attentions.{j}", level, rev_heads[i],
                                           rev_layers[i], kv_all, cb, mask)
@@ -670,7 +680,9 @@ class B200UNet(torch.nn.Module):
                 up = pl.buf(name + ".up", hi.T, C)
                 ops.upsample2x(x, lo.desc, hi.desc, L, hi.max_pixels, C, up)
                 level -= 1
-                x = self._conv(pl, up, C, name, level, 1, pl.buf(name, hi.T, C), epi=ops.EPI_BIAS)
+                x = self._conv(pl, up, C, name, level, 1,
+                               (cb.buf if (cb is not None and rev_attn[i]) else pl.buf)(name, hi.T, C),
+                               mask=mask, mask_scale=-2, epi=ops.EPI_BIAS)
         h = self._gn(pl, x, "conv_norm_out", 0, pl.buf(f"gn0_{ch[0]}", l0.T, ch[0]), True)
         o = self._conv(pl, h, ch[0], "conv_out", 0, 1, pl.buf("conv_out", l0.T, self.n_out_pad), epi=ops.EPI_BIAS)
         ops.scatter_nchw(o, l0.desc, L, l0.max_pixels, cfg.out_channels, pl.out_ptr)

@@ -189,3 +189,52 @@ def test_sdxl_cache_refresh_recomposition_and_unaligned_levels(cuda):
     _step(pipe, a)
     assert nonem(masks(2))
     assert torch.isfinite(a["512"][0].sampling_params.latents.float()).all()
+
+
+@pytest.mark.parametrize("sizes,cin,cout,stride,scale", [
+    ([(32, 32), (64, 64)], 64, 128, 1, 0),       # same level: one / four patches per 16-row strip
+    ([(64, 64), (32, 32)], 128, 320, 1, 0),      # 256-wide tiles (CTA pairs above one round)
+    ([(32, 32), (64, 64)], 64, 64, 2, 2),        # downsampler: the mask describes the INPUT level
+    ([(32, 32), (64, 64)], 64, 128, 1, -2),      # convolution after the 2x upsample: mask one level down
+])
+def test_conv3x3_skips_strips_of_clean_patches(cuda, sizes, cin, cout, stride, scale):
+    """Pixel blocks whose 16 output pixel rows touch only clean 256-row patches (of the level the mask
+    describes) keep their previous output; every other block equals the unmasked convolution bit for bit."""
+    from sduss_b200 import ops
+    from sduss_b200.layout import LevelLayout
+    g = torch.Generator().manual_seed(0)
+    lin = LevelLayout(sizes, cuda)
+    osz = [(h // stride, w // stride) for h, w in sizes]
+    lout = LevelLayout(osz, cuda)
+    x = torch.randn(lin.T, cin, generator=g).cuda().bfloat16()
+    wt = (torch.randn(cout, 9 * cin, generator=g) / (3 * cin ** 0.5)).cuda().bfloat16()
+    bias = torch.randn(cout, generator=g).cuda().bfloat16()
+    maps = ops.conv3x3_encode_maps(x, cin, lin.desc_host, stride)
+    full = torch.zeros(lout.T, cout, device=cuda, dtype=torch.bfloat16)
+    omaps = ops.conv3x3_encode_maps(full, cout, lout.desc_host, 1)
+    ops.conv3x3(maps, lout.tiles, lout.n_tiles, lout.desc, cin, cout, stride, wt, full, out_maps=omaps,
+                bias=bias)
+    # mask level: rows of the output level x 4^(scale / 2)
+    msz = [((h << 1, w << 1) if scale > 0 else (h >> 1, w >> 1) if scale < 0 else (h, w)) for h, w in osz]
+    n_bands = sum(h * w for h, w in msz) // 256
+    mask_host = (torch.rand(n_bands, generator=g) < 0.4).int()
+    mask_host[0] = 0
+    for mask_host in (mask_host, torch.zeros(n_bands, dtype=torch.int32)):
+        out = torch.full((lout.T, cout), 7.0, device=cuda, dtype=torch.bfloat16)
+        om = ops.conv3x3_encode_maps(out, cout, lout.desc_host, 1)
+        ops.conv3x3(maps, lout.tiles, lout.n_tiles, lout.desc, cin, cout, stride, wt, out, out_maps=om,
+                    bias=bias, row_mask=mask_host.cuda(), row_mask_scale=scale)
+        torch.cuda.synchronize()
+        want = torch.zeros(lout.T, dtype=torch.bool)
+        off_o = off_m = 0
+        for (ho, wo), (hm, wm) in zip(osz, msz):
+            f = hm / ho
+            for y0 in range(0, ho, 16):
+                y1 = min(y0 + 16, ho)
+                lo, hi = off_m + int(y0 * f) * wm, off_m + int(y1 * f) * wm
+                if mask_host[lo // 256:(hi - 1) // 256 + 1].any():
+                    want[off_o + y0 * wo:off_o + y1 * wo] = True
+            off_o, off_m = off_o + ho * wo, off_m + hm * wm
+        o, fl = out.cpu(), full.cpu()
+        assert torch.equal(o[want], fl[want]) and (o[~want] == 7.0).all()
+        assert mask_host.any() == want.any()
