@@ -164,11 +164,11 @@ class _CachedState:
 class _UNetPatchCache:
     """What a plan keeps ACROSS steps when the patch cache is on (SURVEY.md row f-3, SDXL variant;
     reference: CacheManager.get_mask, cache_manager.py:101-159, called once per down / mid / up block,
-    modules/unet_2d_blocks.py:40,102,180,250,345). Per UNet block with attention: the block input of the
-    previous step (and, for an up block, of every skip tensor it consumes) for the MSE features, the skip
-    counters and the mask of its 256-row patches. Per Transformer2D of such a block: its residual
-    stream, its output and the fused q|k|v of every layer -- rows of clean patches are not rewritten, so
-    they hold what the patch had when it was last computed. These buffers are owned here, not carved
+    modules/unet_2d_blocks.py:40,102,180,250,345). Per UNet block: the block input of the previous step
+    (and, for an up block, of every skip tensor it consumes) for the MSE features, the skip counters and
+    the mask of its 256-row patches. Per convolution of the block (conv1, conv2, shortcut, sampler) its
+    output, per Transformer2D its residual stream, its output and the fused q|k|v of every layer -- what
+    lies in clean patches is not rewritten, so it holds what the patch had when it was last computed. These buffers are owned here, not carved
     from the model's arena (the arena is shared by all plans and overwritten by whichever ran last).
     Validity is per latent and by plan slot, exactly as for the SD3.5 cache (sd3_transformer._PatchCache)."""
 
@@ -549,9 +549,9 @@ class B200UNet(torch.nn.Module):
         row continues with the MSE of each of the block's skip tensors (reference: the cuML forests of
         ESYMRED_DOWNSAMPLE_PATH / ESYMRED_UPSAMPLE_PATH, cache_manager.py:27-36,101-159; refresh = 4:
         forced recompute after four skips, :147). forest=None switches the cache off.
-        What is skipped here: the Transformer2D modules of a block (76 % of the step's time), per 256-row
-        patch of the packed pixel rows; resnets, samplers and GroupNorms are always recomputed (DESIGN.md
-        section 10)."""
+        What a clean patch skips: the block's Transformer2D modules (per 256-row patch of the packed pixel
+        rows) and the convolutions of its resnets and samplers (per strip of 16 pixel rows); GroupNorms
+        always run over the whole tensor, as in the reference."""
         import collections
         self.patch_forest, self.patch_forest_up, self.patch_refresh = forest, forest_up or forest, refresh
         self._cache_lru, self._cache_max = collections.OrderedDict(), max_cached_plans
@@ -598,8 +598,8 @@ class B200UNet(torch.nn.Module):
         return st.mask
 
     def _run_cached(self, pl: _Plan):
-        """The forward with the patch cache: _run plus one decision per UNet block with attention
-        (total_blocks numbering of modules/unet.py:369-503: down blocks 0.., mid, up blocks)."""
+        """The forward with the patch cache: _run plus one decision per UNet block (down blocks, mid, up
+        blocks: the total_blocks numbering of modules/unet.py:369-503)."""
         return self._run(pl, pl.cache)
 
     def _run(self, pl: _Plan, cb=None):
@@ -633,11 +633,9 @@ class B200UNet(torch.nn.Module):
         skips = [x]
         level = 0
         for i in range(len(ch)):
-            mask = self._decide(pl, cb, f"down_blocks.{i}", level, i, x) \
-                if (cb is not None and cfg.down_has_attn[i]) else None
-            cbi = cb if (cb is not None and cfg.down_has_attn[i]) else None
+            mask = self._decide(pl, cb, f"down_blocks.{i}", level, i, x) if cb is not None else None
             for j in range(cfg.layers_per_block):
-                x = self._resnet(pl, x, f"down_blocks.{i}.resnets.{j}", level, temb_all, cbi, mask)
+                x = self._resnet(pl, x, f"down_blocks.{i}.resnets.{j}", level, temb_all, cb, mask)
                 if cfg.down_has_attn[i]:
                     x = self._transformer(pl, x, f"down_blocks.{i}.attentions.{j}", level,
                                           cfg.num_heads[i], cfg.transformer_layers_per_block[i], kv_all,
@@ -646,7 +644,7 @@ class B200UNet(torch.nn.Module):
             if i != len(ch) - 1:
                 name = f"down_blocks.{i}.downsamplers.0.conv"
                 x = self._conv(pl, x, x.shape[1], name, level, 2,
-                               (cbi.buf if cbi is not None else pl.buf)(name, pl.levels[level + 1].T, x.shape[1]),
+                               (cb.buf if cb is not None else pl.buf)(name, pl.levels[level + 1].T, x.shape[1]),
                                mask=mask, mask_scale=2, epi=ops.EPI_BIAS)
                 level += 1
                 skips.append(x)
@@ -660,16 +658,14 @@ class B200UNet(torch.nn.Module):
         rev_heads = list(reversed(cfg.num_heads))
         for i in range(len(ch)):
             mask = self._decide(pl, cb, f"up_blocks.{i}", level, len(ch) + 1 + i, x,
-                                skips[-(cfg.layers_per_block + 1):]) \
-                if (cb is not None and rev_attn[i]) else None
+                                skips[-(cfg.layers_per_block + 1):]) if cb is not None else None
             for j in range(cfg.layers_per_block + 1):
                 skip = skips.pop()
                 T, c1, c2 = x.shape[0], x.shape[1], skip.shape[1]
                 cat = pl.buf(f"up_blocks.{i}.cat{j}", T, c1 + c2)
                 ops.copy_cols(x, cat, c1)
                 ops.copy_cols(skip, cat[:, c1:], c2)
-                x = self._resnet(pl, cat, f"up_blocks.{i}.resnets.{j}", level, temb_all,
-                                 cb if rev_attn[i] else None, mask)
+                x = self._resnet(pl, cat, f"up_blocks.{i}.resnets.{j}", level, temb_all, cb, mask)
                 if rev_attn[i]:
                     x = self._transformer(pl, x, f"up_blocks.{i}.attentions.{j}", level, rev_heads[i],
                                           rev_layers[i], kv_all, cb, mask)
@@ -681,7 +677,7 @@ class B200UNet(torch.nn.Module):
                 ops.upsample2x(x, lo.desc, hi.desc, L, hi.max_pixels, C, up)
                 level -= 1
                 x = self._conv(pl, up, C, name, level, 1,
-                               (cb.buf if (cb is not None and rev_attn[i]) else pl.buf)(name, hi.T, C),
+                               (cb.buf if cb is not None else pl.buf)(name, hi.T, C),
                                mask=mask, mask_scale=-2, epi=ops.EPI_BIAS)
         h = self._gn(pl, x, "conv_norm_out", 0, pl.buf(f"gn0_{ch[0]}", l0.T, ch[0]), True)
         o = self._conv(pl, h, ch[0], "conv_out", 0, 1, pl.buf("conv_out", l0.T, self.n_out_pad), epi=ops.EPI_BIAS)

@@ -78,7 +78,7 @@ def test_cached_oracle_is_exact_when_everything_is_flagged_and_skips_clean_patch
 
 
 def test_cached_sdxl_oracle_is_exact_when_everything_is_flagged_and_follows_the_refresh_rule():
-    """SDXL variant (oracle.patch_cache.CachedSDXLOracle): one decision per UNet block with attention,
+    """SDXL variant (oracle.patch_cache.CachedSDXLOracle): one decision per UNet block,
     refresh = 4 (cache_manager.py:147), an up block's features include the MSE of its skip tensors."""
     from oracle import patch_cache as pc
     from oracle import sdxl_unet as ox
@@ -98,21 +98,21 @@ def test_cached_sdxl_oracle_is_exact_when_everything_is_flagged_and_follows_the_
     orc = pc.CachedSDXLOracle(sd, cfg, rule, refresh=4)
     out, masks = orc.forward_latent("a", lat, emb, ctx, 801.0)
     assert torch.equal(out, ref)                                     # first sight: everything computed
-    assert set(masks) == {"down_blocks.1", "down_blocks.2", "mid_block", "up_blocks.0", "up_blocks.1"}
-    assert [len(masks[k]) for k in ("down_blocks.1", "down_blocks.2", "mid_block", "up_blocks.0", "up_blocks.1")] \
-        == [4, 1, 1, 1, 4] and all(all(m) for m in masks.values())
+    order = ("down_blocks.0", "down_blocks.1", "down_blocks.2", "mid_block", "up_blocks.0", "up_blocks.1", "up_blocks.2")
+    assert tuple(masks) == order
+    assert [len(masks[k]) for k in order] == [16, 4, 1, 1, 1, 4, 16] and all(all(m) for m in masks.values())
     # block numbering of modules/unet.py:369-503 and the feature count (up blocks: input + 3 skips)
-    assert seen_feats == [(1, (4, 1)), (2, (1, 1)), (3, (1, 1)), (4, (1, 4)), (5, (4, 4))]
+    assert seen_feats == [(0, (16, 1)), (1, (4, 1)), (2, (1, 1)), (3, (1, 1)), (4, (1, 4)), (5, (4, 4)), (6, (16, 4))]
     pattern = []
     for _ in range(6):                                               # the same input again and again
         out2, masks2 = orc.forward_latent("a", lat, emb, ctx, 801.0)
         pattern.append([any(m) for m in masks2.values()])
         assert torch.allclose(out2, ref, atol=1e-5)                  # reuse of unchanged patches is exact
-    assert pattern == [[False] * 5] * 4 + [[True] * 5] + [[False] * 5]   # four skips, then the forced refresh
+    assert pattern == [[False] * 7] * 4 + [[True] * 7] + [[False] * 7]   # four skips, then the forced refresh
     lat2 = lat.clone()
     lat2[:, :, :16] += 0.5 * torch.randn(1, 4, 16, 64, generator=g)  # the top quarter of the image changes
     out3, masks3 = orc.forward_latent("a", lat2, emb, ctx, 801.0)
-    assert masks3["down_blocks.1"][0]            # (GroupNorm couples the whole image: the other bands move too)
+    assert masks3["down_blocks.0"][0] and masks3["down_blocks.1"][0]   # (GroupNorm couples the whole image: the other bands move too)
     ref3 = ox.unet_single(sd, cfg, lat2, emb, ctx)
     assert torch.nn.functional.cosine_similarity(out3.flatten(), ref3.flatten(), dim=0) > 0.99
     full = {k: [True] * len(m) for k, m in masks3.items()}

@@ -10,7 +10,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-BLOCKS = ("down_blocks.1", "down_blocks.2", "mid_block", "up_blocks.0", "up_blocks.1")
+BLOCKS = ("down_blocks.0", "down_blocks.1", "down_blocks.2", "mid_block", "up_blocks.0", "up_blocks.1", "up_blocks.2")
 
 
 def test_up_block_decision_uses_the_skip_tensors(cuda):
@@ -87,10 +87,10 @@ def _step(pipe, reqs):
 
 
 def test_cached_sdxl_step_matches_oracle_policy_and_exact_forward(cuda):
-    """Four steps of a two-request batch (512^2 and 1024^2, CFG on: 4 latents; 4 / 16 patches per latent
-    at level 1, 1 / 4 at level 2) with the cache on. Step 0: nothing kept, everything computed -- equal to
+    """Four steps of a two-request batch (512^2 and 1024^2, CFG on: 4 latents; 16 / 64 patches per latent
+    at level 0, 4 / 16 at level 1, 1 / 4 at level 2) with the cache on. Step 0: nothing kept, everything computed -- equal to
     the uncached step bit for bit. Step 1: rule 'never' -> every patch reused. Steps 2, 3: rule 'MSE > the
-    median of what down block 1 saw', part of one image disturbed in between -> a mixture. Per step and
+    median of what down block 0 saw', part of one image disturbed in between -> a mixture. Per step and
     request the applied prediction is compared with CachedSDXLOracle run with the SAME masks."""
     import _parity as P
     from oracle import patch_cache as pc
@@ -107,8 +107,9 @@ def test_cached_sdxl_step_matches_oracle_policy_and_exact_forward(cuda):
     orc = pc.CachedSDXLOracle(sd, oc, refresh=4)
     sig, ts, _ = osch.euler_sigmas(50)
     order = [("512", 0), ("512", 1), ("1024", 0), ("1024", 1)]      # plan order: per resolution [uncond, cond]
-    rows = {"512": {1: 1024, 2: 256}, "1024": {1: 4096, 2: 1024}}
-    level = {"down_blocks.1": 1, "down_blocks.2": 2, "mid_block": 2, "up_blocks.0": 2, "up_blocks.1": 1}
+    rows = {"512": {0: 4096, 1: 1024, 2: 256}, "1024": {0: 16384, 1: 4096, 2: 1024}}
+    level = {"down_blocks.0": 0, "down_blocks.1": 1, "down_blocks.2": 2, "mid_block": 2, "up_blocks.0": 2,
+             "up_blocks.1": 1, "up_blocks.2": 0}
     seen = []
     for k in range(4):
         before = P.snapshot(reqs)
@@ -148,7 +149,7 @@ def test_cached_sdxl_step_matches_oracle_policy_and_exact_forward(cuda):
             assert P.ok(cos, err, scale), (k, res, cos, err / scale)
         if k == 1:
             assert not seen[1].any()                                 # rule 'never': everything reused
-            tau = float(plan.cache.blocks["down_blocks.1"].mse.median())
+            tau = float(plan.cache.blocks["down_blocks.0"].mse.median())   # (the first block always sees the new latents)
             model.enable_patch_cache(ops.DeviceForest.threshold_rule(tau, cuda), refresh=4)
         # disturb the top quarter of the 1024^2 image before the next step
         lat = reqs["1024"][0].sampling_params.latents.clone()
@@ -183,7 +184,7 @@ def test_sdxl_cache_refresh_recomposition_and_unaligned_levels(cuda):
     _step(pipe, {**a, **b})
     m4 = masks(4)
     # 768^2 at level 2 is 24 x 24 = 576 rows, not whole 256-row patches: those blocks run uncached
-    assert set(m4) == {"down_blocks.1", "up_blocks.1"} and allm(m4)
+    assert set(m4) == {"down_blocks.0", "down_blocks.1", "up_blocks.1", "up_blocks.2"} and allm(m4)
     _step(pipe, a)
     assert allm(masks(2))                                    # back, but a step was missed: recompute
     _step(pipe, a)
