@@ -760,16 +760,8 @@ extern "C" int b200_attn_varlen_ex(const B200AttnSource* src_a, const B200AttnSo
 #endif
   const int extras = (a.causal != 0 || a.rel_bias != nullptr) ? 2 : (a.q_mask != nullptr ? 1 : 0);
   auto kern = extras == 2 ? attn_fwd_kernel<2> : (extras == 1 ? attn_fwd_kernel<1> : attn_fwd_kernel<0>);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
-    if (err == cudaSuccess)
-      err = cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
-    if (err == cudaSuccess)
-      err = cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
-    if (err != cudaSuccess) return static_cast<int>(err);
-    configured = true;
-  }
+  static unsigned long long configured[3] = {0, 0, 0};
+  if (int rc = ensure_dynamic_smem(kern, ATT_SMEM, &configured[extras])) return rc;
   dim3 grid(n_ctas);
   return launch_pdl(kern, grid, dim3(ATT_THREADS), ATT_SMEM,
                     reinterpret_cast<cudaStream_t>(stream_), tm[0][0], tm[1][0], tm[0][1], tm[1][1],

@@ -390,13 +390,8 @@ static int launch_conv(const CUtensorMap& tmW, const ConvArgs& a, const EpiArgs&
                        int num_sms, cudaStream_t stream) {
   using Cfg = ConvCfg<BN, EPI, MT, TWO>;
   auto kern = conv3x3_kernel<BN, EPI, MT, TWO>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t err =
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (err != cudaSuccess) return static_cast<int>(err);
-    configured = true;
-  }
+  static unsigned long long configured = 0;
+  if (int rc = ensure_dynamic_smem(kern, Cfg::kSmemBytes, &configured)) return rc;
   if constexpr (TWO) {
     const int tiles = ((a.n_mtiles + 1) / 2) * ((a.Cout + BN - 1) / BN);
     const int grid = (tiles < num_sms / 2 ? tiles : num_sms / 2) * 2;

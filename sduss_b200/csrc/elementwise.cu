@@ -268,12 +268,8 @@ static int launch_ln_v(const LnArgs& a, cudaStream_t st) {
   const bool has_params = a.gamma || a.mod;
   const size_t smem = has_params ? size_t(2) * nout * 4 * (a.D >> 3) * sizeof(float4) : 0;
   auto kern = ln_mod_kernel<NIT, FULL, PF, MB>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2 * 4 * LN_MAXIT * 32 * 16) != cudaSuccess)
-      return B200_ERR_DRIVER;
-    configured = true;
-  }
+  static unsigned long long configured = 0;
+  if (int rc = ensure_dynamic_smem(kern, 2 * 2 * 4 * LN_MAXIT * 32 * 16, &configured)) return rc;
   return launch_pdl(kern, dim3((a.T + rows_per_block - 1) / rows_per_block), dim3(LN_THREADS), smem, st,
                     a, rows_per_block);
 }

@@ -397,13 +397,8 @@ static int launch_gemm_mc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
                           cudaStream_t stream) {
   using Cfg = GemmCfg<BN, EPI, TWO>;
   auto kern = gemm_bf16_kernel<BN, EPI, MC, TWO>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t err =
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (err != cudaSuccess) return static_cast<int>(err);
-    configured = true;
-  }
+  static unsigned long long configured = 0;
+  if (int rc = ensure_dynamic_smem(kern, Cfg::kSmemBytes, &configured)) return rc;
   const int tiles = ((s.M + BM * MC - 1) / (BM * MC)) * ((s.N + BN - 1) / BN);
   int slots = num_sms / MC;
   if constexpr (MC == 4) {  // clusters of 4 do not pack all GPCs: ask how many are co-resident

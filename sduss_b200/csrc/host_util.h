@@ -26,6 +26,20 @@ inline int launch_status() {
 
 int device_sm_count();
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel AND device: the attribute belongs to
+// the current device's context, so a process that switches devices must set it again there (`done` is
+// the caller's static bit mask, one bit per device ordinal; ordinals >= 64 set it on every call).
+template <typename K>
+inline int ensure_dynamic_smem(K kern, int bytes, unsigned long long* done) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return B200_ERR_DRIVER;
+  if (dev < 64 && ((*done >> dev) & 1ull)) return B200_OK;
+  const cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (err != cudaSuccess) return static_cast<int>(err);
+  if (dev < 64) *done |= 1ull << dev;
+  return B200_OK;
+}
+
 // Tile-width choice for the 128-row tcgen05 GEMM / implicit-GEMM kernels. A tile of 128 x BN does
 // 2 BN tensor-pipe cycles per 64-deep K block and pulls 16 KB of A plus BN x 128 B of W through
 // L2 -> SM (W halved when CTA pairs multicast it). Small-M, deep-K problems (SDXL's level-2 token
