@@ -168,6 +168,20 @@ int b200_attn_varlen_ex(const B200AttnSource* src_a, const B200AttnSource* src_b
                         int32_t* sched_state, int max_ctas, float softmax_scale,
                         const B200AttnExtra* extra, void* stream);
 
+/* SDXL cross attention with a SHORT key sequence (queries: segment A rows of q_src, keys / values:
+ * segment B rows of kv_src, at most b200_attn_cross_short_max_keys() = 80 per sequence: the 77 text
+ * tokens; reference: modules/attention.py:59-110). Same seq_table as above (only qa_row, qa_len, kb_row,
+ * kb_len are read), no work list and no scratch memory: one CTA per 128 query rows of a (sequence,
+ * head), grid sized from max_q_len = the longest qa_len. A launch of this shape is ~1 GFLOP -- latency,
+ * not throughput -- and takes a third of the time of the persistent kernel above, which remains the
+ * fallback for longer key sequences (B200_ERR_UNSUPPORTED when max_kv_len is too large).
+ * q_mask (patch cache, may be NULL): as in B200AttnExtra, one int32 per 2^q_mask_shift rows (>= 7). */
+int b200_attn_cross_short_max_keys(void);
+int b200_attn_cross_short_bf16(const B200AttnSource* q_src, const B200AttnSource* kv_src,
+                               const int32_t* seq_table, int n_seq, int n_heads, int max_q_len,
+                               int max_kv_len, float softmax_scale, const int32_t* q_mask,
+                               int q_mask_shift, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * HBM-bound kernels (coalesced 16-byte vectors, warp-shuffle reductions).
  * ---------------------------------------------------------------------------------------- */

@@ -113,6 +113,8 @@ SIGNATURES = {
     "b200_layernorm_mod_bf16": [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                 c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
                                 c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
+    "b200_attn_cross_short_bf16": [ctypes.POINTER(AttnSource), ctypes.POINTER(AttnSource), c_void_p, c_int, c_int,
+                                   c_int, c_int, c_float, c_void_p, c_int, c_void_p],
     "b200_patch_mask_bf16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(Forest), c_int, c_int,
                              c_void_p, c_void_p],
@@ -165,6 +167,8 @@ def _bind():
     lib.b200_groupnorm_workspace_bytes.restype = ctypes.c_longlong
     lib.b200_patch_mask_workspace_bytes.argtypes = [c_int]
     lib.b200_patch_mask_workspace_bytes.restype = ctypes.c_longlong
+    lib.b200_attn_cross_short_max_keys.argtypes = []
+    lib.b200_attn_cross_short_max_keys.restype = c_int
     lib.b200_attn_workspace_bytes.argtypes = []
     lib.b200_attn_workspace_bytes.restype = ctypes.c_longlong
     lib.b200_conv3x3_maps_bytes.argtypes = [c_int]

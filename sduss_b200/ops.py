@@ -399,6 +399,23 @@ def attn_varlen(src_a, src_b, seq_table, work_units, n_units, sched_state, max_c
         _ev.record()
 
 
+ATTN_CROSS_SHORT_KEYS = lib.b200_attn_cross_short_max_keys()
+
+
+def attn_cross_short(src_q, src_kv, seq_table, n_seq, n_heads, max_q_len, max_kv_len, scale, q_mask=None,
+                     q_mask_shift=8):
+    """Cross attention against at most ATTN_CROSS_SHORT_KEYS keys per sequence (SDXL: the 77 text tokens):
+    Q = segment A rows of src_q, K / V = segment B rows of src_kv, same seq_table as attn_varlen."""
+    _ev = _count("b200_attn_cross_short_bf16", (src_q.q_rows, max_kv_len, n_seq * n_heads))
+    if q_mask is not None:
+        _req(q_mask, torch.int32)
+    check(lib.b200_attn_cross_short_bf16(ctypes.byref(src_q), ctypes.byref(src_kv), _ptr(seq_table), n_seq,
+                                         n_heads, max_q_len, max_kv_len, ctypes.c_float(scale), _ptr(q_mask),
+                                         q_mask_shift, _stream()), "b200_attn_cross_short_bf16")
+    if _ev is not None:
+        _ev.record()
+
+
 class DeviceForest:
     """A RandomForest flattened into device arrays for b200_patch_mask_bf16. Build it from a fitted
     sklearn RandomForestClassifier (`from_sklearn`) or from explicit arrays; `threshold_rule(tau)` is

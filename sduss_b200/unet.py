@@ -108,6 +108,9 @@ class _Plan:
             crossp = [(lay.row_off[i], lay.rows[i], 0, 0, 0, 0, i * ctx_len, ctx_len) for i in range(L)]
             self.self_plan[l] = ops.build_attn_plan(selfp, dev, cfg.num_heads[l])
             self.cross_plan[l] = ops.build_attn_plan(crossp, dev, cfg.num_heads[l])
+        # 77 text tokens: the short-key cross-attention kernel (no work list: it reads the plan's seq_table)
+        self.cross_short = ctx_len <= ops.ATTN_CROSS_SHORT_KEYS and os.environ.get("SDUSS_B200_NO_XSHORT", "0") != "1"
+        self.max_rows = {l: max(lay.rows) for l, lay in enumerate(self.levels)}
         self.gn_ws = ops.groupnorm_workspace(self.levels[0].T, L, dev)
         self.arena, self.block, self.arena_off = model.arena, None, 0
         self.bufs: Dict[str, torch.Tensor] = {}
@@ -479,7 +482,11 @@ class B200UNet(torch.nn.Module):
             src_kv = pl.attn_src.get((b, "kv"))
             if src_kv is None:
                 src_kv = pl.attn_src[(b, "kv")] = ops.attn_source(k=kv_all, k_col=ko, v=kv_all, v_col=ko + C)
-            ops.attn_varlen(pl.attn_src[(level, C, "q")], src_kv, *pl.cross_plan[level], 0.125, q_mask=mask)
+            if pl.cross_short:
+                ops.attn_cross_short(pl.attn_src[(level, C, "q")], src_kv, pl.cross_plan[level][0], pl.L, heads,
+                                     pl.max_rows[level], pl.ctx_len, 0.125, q_mask=mask)
+            else:
+                ops.attn_varlen(pl.attn_src[(level, C, "q")], src_kv, *pl.cross_plan[level], 0.125, q_mask=mask)
             G(att, w[b + ".attn2.out.weight"], h, bias=w[b + ".attn2.out.bias"], epi=ops.EPI_GATE_RESID, resid=h,
               rowpart_out=rp)
             ln_gemm(".norm3", ".ff1", ff, epi=ops.EPI_GEGLU)

@@ -131,3 +131,63 @@ def test_deterministic_and_batch_invariant(cuda):
     for m in (1, 5, 100000):
         oa3, ob3 = _joint(cuda, qkv_a, qkv_b, img_lens, ctx, max_ctas=m)
         assert torch.equal(oa, oa3) and torch.equal(ob, ob3), m
+
+
+@pytest.mark.parametrize("T", [77, 13, 80])
+def test_cross_short_keys(cuda, T):
+    """b200_attn_cross_short_bf16 (SDXL cross attention, <= 80 keys per sequence) vs fp32 softmax
+    attention and vs the persistent kernel on the same inputs; ragged query lengths (partial 128-row
+    tiles, a partial 16-row warp tile), K / V and Q / out living at column offsets of wider buffers;
+    the query-tile mask of the patch cache."""
+    from sduss_b200 import ops
+    img_lens = (1024, 4096, 256, 328)
+    C = H * 64
+    qbuf = _rand((sum(img_lens), C + 64), cuda, 3)            # q at column 64 of a wider buffer
+    kv = _rand((len(img_lens) * T, 2 * C + 128), cuda, 4)     # k at column 128, v right after
+    q = qbuf[:, 64:]
+    seqs, ra = [], 0
+    for i, s in enumerate(img_lens):
+        seqs.append((ra, s, 0, 0, 0, 0, i * T, T))
+        ra += s
+    plan = ops.build_attn_plan(seqs, cuda, H)
+    sb = ops.attn_source(k=kv, k_col=128, v=kv, v_col=128 + C)
+    out = torch.zeros(sum(img_lens), C + 64, device=cuda, dtype=torch.bfloat16)
+    sa = ops.attn_source(q=qbuf, q_col=64, out=out, o_col=64)
+    ops.attn_cross_short(sa, sb, plan[0], len(img_lens), H, max(img_lens), T, 0.125)
+    big = torch.zeros_like(out)
+    ops.attn_varlen(ops.attn_source(q=qbuf, q_col=64, out=big, o_col=64), sb, *plan, 0.125)
+    torch.cuda.synchronize()
+    assert (out[:, :64] == 0).all()                            # nothing written outside the head columns
+    ra = 0
+    for i, s in enumerate(img_lens):
+        kk = kv[i * T:(i + 1) * T, 128:].reshape(T, 2, H, 64)
+        ref = _ref(q[ra:ra + s].reshape(s, H, 64), kk[:, 0], kk[:, 1], 0.125).reshape(s, C)
+        _check(out[ra:ra + s, 64:], ref)
+        ra += s
+    d = (out.float() - big.float()).abs().max().item()
+    assert d <= 2e-2 * big.float().abs().max().item(), d      # the two kernels agree to bf16 rounding
+    # deterministic, and a sequence's result does not depend on its neighbours
+    out2 = torch.zeros_like(out)
+    ops.attn_cross_short(ops.attn_source(q=qbuf, q_col=64, out=out2, o_col=64), sb, plan[0], len(img_lens), H,
+                         max(img_lens), T, 0.125)
+    solo = torch.zeros_like(out)
+    one = ops.build_attn_plan([seqs[1]], cuda, H)
+    ops.attn_cross_short(ops.attn_source(q=qbuf, q_col=64, out=solo, o_col=64), sb, one[0], 1, H, img_lens[1], T, 0.125)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+    assert torch.equal(solo[1024:1024 + 4096], out[1024:1024 + 4096])
+    # query-tile mask (256-row chunks of the packed rows): clean chunks keep what the buffer held
+    n_chunks = (sum(img_lens) + 255) // 256
+    mask = (torch.arange(n_chunks) % 3 != 1).int().cuda()
+    m = torch.full_like(out, 7.0)
+    ops.attn_cross_short(ops.attn_source(q=qbuf, q_col=64, out=m, o_col=64), sb, plan[0], len(img_lens), H,
+                         max(img_lens), T, 0.125, q_mask=mask)
+    torch.cuda.synchronize()
+    rows = torch.zeros(sum(img_lens), dtype=torch.bool, device=cuda)
+    ra = 0
+    for s in img_lens:                                         # a tile is looked up by its first row
+        for t0 in range(0, s, 128):
+            if mask[(ra + t0) >> 8] != 0:
+                rows[ra + t0:ra + min(t0 + 128, s)] = True
+        ra += s
+    assert torch.equal(m[rows][:, 64:], out[rows][:, 64:]) and (m[~rows] == 7.0).all()
