@@ -494,6 +494,10 @@ extern "C" int b200_gemm_bf16(const void* A, int lda, const void* W, int ldw, in
     const long t256 = mt * ((N + 255) / 256), t192 = mt * ((N + 191) / 192);
     if (!no192 && BN == 256 && t256 * 4 <= 3L * sms && t192 <= sms && t192 > t256) BN = 192;
   }
+  if (const char* fb = getenv("SDUSS_B200_FORCE_BN")) {  // experiment hook (tools/bench_gemm_bn.py), read per call
+    const int v = atoi(fb);
+    if ((v == 128 || v == 192 || v == 256) && N >= v) BN = v;
+  }
 
   // pair CTAs (W-tile multicast) whenever there are at least two M tiles and enough pairs of
   // tiles to occupy the 74 SM pairs
