@@ -162,6 +162,11 @@ typedef struct B200AttnExtra {
   int32_t q_mask_shift;    /* patch cache: q_mask[row >> shift] (shift >= 7) == 0 */
   const int32_t* q_mask;   /* marks segment-A query rows to skip (output rows stay untouched);     */
                            /* keys / values of skipped rows are still read. NULL = all computed.   */
+  int32_t bounded_logits;  /* 1: the caller guarantees |logit * softmax_scale * log2(e)| <= 64 for  */
+                           /* every pair (SD3.5: q and k are RMS-normalised per head, the model     */
+                           /* checks its learned norm weights at load). The kernel then runs the   */
+                           /* softmax without a reference maximum (same result, one pass less in   */
+                           /* the step's dependent chain). Ignored with causal / rel_bias.          */
 } B200AttnExtra;
 int b200_attn_varlen_ex(const B200AttnSource* src_a, const B200AttnSource* src_b,
                         const int32_t* seq_table, const int32_t* work_units, int n_units,

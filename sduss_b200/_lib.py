@@ -48,7 +48,8 @@ ACT_DEFAULT, ACT_GELU_TANH, ACT_GELU_ERF, ACT_QUICK_GELU = 0, 1, 2, 3
 class AttnExtra(ctypes.Structure):
     """Mirror of B200AttnExtra: causal mask / relative position bias of the text encoders."""
     _fields_ = [("causal", ctypes.c_int32), ("rel_len", ctypes.c_int32), ("rel_bias", c_void_p),
-                ("rel_ld", ctypes.c_int32), ("q_mask_shift", ctypes.c_int32), ("q_mask", c_void_p)]
+                ("rel_ld", ctypes.c_int32), ("q_mask_shift", ctypes.c_int32), ("q_mask", c_void_p),
+                ("bounded_logits", ctypes.c_int32)]
 
 
 class Forest(ctypes.Structure):

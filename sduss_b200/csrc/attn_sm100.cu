@@ -32,6 +32,7 @@
 #include "host_util.h"
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <queue>
 #include <vector>
 
@@ -105,6 +106,14 @@ struct AttnArgs {
   const int* q_mask; int q_mask_shift;
   long long* dbg;                    // optional phase cycle counters (ATT_TIMING builds)
 };
+// BOUNDED (second template flag of the kernel; denoising instantiations, with or without the query-tile mask): the caller guarantees
+// |logit * softmax_scale * log2(e)| <= 64 for every (query, key) pair -- SD3.5's joint attention, whose q
+// and k are RMS-normalised per head (|q|, |k| <= 8 max|w|: the model checks the learned weights at load,
+// sd3_transformer.py). exp2 of such a value needs no reference maximum: bf16 / fp32 hold 2^-64 .. 2^64
+// with full relative precision, the row sum and the P V accumulation stay far inside fp32. The softmax
+// warps then skip the row-maximum pass (255 of the ~2300 cycles of a step's dependent chain, the bound of
+// this kernel: DESIGN.md 4.1), the running maximum and the O rescale; the result is the same softmax,
+// rounded at different points.
 
 #ifdef ATT_TIMING
 #define ATT_T(var) const long long var = clock64()
@@ -178,7 +187,7 @@ __device__ __forceinline__ float2 poly_exp2_pair(float2 x) {
 }
 #endif
 
-template <int EXTRAS>
+template <int EXTRAS, bool BOUNDED = false>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant__ CUtensorMap tmQB,
                 const __grid_constant__ CUtensorMap tmKA, const __grid_constant__ CUtensorMap tmKB,
@@ -491,23 +500,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
               if (kpos0 + i > qpos) s[i] = -INFINITY;
           }
         }
-        // 8 independent chains (one long fmax chain would expose its full latency)
-        float mx8[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) mx8[i] = s[i];
-#pragma unroll
-        for (int i = 8; i < ATT_BN; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], s[i]);
-        const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
-                               fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
-        const float m_new = fmaxf(m_run, mx);
-        // lazy rescale: only move the reference max when it grew by more than 2^8
-        const bool resc = (m_new - m_run) * sc > ATT_RESCALE_THRESHOLD;
         float alpha = 1.f;
-        if (resc) {
-          alpha = fast_exp2((m_run - m_new) * sc);
-          m_run = m_new;
+        bool resc = false;
+        if constexpr (!BOUNDED) {
+          // 8 independent chains (one long fmax chain would expose its full latency)
+          float mx8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) mx8[i] = s[i];
+#pragma unroll
+          for (int i = 8; i < ATT_BN; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], s[i]);
+          const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                                 fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+          const float m_new = fmaxf(m_run, mx);
+          // lazy rescale: only move the reference max when it grew by more than 2^8
+          resc = (m_new - m_run) * sc > ATT_RESCALE_THRESHOLD;
+          if (resc) {
+            alpha = fast_exp2((m_run - m_new) * sc);
+            m_run = m_new;
+          }
         }
-        const float m_sc = m_run * sc;
+        const float m_sc = BOUNDED ? 0.f : m_run * sc;  // BOUNDED: exp2(s * sc) as it is
         ATT_T(c3);
         uint32_t pk[ATT_BN / 2];
 #if ATT_F32X2
@@ -759,9 +771,16 @@ extern "C" int b200_attn_varlen_ex(const B200AttnSource* src_a, const B200AttnSo
   }
 #endif
   const int extras = (a.causal != 0 || a.rel_bias != nullptr) ? 2 : (a.q_mask != nullptr ? 1 : 0);
-  auto kern = extras == 2 ? attn_fwd_kernel<2> : (extras == 1 ? attn_fwd_kernel<1> : attn_fwd_kernel<0>);
-  static unsigned long long configured[3] = {0, 0, 0};
-  if (int rc = ensure_dynamic_smem(kern, ATT_SMEM, &configured[extras])) return rc;
+  // bounded logits (see AttnArgs): the denoising instantiation without the row-maximum pass
+  static const bool no_bounded = []() { const char* v = getenv("SDUSS_B200_NO_BOUNDED"); return v && v[0] == '1'; }();
+  // (also with the patch cache's query-tile mask: a cached step with every patch flagged stays
+  //  bit-identical to the uncached one)
+  const bool bounded = extras <= 1 && extra != nullptr && extra->bounded_logits != 0 && !no_bounded;
+  auto kern = extras == 2 ? attn_fwd_kernel<2>
+            : extras == 1 ? (bounded ? attn_fwd_kernel<1, true> : attn_fwd_kernel<1>)
+                          : (bounded ? attn_fwd_kernel<0, true> : attn_fwd_kernel<0>);
+  static unsigned long long configured[5] = {0, 0, 0, 0, 0};
+  if (int rc = ensure_dynamic_smem(kern, ATT_SMEM, &configured[bounded ? 3 + extras : extras])) return rc;
   dim3 grid(n_ctas);
   return launch_pdl(kern, grid, dim3(ATT_THREADS), ATT_SMEM,
                     reinterpret_cast<cudaStream_t>(stream_), tm[0][0], tm[1][0], tm[0][1], tm[1][1],

@@ -374,14 +374,16 @@ def build_attn_plan(seqs, device, n_heads, max_ctas=None):
 
 
 def attn_varlen(src_a, src_b, seq_table, work_units, n_units, sched_state, max_ctas, scale,
-                causal=False, rel_bias=None, rel_len=0, q_mask=None, q_mask_shift=8):
+                causal=False, rel_bias=None, rel_len=0, q_mask=None, q_mask_shift=8, bounded=False):
     """rel_bias: fp32 [heads, >= 2 rel_len - 1], bias of key offset (k - q) at column k - q + rel_len - 1,
-    already divided by `scale` (T5); causal: CLIP's mask. Both off on the denoising path."""
+    already divided by `scale` (T5); causal: CLIP's mask. Both off on the denoising path.
+    bounded: the caller guarantees |logit * scale * log2(e)| <= 64 (B200AttnExtra.bounded_logits)."""
     _ev = _count("b200_attn_varlen_bf16", (src_a.q_rows, src_a.kv_rows, n_units))
     extra = None
-    if causal or rel_bias is not None or q_mask is not None:
+    if causal or rel_bias is not None or q_mask is not None or bounded:
         extra = _lib.AttnExtra()
         extra.causal = int(causal)
+        extra.bounded_logits = int(bool(bounded))
         if q_mask is not None:  # patch cache: query tiles of clean patches (segment A) are skipped
             _req(q_mask, torch.int32)
             extra.q_mask, extra.q_mask_shift = _ptr(q_mask), q_mask_shift

@@ -255,6 +255,17 @@ class B200SD3Transformer2DModel(torch.nn.Module):
                 blk["out2_w"], blk["out2_b"] = w(b + ".attn2.to_out.0.weight"), w(b + ".attn2.to_out.0.bias")
             blk["ff1_w"], blk["ff1_b"] = w(b + ".ff.net.0.proj.weight"), w(b + ".ff.net.0.proj.bias")
             blk["ff2_w"], blk["ff2_b"] = w(b + ".ff.net.2.weight"), w(b + ".ff.net.2.bias")
+            # q and k are RMS-normalised per head and scaled by learned weights: |q| <= 8 max|w_q|,
+            # |k| <= 8 max|w_k| (head_dim 64), so |logit * scale * log2 e| <= 64 max|w_q| max|w_k| / 8 * 1.4427
+            # (+1 % for the bf16 rounding of q and k). When that is <= 64 the attention kernel may run its
+            # softmax without a reference maximum (B200AttnExtra.bounded_logits); checked per block and per
+            # attention from the weights actually loaded, never assumed.
+            def _bounded(qs, ks):
+                wq = max(float(blk[n].float().abs().max()) for n in qs)
+                wk = max(float(blk[n].float().abs().max()) for n in ks)
+                return cfg.attention_head_dim * wq * wk / math.sqrt(cfg.attention_head_dim) * 1.4427 * 1.01 <= 64.0
+            blk["bounded"] = _bounded(("norm_q", "norm_added_q"), ("norm_k", "norm_added_k"))
+            blk["bounded2"] = dual and _bounded(("norm_q2",), ("norm_k2",))
             self.blocks.append(blk)
         self.out_mod = col
         mod_w.append(sd["norm_out.linear.weight"]); mod_b.append(sd["norm_out.linear.bias"])
@@ -407,7 +418,7 @@ class B200SD3Transformer2DModel(torch.nn.Module):
             G(pl.xn, blk["qkv_w"], pl.qkv, bias=blk["qkv_b"], epi=ops.EPI_QK_RMSNORM,
               rms_wq=blk["norm_q"], rms_wk=blk["norm_k"], rms_q_cols=D, rms_k_cols=D)
             main.wait_event(ev_side)
-            ops.attn_varlen(pl.src_img, pl.src_ctx, *pl.joint_plan, scale)
+            ops.attn_varlen(pl.src_img, pl.src_ctx, *pl.joint_plan, scale, bounded=blk["bounded"])
             ev_main.record(main)
             if not last:
                 with torch.cuda.stream(side):
@@ -424,7 +435,7 @@ class B200SD3Transformer2DModel(torch.nn.Module):
             if dual:
                 G(pl.xn2, blk["qkv2_w"], pl.qkv, bias=blk["qkv2_b"], epi=ops.EPI_QK_RMSNORM,
                   rms_wq=blk["norm_q2"], rms_wk=blk["norm_k2"], rms_q_cols=D, rms_k_cols=D)
-                ops.attn_varlen(pl.src_img, None, *pl.self_plan, scale)
+                ops.attn_varlen(pl.src_img, None, *pl.self_plan, scale, bounded=blk["bounded2"])
                 G(pl.att, blk["out2_w"], pl.x, bias=blk["out2_b"], epi=ops.EPI_GATE_RESID,
                   resid=pl.x, gate=mod[:, m + 8 * D:m + 9 * D], row_group=pl.row_group)
             ops.layernorm_mod(pl.x, pl.xn, eps=1e-6, mod=mod, row_group=pl.row_group,
@@ -495,7 +506,7 @@ class B200SD3Transformer2DModel(torch.nn.Module):
             G(pl.xn, blk["qkv_w"], cb.qkv[i], bias=blk["qkv_b"], epi=ops.EPI_QK_RMSNORM,
               rms_wq=blk["norm_q"], rms_wk=blk["norm_k"], rms_q_cols=D, rms_k_cols=D, row_mask=mk)
             main.wait_event(ev_side)
-            ops.attn_varlen(cb.src[i], pl.src_ctx, *pl.joint_plan, scale, q_mask=mk)
+            ops.attn_varlen(cb.src[i], pl.src_ctx, *pl.joint_plan, scale, q_mask=mk, bounded=blk["bounded"])
             ev_main.record(main)
             if not last:
                 with torch.cuda.stream(side):
@@ -512,7 +523,7 @@ class B200SD3Transformer2DModel(torch.nn.Module):
             if dual:
                 G(pl.xn2, blk["qkv2_w"], cb.qkv2[i], bias=blk["qkv2_b"], epi=ops.EPI_QK_RMSNORM,
                   rms_wq=blk["norm_q2"], rms_wk=blk["norm_k2"], rms_q_cols=D, rms_k_cols=D, row_mask=mk)
-                ops.attn_varlen(cb.src2[i], None, *pl.self_plan, scale, q_mask=mk)
+                ops.attn_varlen(cb.src2[i], None, *pl.self_plan, scale, q_mask=mk, bounded=blk["bounded2"])
                 G(pl.att, blk["out2_w"], pl.xa, bias=blk["out2_b"], epi=ops.EPI_GATE_RESID,
                   resid=pl.xa, gate=mod[:, m + 8 * D:m + 9 * D], row_group=pl.row_group, row_mask=mk)
             ops.layernorm_mod(pl.xa, pl.xn, eps=1e-6, mod=mod, row_group=pl.row_group,

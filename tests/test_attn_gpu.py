@@ -191,3 +191,49 @@ def test_cross_short_keys(cuda, T):
                 rows[ra + t0:ra + min(t0 + 128, s)] = True
         ra += s
     assert torch.equal(m[rows][:, 64:], out[rows][:, 64:]) and (m[~rows] == 7.0).all()
+
+
+def test_joint_bounded_logits_matches_the_running_max_path(cuda):
+    """B200AttnExtra.bounded_logits (SD3.5: q, k RMS-normalised, |logit * scale * log2 e| <= 64): the
+    softmax without a reference maximum gives the same attention -- against fp32 and against the default
+    instantiation on the same inputs, with rows whose logits are all far below zero (no maximum to
+    subtract: their P values are tiny, their normalised output must still be exact to bf16)."""
+    from sduss_b200 import ops
+    C = H * 64
+    img_lens, ctx = (1024, 2304, 333), 77
+    g = torch.Generator().manual_seed(5)
+
+    def unit(n, cols):  # rows of norm 8 per head, like an RMS-normalised head
+        t = torch.randn(n, cols // 64, 64, generator=g)
+        return (t / t.norm(dim=-1, keepdim=True) * 8).reshape(n, cols)
+    def pack(n):
+        q, k = unit(n, C) * 1.5, unit(n, C) * 1.5           # |logit| * 0.125 * 1.4427 <= 26
+        return torch.cat([q, k, torch.randn(n, C, generator=g)], 1)
+    qkv_a, qkv_b = pack(sum(img_lens)), pack(len(img_lens) * ctx)
+    qkv_a[:64, :C] = -qkv_a[100:101, C:2 * C] * 1.0         # queries anti-aligned with one key: very negative row maxima elsewhere
+    qkv_a, qkv_b = qkv_a.cuda().bfloat16(), qkv_b.cuda().bfloat16()
+    seqs, ra = [], 0
+    for i, s in enumerate(img_lens):
+        seqs.append((ra, s, i * ctx, ctx, ra, s, i * ctx, ctx))
+        ra += s
+    plan = ops.build_attn_plan(seqs, cuda, H)
+    outs = {}
+    for bounded in (False, True):
+        oa = torch.zeros(qkv_a.shape[0], C, device=cuda, dtype=torch.bfloat16)
+        ob = torch.zeros(qkv_b.shape[0], C, device=cuda, dtype=torch.bfloat16)
+        sa = ops.attn_source(q=qkv_a, q_col=0, k=qkv_a, k_col=C, v=qkv_a, v_col=2 * C, out=oa)
+        sb = ops.attn_source(q=qkv_b, q_col=0, k=qkv_b, k_col=C, v=qkv_b, v_col=2 * C, out=ob)
+        ops.attn_varlen(sa, sb, *plan, 0.125, bounded=bounded)
+        torch.cuda.synchronize()
+        outs[bounded] = (oa, ob)
+    ra = 0
+    for i, s in enumerate(img_lens):
+        x = torch.cat([qkv_a[ra:ra + s], qkv_b[i * ctx:(i + 1) * ctx]], 0).view(s + ctx, 3, H, 64)
+        ref = _ref(x[:, 0], x[:, 1], x[:, 2], 0.125).reshape(-1, C)
+        for bounded in (False, True):
+            _check(outs[bounded][0][ra:ra + s], ref[:s])
+            _check(outs[bounded][1][i * ctx:(i + 1) * ctx], ref[s:])
+        ra += s
+    assert torch.isfinite(outs[True][0].float()).all() and torch.isfinite(outs[True][1].float()).all()
+    d = (outs[True][0].float() - outs[False][0].float()).abs().max().item()
+    assert d < 2e-2, d
