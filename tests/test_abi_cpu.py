@@ -27,7 +27,8 @@ def test_ctypes_signatures_cover_header():
     from sduss_b200 import _lib
     declared = set(_header_functions())
     bound = set(_lib.SIGNATURES) | {"b200_groupnorm_workspace_bytes", "b200_patch_mask_workspace_bytes",
-                                    "b200_attn_workspace_bytes", "b200_conv3x3_maps_bytes"}
+                                    "b200_attn_workspace_bytes", "b200_conv3x3_maps_bytes",
+                                    "b200_attn_cross_short_max_keys"}
     assert declared == bound, declared ^ bound
 
 
@@ -38,7 +39,10 @@ def test_struct_layouts_match_header():
     assert _lib.EpilogueDesc.ln_rowpart.offset == 160 and _lib.EpilogueDesc.rowpart_out.offset == 176
     assert _lib.EpilogueDesc.ln_stats.offset == 144
     assert _lib.EpilogueDesc.stats_out.offset == 136
-    assert _lib.EpilogueDesc.row_mask.offset == 120 and ctypes.sizeof(_lib.AttnExtra) == 32
+    assert _lib.EpilogueDesc.row_mask.offset == 120 and _lib.EpilogueDesc.row_mask_scale.offset == 188
+    # B200AttnExtra: 2 i32, ptr, 2 i32, ptr, i32 (+ pad)
+    assert ctypes.sizeof(_lib.AttnExtra) == 40 and _lib.AttnExtra.q_mask.offset == 24
+    assert _lib.AttnExtra.bounded_logits.offset == 32
     assert _lib.EpilogueDesc.row_group.offset == 56 and _lib.EpilogueDesc.rms_eps.offset == 104
     assert ctypes.sizeof(_lib.AttnSource) == 80
     assert _lib.AttnSource.k.offset == 24 and _lib.AttnSource.out.offset == 64
