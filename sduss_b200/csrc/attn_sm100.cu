@@ -159,7 +159,9 @@ __device__ __forceinline__ AttnUnit load_unit(const AttnArgs& a, int u) {
   return w;
 }
 
-#if ATT_POLY_MOD > 0
+#ifndef ATT_POLY_BOUNDED
+#define ATT_POLY_BOUNDED 5  // the same for the BOUNDED instantiations, where it pays (below); 0 = off
+#endif
 // exp2 of a pair on the FMA + ALU pipes instead of MUFU (the kernel's bound, see the header):
 // Cody-Waite split x = n + r with the 1.5 * 2^23 magic add (n lands in the low mantissa bits of t),
 // packed degree-2/3 minimax of 2^r on [-0.5, 0.5] (relative error 1.7e-3 / 7.5e-5: below the bf16
@@ -179,7 +181,6 @@ __device__ __forceinline__ float2 poly_exp2_pair(float2 x) {
   float2 p = __ffma2_rn(make_float2(0.0551716677f, 0.0551716677f), r, make_float2(0.242611122f, 0.242611122f));
   p = __ffma2_rn(p, r, make_float2(0.693260986f, 0.693260986f));
   p = __ffma2_rn(p, r, make_float2(0.999928074f, 0.999928074f));
-#endif
   float2 out;
   out.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
   out.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
@@ -530,9 +531,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQA, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < ATT_BN / 2; ++i) {
           const float2 x = __ffma2_rn(s2[i], sc2, nm2);
-#if ATT_POLY_MOD > 0
-          if (i % ATT_POLY_MOD == 0) { s2[i] = poly_exp2_pair(x); continue; }
-#endif
+          // With the running maximum the softmax warps are bound by their dependent chain and freeing MUFU
+          // slots buys nothing (+0.5 %); without it (BOUNDED) the chain is 11 % shorter, the
+          // MUFU pipe is the tighter bound again and every 5th pair on the FMA pipe gives 766 -> 820 TFLOP/s
+          // (every 6th 809, 4th 788-791, 3rd 786, 2nd 732: profiles/r02_attn_variants.txt).
+          constexpr int kPoly = BOUNDED ? ATT_POLY_BOUNDED : ATT_POLY_MOD;
+          if (kPoly > 0 && i % (kPoly > 0 ? kPoly : 1) == 0) { s2[i] = poly_exp2_pair(x); continue; }
           s2[i] = make_float2(fast_exp2(x.x), fast_exp2(x.y));
         }
         float2 acc2[4];
