@@ -15,6 +15,7 @@ with halos, each UNet level keeps ONE packed channels-last buffer [sum_i h_i*w_i
 """
 import os
 from dataclasses import dataclass
+from types import SimpleNamespace
 from typing import Dict, Optional, Tuple
 
 import numpy as np
@@ -206,7 +207,7 @@ class _UNetPatchCache:
                 pat = np.repeat(np.arange(lay.L, dtype=np.int32), [r // self.PATCH for r in lay.rows])
                 self.level_tabs[level] = (torch.from_numpy(pat).to(self.device),
                                           ops.patch_mask_workspace(n, self.device))
-            st = _G_ns()
+            st = SimpleNamespace()
             st.n = n
             st.patch_latent, st.ws = self.level_tabs[level]
             st.skipped = torch.zeros((n,), device=self.device, dtype=torch.int32)
@@ -222,9 +223,6 @@ class _UNetPatchCache:
     def bytes(self):
         return sum(t.numel() * t.element_size() for t in self.bufs.values())
 
-
-class _G_ns:
-    pass
 
 
 class B200UNet(torch.nn.Module):
