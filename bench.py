@@ -407,7 +407,9 @@ def measure_model(model, args, rank, world, dev, dist):
                 "peak_source": pk_src + ", sustained bf16", "kernel_ms_per_step": gemm_ms,
                 "algorithmic_tflop_per_step": gemm_fl / 1e12,
                 "conv": {"ms_per_step": per_kernel.get("b200_conv3x3_bf16", 0.0), "tflop_per_step": conv_fl / 1e12},
-                "attn": {"ms_per_step": attn_ms}}
+                "attn": {"ms_per_step": attn_ms + per_kernel.get("b200_attn_cross_short_bf16", 0.0),
+                         "self_ms_per_step": attn_ms,
+                         "cross_ms_per_step": per_kernel.get("b200_attn_cross_short_bf16", 0.0)}}
     rec = {"metric": METRIC[model], "value": world * 1000.0 / ms_step, "unit": "denoise steps/s",
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
